@@ -1,0 +1,154 @@
+/*
+ * lcs_b200.h -- C ABI of the B200-native FTLE engine (liblcs_b200.so, sm_100a only).
+ *
+ * The reference (gabrielmpp/LagrangianCoherence) has no FFI layer: its hot path is three
+ * Python callables whose arithmetic lives in scipy.ndimage.map_coordinates, a numba stencil
+ * and scipy.linalg.norm.  Each entry point below names the reference code it replaces
+ * (paths relative to the reference checkout).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer marked "device" is a CUDA device pointer owned by the caller; the library
+ *     never allocates device memory (workspaces are sized by lcs_*_workspace_bytes);
+ *   - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it and are
+ *     thread-safe for distinct streams;
+ *   - return value: 0 on success, a negative LCS_E_* code otherwise; lcs_last_error() returns
+ *     a thread-local message;
+ *   - grids are ascending and row-major [lat][lon]; wind series are [level][lat][lon].
+ */
+#ifndef LCS_B200_H_
+#define LCS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LCS_ABI_VERSION 1
+
+enum { LCS_OK = 0, LCS_E_INVALID = -1, LCS_E_CUDA = -2, LCS_E_WORKSPACE = -3, LCS_E_UNSUPPORTED = -4 };
+enum { LCS_F64 = 0, LCS_F32 = 1 };
+/* x-boundary of the integrator: trajectory.py:92-97 / 118-123 */
+enum { LCS_X_CYCLIC = 0,          /* cyclic_xboundary=True: the two `where` with Python-sign % 180 */
+       LCS_X_CLAMP_POINTWISE = 1, /* per-particle clamp to [lon_min, lon_max] */
+       LCS_X_CLAMP_OUTER = 2 };   /* as executed: xarray orthogonal assignment (rows x cols having any exit) */
+
+/* Wind grid; min/max are coord.min()/coord.max() used by the index map of tools.py:19-22. */
+typedef struct lcs_grid {
+    int32_t nlat, nlon;
+    double lat_min, lat_max, lon_min, lon_max;
+} lcs_grid;
+
+/* Particle set = a band of rows of the arrival grid (the reference seeds one particle per
+ * wind grid point, trajectory.py:68-70; a finer particle grid is an extension).
+ * kx/hx carry timestep*conversion_x(row) and 0.5*timestep*conversion_x(row) evaluated by the
+ * host exactly as trajectory.py:56,87,112 does, so the device reproduces numpy's rounding. */
+typedef struct lcs_particles {
+    int32_t nrow, ncol;          /* rows held by this call (band incl. halo), columns          */
+    int32_t row0, nrow_global;   /* global index of the first row, global row count: the
+                                    order-1 "pole row" rule of tools.py:31-39 uses global rows */
+    const double* lat;           /* device [nrow]  start latitude of each row                   */
+    const double* lon;           /* device [ncol]  start longitude of each column               */
+    const double* kx;            /* device [nrow]  timestep * conversion_x(row)                 */
+    const double* hx;            /* device [nrow]  0.5 * timestep * conversion_x(row)           */
+    double ky, hy;               /* timestep * conversion_y ; 0.5 * timestep * conversion_y     */
+} lcs_particles;
+
+typedef struct lcs_advect_opts {
+    int32_t nsteps;         /* wind intervals to cross = nt-1 (trajectory.py:80)                 */
+    int32_t settls_order;   /* accumulating sub-iterations per interval (trajectory.py:100)      */
+    int32_t interp_order;   /* 1 or 3 (tools.py:11 `order`)                                       */
+    int32_t xmode;          /* LCS_X_*                                                            */
+    int32_t pair_dtype;     /* LCS_F64 or LCS_F32: storage of the packed wind/coefficient pairs   */
+    int32_t strict;         /* 1: accumulate taps as scipy does ((c*wy)*wx, no fused multiply-add) */
+    int32_t nwindows;       /* independent start times integrated by this call (rolling series)  */
+    int32_t level0, level_stride; /* window b starts at packed pair index level0 + b*level_stride  */
+} lcs_advect_opts;
+
+/* ---------------------------------------------------------------- housekeeping */
+int lcs_abi_version(void);
+const char* lcs_last_error(void);
+
+/* ---------------------------------------------------------------- wind staging
+ * lcs_prefilter: cubic B-spline coefficients of every level, mirror boundary, axis 0 then axis 1,
+ * f64 -- what scipy.ndimage.map_coordinates(order=3, mode='wrap') recomputes inside every call at
+ * tools.py:26-30; here it runs once per level.  u, v: device [nlev][nlat][nlon] of `in_dtype`;
+ * coef_u, coef_v: device f64 planes of the same shape (may not alias the inputs). */
+int lcs_prefilter(const void* u, const void* v, int in_dtype, double* coef_u, double* coef_v,
+                  int nlev, int nlat, int nlon, void* stream);
+
+/* lcs_pack_pairs: interleave two planar series into the gather layout
+ * pairs[k][lat][lon] = (u_k, v_k, u_{k+1}, v_{k+1}), k = 0..nlev-2, one 32-byte (f64) or 16-byte
+ * (f32) element per grid point, so that one vector load feeds all four operands of a SETTLS
+ * sub-iteration (trajectory.py:105-108).  Pure data movement, no reference counterpart. */
+int lcs_pack_pairs(const void* u, const void* v, int in_dtype, void* pairs, int pair_dtype,
+                   int nlev, int nlat, int nlon, void* stream);
+
+/* ---------------------------------------------------------------- integrator
+ * lcs_advect replaces parcel_propagation's loop, trajectory.py:80-126, together with the
+ * xr_map_coordinates calls inside it (tools.py:11-41).
+ *   raw_pairs : packed raw winds (always needed: order-1 pole rows, or interp_order == 1)
+ *   coef_pairs: packed cubic coefficients (interp_order == 3), else NULL
+ *   x_out,y_out: device f64 [nwindows][nrow][ncol] final positions
+ *   x_traj,y_traj: NULL, or device f64 [nwindows][nsteps+1][nrow][ncol] (level 0 = start grid,
+ *                  trajectory.py:76-77,125-126)
+ *   workspace : device scratch of lcs_advect_workspace_bytes() bytes (only LCS_X_CLAMP_OUTER
+ *               needs any: positions, Euler samples and per-sub-step row/column exit flags) */
+size_t lcs_advect_workspace_bytes(const lcs_particles* p, const lcs_advect_opts* o);
+int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_advect_opts* o,
+               const void* raw_pairs, const void* coef_pairs,
+               double* x_out, double* y_out, double* x_traj, double* y_traj,
+               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------- fused epilogue
+ * lcs_ftle_epilogue replaces flowmap_gradient (LCS.py:171-225), the six
+ * derivative_spherical_coords/fourth_order_derivative calls (tools.py:190-267) and the batched
+ * spectral norm of LCS.py:145-157 with one kernel.
+ *   x_dep,y_dep: device f64 [nfields][nrow_in][nlon]; rows cover global rows
+ *                [in_row0, in_row0+nrow_in) and must include the +-2 halo of the output band
+ *   out_row0,nrow_out: global rows written;  sigma: device f64 [nfields][nrow_out][nlon]
+ *   jac: NULL or device f64 [nfields][6][nrow_out][nlon] = dXdx,dXdy,dYdx,dYdy,dZdx,dZdy
+ *   dx: device [nlat_global] metric spacing per global row, dy scalar (tools.py:255-256)
+ *   mask: NULL or device u8 [nrow_out][nlon] (subdomain crop, LCS.py:143-144): 0 => NaN
+ *   log_scale: 0 => sigma_max (what LCS.__call__ returns); 1 => 0.5*log(sigma_max), the scaling
+ *              the reference's callers apply (examples/ideal_vortex.py:282)
+ *   status: NULL or device int32[1], OR-ed with 1 if any derivative is +-inf (the reference's
+ *           scipy.linalg.norm raises ValueError there, LCS.py:154) */
+int lcs_ftle_epilogue(const double* x_dep, const double* y_dep, int nfields,
+                      int nlat_global, int nlon, int in_row0, int nrow_in,
+                      int out_row0, int nrow_out, const double* dx, double dy,
+                      const uint8_t* mask, int log_scale,
+                      double* sigma, double* jac, int32_t* status, void* stream);
+
+/* ---------------------------------------------------------------- array-level seams
+ * The three third-party kernels the reference calls, as stand-alone device operations. */
+
+/* xr_map_coordinates body (tools.py:19-41) for one field: positions in degrees,
+ * [nrow][ncol]; rows < order or >= nrow_global-order (global row index) take the
+ * order-1/'constant' branch.  field: device f64 [nlat][nlon] raw values; coef: its cubic
+ * coefficients (order 3) or NULL; out: device f64 [nrow][ncol]. */
+int lcs_map_coordinates(const lcs_grid* g, const double* field, const double* coef, int order,
+                        const double* pos_x, const double* pos_y, int nrow, int ncol,
+                        int row0, int nrow_global, double* out, void* stream);
+
+/* fourth_order_derivative (tools.py:190-245) on an f32 array [n0][n1], dim 0 or 1. */
+int lcs_fourth_order_derivative(const float* arr, int n0, int n1, int dim, int isglobal,
+                                float* out, void* stream);
+
+/* scipy.linalg.norm(vals[3,3,N], axis=(0,1), ord=2) of LCS.py:154 for the layout the reference
+ * feeds it: vals = nine stacked planes of N points (plane k = entry k of the row-major 3x3). */
+int lcs_spectral_norm_3x3(const double* vals, int64_t n, double* out, void* stream);
+
+/* ---------------------------------------------------------------- roofline microbenchmark
+ * Same 16-tap x 32-byte (or 4-tap) gather pattern as the integrator on packed pairs, no
+ * dependent arithmetic: the measured upper bound for the L1/L2 gather roofline.
+ * jitter: displacement amplitude in grid cells applied to the start grid (smooth field). */
+int lcs_gather_peak(const void* pairs, int pair_dtype, int nlat, int nlon, int nrow, int ncol,
+                    int nwindows, int taps, double jitter, int iters, double* sink, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCS_B200_H_ */

@@ -1,0 +1,86 @@
+"""ctypes binding of liblcs_b200.so (the C ABI declared in include/lcs_b200.h).
+
+There is no CPU fallback: if the shared object is missing this module raises at first use.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'liblcs_b200.so')
+
+LCS_F64, LCS_F32 = 0, 1
+LCS_X_CYCLIC, LCS_X_CLAMP_POINTWISE, LCS_X_CLAMP_OUTER = 0, 1, 2
+ABI_VERSION = 1
+
+c_void_p, c_int, c_double, c_size_t, c_int64 = C.c_void_p, C.c_int, C.c_double, C.c_size_t, C.c_int64
+
+
+class Grid(C.Structure):
+    _fields_ = [('nlat', C.c_int32), ('nlon', C.c_int32),
+                ('lat_min', c_double), ('lat_max', c_double), ('lon_min', c_double), ('lon_max', c_double)]
+
+
+class Particles(C.Structure):
+    _fields_ = [('nrow', C.c_int32), ('ncol', C.c_int32), ('row0', C.c_int32), ('nrow_global', C.c_int32),
+                ('lat', c_void_p), ('lon', c_void_p), ('kx', c_void_p), ('hx', c_void_p),
+                ('ky', c_double), ('hy', c_double)]
+
+
+class AdvectOpts(C.Structure):
+    _fields_ = [('nsteps', C.c_int32), ('settls_order', C.c_int32), ('interp_order', C.c_int32),
+                ('xmode', C.c_int32), ('pair_dtype', C.c_int32), ('strict', C.c_int32),
+                ('nwindows', C.c_int32), ('level0', C.c_int32), ('level_stride', C.c_int32)]
+
+
+# name -> (restype, argtypes): every symbol include/lcs_b200.h declares
+SIGNATURES = {
+    'lcs_abi_version': (c_int, []),
+    'lcs_last_error': (C.c_char_p, []),
+    'lcs_prefilter': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'lcs_pack_pairs': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'lcs_advect_workspace_bytes': (c_size_t, [C.POINTER(Particles), C.POINTER(AdvectOpts)]),
+    'lcs_advect': (c_int, [C.POINTER(Grid), C.POINTER(Particles), C.POINTER(AdvectOpts), c_void_p, c_void_p,
+                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    'lcs_ftle_epilogue': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                  c_void_p, c_double, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'lcs_map_coordinates': (c_int, [C.POINTER(Grid), c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int,
+                                    c_int, c_int, c_void_p, c_void_p]),
+    'lcs_fourth_order_derivative': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    'lcs_spectral_norm_3x3': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
+    'lcs_gather_peak': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int,
+                                c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+class LcsError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the library once; raise loudly when it is absent (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LcsError(
+            f'{LIB_PATH} is missing: build it with `python -m lagrangiancoherence_b200.build` '
+            '(nvcc, sm_100a). lagrangiancoherence_b200 has no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if lib.lcs_abi_version() != ABI_VERSION:
+        raise LcsError(f'liblcs_b200.so ABI {lib.lcs_abi_version()} != binding {ABI_VERSION}: rebuild')
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().lcs_last_error().decode(errors='replace')
+        raise LcsError(f'{what} failed with status {status}: {msg}')

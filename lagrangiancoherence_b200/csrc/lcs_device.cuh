@@ -1,0 +1,222 @@
+// Device-side building blocks shared by the integrator, the seams and the microbenchmark.
+//
+// Everything here restates the *published* algorithm of scipy.ndimage.map_coordinates
+// (scipy 1.18.1; the third-party call behind tools.py:26-30,35-39 of the reference) in the
+// order scipy evaluates it.  `oracle/lcs_oracle.py` holds the same restatement in numpy and is
+// checked bit-for-bit against scipy on the CPU (tests/test_oracle_scipy_spec.py).
+//
+// STRICT=true  : every product/sum is a separate IEEE operation in scipy's order
+//                ((c*wy)*wx accumulated sequentially, true division by 6).
+// STRICT=false : same tap order, but weights are pre-multiplied and accumulated with FMA and
+//                the /6 becomes *(1/6).  Differences are O(1 ulp) per sample.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lcs {
+
+// ------------------------------------------------------------------ packed pair types
+struct __align__(32) d4 { double x, y, z, w; };   // (u_k, v_k, u_{k+1}, v_{k+1}) f64: one 32-B sector
+struct __align__(16) d2 { double x, y; };
+
+template <typename T> struct PairOf;
+template <> struct PairOf<double> {
+    using type = d4;
+    // 256-bit read-only load (LDG.E.256.CONSTANT on sm_100a): all four SETTLS operands of a tap.
+    static __device__ __forceinline__ void load4(const type* p, double (&o)[4]) {
+        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+            : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
+    }
+    // first half only (u_k, v_k): the Euler stage samples a single level (trajectory.py:82-84)
+    static __device__ __forceinline__ void load2(const type* p, double (&o)[2]) {
+        asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "l"(p));
+    }
+};
+template <> struct PairOf<float> {
+    using type = float4;
+    static __device__ __forceinline__ void load4(const type* p, double (&o)[4]) {
+        float4 t = __ldg(p);
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    }
+    static __device__ __forceinline__ void load2(const type* p, double (&o)[2]) {
+        float2 t = __ldg(reinterpret_cast<const float2*>(p));
+        o[0] = t.x; o[1] = t.y;
+    }
+};
+
+template <typename T, int NV> struct Loader;
+template <typename T> struct Loader<T, 4> {
+    static __device__ __forceinline__ void ld(const typename PairOf<T>::type* p, double (&o)[4]) { PairOf<T>::load4(p, o); }
+};
+template <typename T> struct Loader<T, 2> {
+    static __device__ __forceinline__ void ld(const typename PairOf<T>::type* p, double (&o)[2]) { PairOf<T>::load2(p, o); }
+};
+
+// ------------------------------------------------------------------ index arithmetic
+// tools.py:21-22: n * (pos - cmin) / (cmax - cmin)   (n points, not n-1: quirk Q4)
+__device__ __forceinline__ double index_map(double pos, double cmin, double span, double n) {
+    return __ddiv_rn(__dmul_rn(n, __dsub_rn(pos, cmin)), span);
+}
+
+// scipy mode='wrap' coordinate fold: period n-1, result in [0, n-1]
+__device__ __forceinline__ double fold_wrap(double c, int n) {
+    const long long sz = n - 1;
+    if (c < 0.0) {
+        c += (double)(sz * ((long long)(__ddiv_rn(-c, (double)sz)) + 1));
+    } else if (c > (double)(n - 1)) {
+        c -= (double)(sz * (long long)(__ddiv_rn(c, (double)sz)));
+    }
+    return c;
+}
+
+// scipy spline_mode mirror for out-of-range tap indices: d c b | a b c d | c b a
+__device__ __forceinline__ int mirror_idx(int i, int n) {
+    if (i < 0) {
+        const int sz2 = 2 * n - 2;
+        i = sz2 * (-i / sz2) + i;
+        i = (i <= 1 - n) ? i + sz2 : -i;
+    } else if (i > n - 1) {
+        const int sz2 = 2 * n - 2;
+        i -= sz2 * (i / sz2);
+        if (i >= n) i = sz2 - i;
+    }
+    return i;
+}
+
+template <bool STRICT>
+__device__ __forceinline__ void cubic_weights(double y, double (&w)[4]) {
+    const double z = __dsub_rn(1.0, y);
+    if (STRICT) {
+        w[1] = __ddiv_rn(__dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(y, y), __dsub_rn(y, 2.0)), 3.0), 4.0), 6.0);
+        w[2] = __ddiv_rn(__dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(z, z), __dsub_rn(z, 2.0)), 3.0), 4.0), 6.0);
+        w[0] = __ddiv_rn(__dmul_rn(__dmul_rn(z, z), z), 6.0);
+        w[3] = __dsub_rn(__dsub_rn(__dsub_rn(1.0, w[0]), w[1]), w[2]);
+    } else {
+        const double s = 1.0 / 6.0;
+        w[1] = (y * y * (y - 2.0) * 3.0 + 4.0) * s;
+        w[2] = (z * z * (z - 2.0) * 3.0 + 4.0) * s;
+        w[0] = z * z * z * s;
+        w[3] = 1.0 - w[0] - w[1] - w[2];
+    }
+}
+
+template <bool STRICT>
+__device__ __forceinline__ double tap_acc(double t, double c, double wy, double wx, double wyx) {
+    if (STRICT) return __dadd_rn(t, __dmul_rn(__dmul_rn(c, wy), wx));
+    return fma(c, wyx, t);
+}
+
+// ------------------------------------------------------------------ gathers
+// Cubic B-spline, mode='wrap' (fold period n-1, mirror taps), 4x4 taps in scipy's order
+// (axis-0 index outer, axis-1 inner).  NV = 2: level k only; NV = 4: levels k and k+1.
+template <typename T, bool STRICT, int NV>
+__device__ __forceinline__ void gather_cubic_wrap(const typename PairOf<T>::type* __restrict__ f,
+                                                  int nlat, int nlon, double iy, double ix,
+                                                  double (&out)[NV]) {
+    const double cy = fold_wrap(iy, nlat);
+    const double cx = fold_wrap(ix, nlon);
+    const double fy = floor(cy), fx = floor(cx);
+    double wy[4], wx[4];
+    cubic_weights<STRICT>(__dsub_rn(cy, fy), wy);
+    cubic_weights<STRICT>(__dsub_rn(cx, fx), wx);
+    const int sy = (int)fy - 1, sx = (int)fx - 1;
+    int col[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) col[j] = mirror_idx(sx + j, nlon);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) out[v] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const typename PairOf<T>::type* rowp = f + (size_t)mirror_idx(sy + i, nlat) * nlon;
+        double c[4][NV];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Loader<T, NV>::ld(rowp + col[j], c[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double wyx = wy[i] * wx[j];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) out[v] = tap_acc<STRICT>(out[v], c[j][v], wy[i], wx[j], wyx);
+        }
+    }
+}
+
+// Shared 2x2 tap sum of the order-1 branches (weights (1-y, 1-(1-y)), mirror taps).
+template <typename T, bool STRICT, int NV>
+__device__ __forceinline__ void bilinear_taps(const typename PairOf<T>::type* __restrict__ f,
+                                              int nlat, int nlon, double cy, double cx,
+                                              double (&out)[NV]) {
+    const double fy = floor(cy), fx = floor(cx);
+    const double y = __dsub_rn(cy, fy), x = __dsub_rn(cx, fx);
+    // scipy: weights[0] = 1 - x; weights[order] = 1 - sum(others)
+    const double wy0 = __dsub_rn(1.0, y), wx0 = __dsub_rn(1.0, x);
+    const double wy[2] = {wy0, __dsub_rn(1.0, wy0)};
+    const double wx[2] = {wx0, __dsub_rn(1.0, wx0)};
+    const int iy0 = (int)fy, ix0 = (int)fx;
+    const int col[2] = {mirror_idx(ix0, nlon), mirror_idx(ix0 + 1, nlon)};
+#pragma unroll
+    for (int v = 0; v < NV; ++v) out[v] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const typename PairOf<T>::type* rowp = f + (size_t)mirror_idx(iy0 + i, nlat) * nlon;
+        double c[2][NV];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) Loader<T, NV>::ld(rowp + col[j], c[j]);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double wyx = wy[i] * wx[j];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) out[v] = tap_acc<STRICT>(out[v], c[j][v], wy[i], wx[j], wyx);
+        }
+    }
+}
+
+// order=1, mode='wrap' (interior rows when interp_order == 1)
+template <typename T, bool STRICT, int NV>
+__device__ __forceinline__ void gather_linear_wrap(const typename PairOf<T>::type* __restrict__ f,
+                                                   int nlat, int nlon, double iy, double ix,
+                                                   double (&out)[NV]) {
+    bilinear_taps<T, STRICT, NV>(f, nlat, nlon, fold_wrap(iy, nlat), fold_wrap(ix, nlon), out);
+}
+
+// order=1, mode='constant', cval=0: coordinates outside [0, n-1] sample 0 (tools.py:35-39)
+template <typename T, bool STRICT, int NV>
+__device__ __forceinline__ void gather_linear_constant(const typename PairOf<T>::type* __restrict__ f,
+                                                       int nlat, int nlon, double iy, double ix,
+                                                       double (&out)[NV]) {
+    // written so that NaN coordinates also take the constant branch
+    if (!(iy >= 0.0 && iy <= (double)(nlat - 1) && ix >= 0.0 && ix <= (double)(nlon - 1))) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) out[v] = 0.0;
+        return;
+    }
+    bilinear_taps<T, STRICT, NV>(f, nlat, nlon, iy, ix, out);
+}
+
+// ------------------------------------------------------------------ boundaries (trajectory.py:89-97)
+__device__ __forceinline__ double clamp_y(double y, double ymin, double ymax) {
+    y = (y > ymin) ? y : ymin;      // .where(y > y_min, y_min): NaN -> y_min
+    y = (y < ymax) ? y : ymax;
+    return y;
+}
+
+// numpy float `%` (sign of the divisor)
+__device__ __forceinline__ double pymod(double a, double b) {
+    double r = fmod(a, b);
+    if (r != 0.0) { if ((b < 0.0) != (r < 0.0)) r = __dadd_rn(r, b); }
+    else r = copysign(0.0, b);
+    return r;
+}
+
+__device__ __forceinline__ double wrap_x_cyclic(double x) {
+    x = (x > -180.0) ? x : pymod(x, 180.0);                       // trajectory.py:93
+    x = (x < 180.0) ? x : __dadd_rn(-180.0, pymod(x, 180.0));     // trajectory.py:94
+    return x;
+}
+
+__device__ __forceinline__ double clamp_x_pointwise(double x, double xmin, double xmax) {
+    if (x < xmin) x = xmin;
+    if (x > xmax) x = xmax;
+    return x;
+}
+
+}  // namespace lcs

@@ -1,0 +1,160 @@
+// xr_map_coordinates as a stand-alone device operation (tools.py:19-41), the gather-roofline
+// microbenchmark, and the library's error plumbing.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include "lcs_internal.h"
+#include "lcs_device.cuh"
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local char g_err[512] = "";
+
+int lcs_fail(int code, const char* msg) {
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return code;
+}
+int lcs_fail_cuda(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof g_err, "%s: CUDA error %d (%s)", where, (int)e, cudaGetErrorString(e));
+    return LCS_E_CUDA;
+}
+int lcs_env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+extern "C" int lcs_abi_version(void) { return LCS_ABI_VERSION; }
+extern "C" const char* lcs_last_error(void) { return g_err; }
+
+namespace lcs {
+
+// planar f64 field viewed through the same gather templates (one value per tap)
+struct scalar64 {};
+template <> struct PairOf<scalar64> { using type = double; };
+template <> struct Loader<scalar64, 1> {
+    static __device__ __forceinline__ void ld(const double* p, double (&o)[1]) { o[0] = __ldg(p); }
+};
+
+struct MapParams {
+    const double* field;
+    const double* coef;
+    int nlat, nlon;
+    double nlat_d, nlon_d, lat_min, lat_span, lon_min, lon_span;
+    int order, nrow, ncol, row0, nrow_global;
+    const double* pos_x;
+    const double* pos_y;
+    double* out;
+};
+
+__global__ void __launch_bounds__(256)
+map_coordinates_kernel(const MapParams P) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)P.nrow * P.ncol) return;
+    const int row = (int)(idx / P.ncol);
+    const int grow = P.row0 + row;
+    const bool pole = (grow < P.order) || (grow >= P.nrow_global - P.order);      // tools.py:31-33
+    const double iy = index_map(P.pos_y[idx], P.lat_min, P.lat_span, P.nlat_d);   // tools.py:22
+    const double ix = index_map(P.pos_x[idx], P.lon_min, P.lon_span, P.nlon_d);   // tools.py:21
+    double o[1];
+    if (pole) gather_linear_constant<scalar64, true, 1>(P.field, P.nlat, P.nlon, iy, ix, o);
+    else if (P.order == 3) gather_cubic_wrap<scalar64, true, 1>(P.coef, P.nlat, P.nlon, iy, ix, o);
+    else gather_linear_wrap<scalar64, true, 1>(P.field, P.nlat, P.nlon, iy, ix, o);
+    P.out[idx] = o[0];
+}
+
+// ------------------------------------------------------------------ gather roofline microbenchmark
+// Same tap pattern as the integrator (TAPS x TAPS neighbourhood of packed pairs around a smoothly
+// displaced copy of the start grid), no index folding, no dependent position update: the loads of
+// all `iters` rounds are independent, so the measured rate is what L1/L2 can deliver for this
+// access pattern.  Bytes counted = particles * iters * TAPS^2 * sizeof(pair).
+template <typename T, int TAPS>
+__global__ void __launch_bounds__(256)
+gather_peak_kernel(const typename PairOf<T>::type* __restrict__ pairs, int nlat, int nlon,
+                   int nrow, int ncol, double jitter, int iters, int band, double* sink) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long np = (long long)nrow * ncol;
+    if (p >= np) return;
+    const int w = blockIdx.y;
+    // banded enumeration identical to the integrator's
+    const long long per_band = (long long)band * ncol;
+    const int nbands = (nrow + band - 1) / band;
+    int b = (int)(p / per_band);
+    if (b > nbands - 1) b = nbands - 1;
+    const long long q = p - (long long)b * per_band;
+    const int h = (b == nbands - 1) ? (nrow - b * band) : band;
+    const int col = (int)(q / h);
+    const int row = b * band + (int)(q - (long long)col * h);
+    const double sy = (double)(nlat - 1) / (double)(nrow > 1 ? nrow - 1 : 1);
+    const double sx = (double)(nlon - 1) / (double)(ncol > 1 ? ncol - 1 : 1);
+    double acc[4] = {0, 0, 0, 0};
+    for (int it = 0; it < iters; ++it) {
+        const double ph = 0.37 * (it + 1) + 0.11 * w;
+        const double fy = row * sy + jitter * sin(0.05 * col + ph);
+        const double fx = col * sx + jitter * cos(0.05 * row - ph);
+        int iy = (int)floor(fy) - (TAPS / 2 - 1), ix = (int)floor(fx) - (TAPS / 2 - 1);
+        iy = max(0, min(iy, nlat - TAPS));
+        ix = max(0, min(ix, nlon - TAPS));
+        const typename PairOf<T>::type* base = pairs + (size_t)iy * nlon + ix;
+#pragma unroll
+        for (int i = 0; i < TAPS; ++i) {
+            double c[TAPS][4];
+#pragma unroll
+            for (int j = 0; j < TAPS; ++j) Loader<T, 4>::ld(base + (size_t)i * nlon + j, c[j]);
+#pragma unroll
+            for (int j = 0; j < TAPS; ++j) {
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[v] += c[j][v];
+            }
+        }
+    }
+    const double s = acc[0] + acc[1] + acc[2] + acc[3];
+    if (s == 1.2345e308) sink[0] = s;                     // keeps the loads alive, never true
+}
+
+}  // namespace lcs
+
+using namespace lcs;
+
+extern "C" int lcs_map_coordinates(const lcs_grid* g, const double* field, const double* coef, int order,
+                                   const double* pos_x, const double* pos_y, int nrow, int ncol,
+                                   int row0, int nrow_global, double* out, void* stream) {
+    if (!g || !field || !pos_x || !pos_y || !out) return lcs_fail(LCS_E_INVALID, "lcs_map_coordinates: null argument");
+    if (order != 1 && order != 3) return lcs_fail(LCS_E_UNSUPPORTED, "lcs_map_coordinates: order must be 1 or 3");
+    if (order == 3 && !coef) return lcs_fail(LCS_E_INVALID, "lcs_map_coordinates: coef required for order 3");
+    if (g->nlat < 4 || g->nlon < 4 || nrow < 1 || ncol < 1) return lcs_fail(LCS_E_INVALID, "lcs_map_coordinates: bad sizes");
+    MapParams P{};
+    P.field = field; P.coef = coef; P.nlat = g->nlat; P.nlon = g->nlon;
+    P.nlat_d = (double)g->nlat; P.nlon_d = (double)g->nlon;
+    P.lat_min = g->lat_min; P.lat_span = g->lat_max - g->lat_min;
+    P.lon_min = g->lon_min; P.lon_span = g->lon_max - g->lon_min;
+    P.order = order; P.nrow = nrow; P.ncol = ncol; P.row0 = row0; P.nrow_global = nrow_global;
+    P.pos_x = pos_x; P.pos_y = pos_y; P.out = out;
+    const long long n = (long long)nrow * ncol;
+    map_coordinates_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(P);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_map_coordinates");
+    return LCS_OK;
+}
+
+extern "C" int lcs_gather_peak(const void* pairs, int pair_dtype, int nlat, int nlon, int nrow, int ncol,
+                               int nwindows, int taps, double jitter, int iters, double* sink, void* stream) {
+    if (!pairs || !sink) return lcs_fail(LCS_E_INVALID, "lcs_gather_peak: null argument");
+    if (nlat < 4 || nlon < 4 || nrow < 1 || ncol < 1 || nwindows < 1 || iters < 1)
+        return lcs_fail(LCS_E_INVALID, "lcs_gather_peak: bad sizes");
+    const long long np = (long long)nrow * ncol;
+    const dim3 grid((unsigned)((np + 255) / 256), (unsigned)nwindows);
+    int band = lcs_env_int("LCS_ADVECT_BAND", 4);
+    if (band < 1) band = 1;
+    if (band > 32) band = 32;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pair_dtype == LCS_F64 && taps == 4)
+        gather_peak_kernel<double, 4><<<grid, 256, 0, st>>>((const d4*)pairs, nlat, nlon, nrow, ncol, jitter, iters, band, sink);
+    else if (pair_dtype == LCS_F64 && taps == 2)
+        gather_peak_kernel<double, 2><<<grid, 256, 0, st>>>((const d4*)pairs, nlat, nlon, nrow, ncol, jitter, iters, band, sink);
+    else if (pair_dtype == LCS_F32 && taps == 4)
+        gather_peak_kernel<float, 4><<<grid, 256, 0, st>>>((const float4*)pairs, nlat, nlon, nrow, ncol, jitter, iters, band, sink);
+    else if (pair_dtype == LCS_F32 && taps == 2)
+        gather_peak_kernel<float, 2><<<grid, 256, 0, st>>>((const float4*)pairs, nlat, nlon, nrow, ncol, jitter, iters, band, sink);
+    else return lcs_fail(LCS_E_INVALID, "lcs_gather_peak: taps must be 2 or 4");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_gather_peak");
+    return LCS_OK;
+}

@@ -1,0 +1,283 @@
+"""Device-level FTLE engine: torch tensors for memory/streams, liblcs_b200.so for every kernel.
+
+This is the layer between the reference-shaped Python API (``LCS``, ``parcel_propagation``,
+``flowmap_gradient``) and the C ABI of ``include/lcs_b200.h``.  Host-side scalars and per-row
+factors are evaluated with numpy in the reference's order of operations
+(trajectory.py:54-57,86-87,110-112; tools.py:253-256) so that the device reproduces numpy's
+rounding; everything per-particle or per-grid-point runs in the CUDA kernels.
+
+No CPU fallback: a missing shared object or a non-CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+EARTH_R = 6371000          # trajectory.py:54
+XMODES = {'cyclic': _lib.LCS_X_CYCLIC, 'pointwise': _lib.LCS_X_CLAMP_POINTWISE, 'outer': _lib.LCS_X_CLAMP_OUTER}
+DTYPES = {'f64': _lib.LCS_F64, 'f32': _lib.LCS_F32}
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float64:
+        return _lib.LCS_F64
+    if t.dtype == torch.float32:
+        return _lib.LCS_F32
+    raise TypeError(f'winds must be float32 or float64, got {t.dtype}')
+
+
+@dataclass
+class StagedWinds:
+    """Packed gather layouts of a wind series on the device (see lcs_pack_pairs)."""
+    raw_pairs: torch.Tensor            # [nlev-1, nlat, nlon, 4]
+    coef_pairs: torch.Tensor | None    # same, cubic B-spline coefficients (interp_order == 3)
+    nlev: int
+
+
+class FtleEngine:
+    """One wind grid + one integration recipe; reusable across calls (buffers are cached).
+
+    Parameters mirror the reference: ``timestep`` [s, sign = direction], ``SETTLS_order``,
+    ``interp_order`` (= ``traj_interp_order``), and the x-boundary: ``'cyclic'``
+    (cyclic_xboundary=True), ``'outer'`` (as-executed non-cyclic clamp, quirk Q6) or
+    ``'pointwise'``.  ``pair_dtype`` selects the storage of the packed winds: ``'f64'`` (parity
+    path) or ``'f32'`` (fast path); positions and the epilogue stay f64 either way.
+    ``part_lat``/``part_lon`` seed a particle grid different from the wind grid (extension, C5).
+    """
+
+    def __init__(self, lat, lon, timestep, SETTLS_order=0, interp_order=3, xmode='outer',
+                 pair_dtype='f64', strict=False, device='cuda:0', part_lat=None, part_lon=None):
+        if not torch.cuda.is_available():
+            raise _lib.LcsError('lagrangiancoherence_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self.lat = np.ascontiguousarray(lat, dtype=np.float64)
+        self.lon = np.ascontiguousarray(lon, dtype=np.float64)
+        if np.any(np.diff(self.lat) <= 0) or np.any(np.diff(self.lon) <= 0):
+            raise ValueError('latitude/longitude must be ascending (the reference sorts first, LCS.py:101-104)')
+        self.nlat, self.nlon = self.lat.size, self.lon.size
+        self.timestep = timestep
+        self.S = int(SETTLS_order)
+        self.order = int(interp_order)
+        if self.order not in (1, 3):
+            raise NotImplementedError('interp_order must be 1 or 3 (the reference default is 3; 0 is broken upstream, '
+                                      '2/4/5 are not implemented in the CUDA gather)')
+        self.xmode = XMODES[xmode]
+        self.pair_dtype = DTYPES[pair_dtype]
+        self.strict = int(bool(strict))
+        self.grid = _lib.Grid(self.nlat, self.nlon, self.lat.min(), self.lat.max(), self.lon.min(), self.lon.max())
+        self.part_lat = self.lat if part_lat is None else np.ascontiguousarray(part_lat, dtype=np.float64)
+        self.part_lon = self.lon if part_lon is None else np.ascontiguousarray(part_lon, dtype=np.float64)
+        # trajectory.py:54-57 (arrival-grid latitude, quirk Q5) and the products of :86-87,:110-112
+        conversion_y = 180 / (EARTH_R * np.pi)
+        conversion_x = 180 / (np.pi * EARTH_R * np.abs(np.cos(self.part_lat * np.pi / 180)))
+        self.ky = float(timestep * conversion_y)
+        self.hy = float(0.5 * timestep * conversion_y)
+        kx = timestep * conversion_x
+        hx = 0.5 * timestep * conversion_x
+        # tools.py:253-256 (uniform spacing taken from the first two coordinates)
+        y = self.lat * np.pi / 180
+        dx = (np.pi / 180) * (self.lon[1] - self.lon[0]) * EARTH_R * np.cos(y)
+        self.dy = float((np.pi / 180) * (self.lat[1] - self.lat[0]) * EARTH_R)
+        with torch.cuda.device(self.device):
+            dev = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(self.device)
+            self.d_plat, self.d_plon = dev(self.part_lat), dev(self.part_lon)
+            self.d_kx, self.d_hx, self.d_dx = dev(kx), dev(hx), dev(dx)
+            self.d_status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._ws = None
+
+    # ------------------------------------------------------------------ staging
+    def stage(self, u, v):
+        """Upload (if needed), prefilter (order 3) and pack a wind series ``[nlev, nlat, nlon]``."""
+        u = self._to_device(u)
+        v = self._to_device(v)
+        if u.shape != v.shape or u.dim() != 3 or tuple(u.shape[1:]) != (self.nlat, self.nlon):
+            raise ValueError(f'winds must be [nlev, {self.nlat}, {self.nlon}], got {tuple(u.shape)} / {tuple(v.shape)}')
+        nlev = u.shape[0]
+        if nlev < 2:
+            return StagedWinds(None, None, nlev)
+        tdt = torch.float64 if self.pair_dtype == _lib.LCS_F64 else torch.float32
+        with torch.cuda.device(self.device):
+            st = _stream(self.device)
+            raw = torch.empty((nlev - 1, self.nlat, self.nlon, 4), dtype=tdt, device=self.device)
+            _lib.check(self.lib.lcs_pack_pairs(_ptr(u), _ptr(v), _dtype_code(u), _ptr(raw), self.pair_dtype,
+                                               nlev, self.nlat, self.nlon, st), 'lcs_pack_pairs')
+            coef = None
+            if self.order == 3:
+                cu = torch.empty((nlev, self.nlat, self.nlon), dtype=torch.float64, device=self.device)
+                cv = torch.empty_like(cu)
+                _lib.check(self.lib.lcs_prefilter(_ptr(u), _ptr(v), _dtype_code(u), _ptr(cu), _ptr(cv),
+                                                  nlev, self.nlat, self.nlon, st), 'lcs_prefilter')
+                coef = torch.empty_like(raw)
+                _lib.check(self.lib.lcs_pack_pairs(_ptr(cu), _ptr(cv), _lib.LCS_F64, _ptr(coef), self.pair_dtype,
+                                                   nlev, self.nlat, self.nlon, st), 'lcs_pack_pairs')
+        return StagedWinds(raw, coef, nlev)
+
+    def _to_device(self, a):
+        if isinstance(a, torch.Tensor):
+            t = a
+        else:
+            a = np.asarray(a)
+            if a.dtype not in (np.float32, np.float64):
+                a = a.astype(np.float64)
+            t = torch.from_numpy(np.ascontiguousarray(a))
+        if t.dtype not in (torch.float32, torch.float64):
+            t = t.to(torch.float64)
+        return t.to(self.device, non_blocking=True).contiguous()
+
+    # ------------------------------------------------------------------ integrator
+    def advect(self, staged, nsteps=None, nwindows=1, level0=0, level_stride=1, return_traj=False,
+               rows=None, out=None):
+        """Run lcs_advect.  ``rows=(r0, r1)`` restricts to a band of particle rows (global indices).
+
+        Returns ``(x, y)`` shaped ``[nwindows, nrow, ncol]`` (+ ``(x_traj, y_traj)`` shaped
+        ``[nwindows, nsteps+1, nrow, ncol]`` with ``return_traj``).
+        """
+        if nsteps is None:
+            nsteps = staged.nlev - 1
+        if nsteps > 0 and level0 + (nwindows - 1) * level_stride + nsteps > staged.nlev - 1:
+            raise ValueError('window runs past the staged wind series')
+        r0, r1 = (0, self.part_lat.size) if rows is None else rows
+        nrow, ncol = r1 - r0, self.part_lon.size
+        with torch.cuda.device(self.device):
+            if out is None:
+                x = torch.empty((nwindows, nrow, ncol), dtype=torch.float64, device=self.device)
+                y = torch.empty_like(x)
+            else:
+                x, y = out
+            xt = yt = None
+            if return_traj:
+                xt = torch.empty((nwindows, nsteps + 1, nrow, ncol), dtype=torch.float64, device=self.device)
+                yt = torch.empty_like(xt)
+            part = _lib.Particles(nrow, ncol, r0, self.part_lat.size,
+                                  self.d_plat[r0:].data_ptr(), self.d_plon.data_ptr(),
+                                  self.d_kx[r0:].data_ptr(), self.d_hx[r0:].data_ptr(), self.ky, self.hy)
+            opts = _lib.AdvectOpts(nsteps, self.S, self.order, self.xmode, self.pair_dtype, self.strict,
+                                   nwindows, level0, level_stride)
+            need = self.lib.lcs_advect_workspace_bytes(C.byref(part), C.byref(opts))
+            ws = None
+            if need:
+                if self._ws is None or self._ws.numel() < need:
+                    self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+                ws = self._ws
+            if nsteps > 0:
+                raw, coef = staged.raw_pairs, staged.coef_pairs
+            else:   # nothing is sampled: any valid pointer will do
+                raw = coef = x
+            _lib.check(self.lib.lcs_advect(C.byref(self.grid), C.byref(part), C.byref(opts), _ptr(raw), _ptr(coef),
+                                           _ptr(x), _ptr(y), _ptr(xt), _ptr(yt), _ptr(ws), need,
+                                           _stream(self.device)), 'lcs_advect')
+        return (x, y, xt, yt) if return_traj else (x, y)
+
+    # ------------------------------------------------------------------ epilogue
+    def epilogue(self, x_dep, y_dep, log_scale=False, mask=None, return_jac=False, in_row0=0, out_rows=None):
+        """lcs_ftle_epilogue on ``[nfields, nrow_in, nlon]`` departure points (wind-grid shaped)."""
+        if x_dep.dim() == 2:
+            x_dep, y_dep = x_dep[None], y_dep[None]
+        nfields, nrow_in, nlon = x_dep.shape
+        if nlon != self.nlon:
+            raise ValueError('the epilogue needs departure points on the wind grid columns')
+        o0, o1 = (0, self.nlat) if out_rows is None else out_rows
+        with torch.cuda.device(self.device):
+            sigma = torch.empty((nfields, o1 - o0, nlon), dtype=torch.float64, device=self.device)
+            jac = torch.empty((nfields, 6, o1 - o0, nlon), dtype=torch.float64, device=self.device) if return_jac else None
+            d_mask = None
+            if mask is not None:
+                d_mask = torch.as_tensor(np.ascontiguousarray(mask, dtype=np.uint8)).to(self.device)
+            self.d_status.zero_()
+            _lib.check(self.lib.lcs_ftle_epilogue(_ptr(x_dep.contiguous()), _ptr(y_dep.contiguous()), nfields,
+                                                  self.nlat, nlon, in_row0, nrow_in, o0, o1 - o0,
+                                                  _ptr(self.d_dx), self.dy, _ptr(d_mask), int(bool(log_scale)),
+                                                  _ptr(sigma), _ptr(jac), _ptr(self.d_status),
+                                                  _stream(self.device)), 'lcs_ftle_epilogue')
+        return (sigma, jac) if return_jac else sigma
+
+    def check_finite(self):
+        """Raise like scipy.linalg.norm(check_finite=True) does at LCS.py:154 (synchronises)."""
+        if int(self.d_status.item()) & 1:
+            raise ValueError('array must not contain infs or NaNs')
+
+    # ------------------------------------------------------------------ whole path
+    def ftle(self, u, v, log_scale=False, mask=None):
+        """prefilter -> advect -> epilogue for one window; returns sigma ``[nlat, nlon]`` (device)."""
+        st = self.stage(u, v)
+        x, y = self.advect(st)
+        return self.epilogue(x, y, log_scale=log_scale, mask=mask)[0]
+
+
+# ---------------------------------------------------------------------- array-level seams
+def map_coordinates_device(field, pos_x, pos_y, lat, lon, order=1, device='cuda:0'):
+    """xr_map_coordinates (tools.py:11-41) on the device for one field; returns a f64 tensor."""
+    lib = _lib.load()
+    device = torch.device(device)
+    lat = np.asarray(lat, dtype=np.float64)
+    lon = np.asarray(lon, dtype=np.float64)
+    grid = _lib.Grid(lat.size, lon.size, lat.min(), lat.max(), lon.min(), lon.max())
+    with torch.cuda.device(device):
+        f = torch.as_tensor(np.ascontiguousarray(field, dtype=np.float64)).to(device)
+        px = torch.as_tensor(np.ascontiguousarray(pos_x, dtype=np.float64)).to(device)
+        py = torch.as_tensor(np.ascontiguousarray(pos_y, dtype=np.float64)).to(device)
+        nrow, ncol = px.shape
+        coef = None
+        if order == 3:
+            coef = torch.empty_like(f)
+            dummy = torch.empty_like(f)
+            _lib.check(lib.lcs_prefilter(_ptr(f), _ptr(f), _lib.LCS_F64, _ptr(coef), _ptr(dummy), 1,
+                                         lat.size, lon.size, _stream(device)), 'lcs_prefilter')
+        out = torch.empty_like(px)
+        _lib.check(lib.lcs_map_coordinates(C.byref(grid), _ptr(f), _ptr(coef), order, _ptr(px), _ptr(py),
+                                           nrow, ncol, 0, nrow, _ptr(out), _stream(device)), 'lcs_map_coordinates')
+    return out
+
+
+def prefilter_device(u, v, device='cuda:0'):
+    """Cubic B-spline coefficients of ``[nlev, nlat, nlon]`` series (f64 tensors on the device)."""
+    lib = _lib.load()
+    device = torch.device(device)
+    with torch.cuda.device(device):
+        tu = torch.as_tensor(np.ascontiguousarray(u)).to(device)
+        tv = torch.as_tensor(np.ascontiguousarray(v)).to(device)
+        nlev, nlat, nlon = tu.shape
+        cu = torch.empty(tu.shape, dtype=torch.float64, device=device)
+        cv = torch.empty_like(cu)
+        _lib.check(lib.lcs_prefilter(_ptr(tu), _ptr(tv), _dtype_code(tu), _ptr(cu), _ptr(cv), nlev, nlat, nlon,
+                                     _stream(device)), 'lcs_prefilter')
+    return cu, cv
+
+
+def fourth_order_derivative_device(arr, dim=0, isglobal=True, device='cuda:0'):
+    """fourth_order_derivative (tools.py:190-245) on an f32 array."""
+    lib = _lib.load()
+    device = torch.device(device)
+    with torch.cuda.device(device):
+        a = torch.as_tensor(np.ascontiguousarray(arr, dtype=np.float32)).to(device)
+        out = torch.empty_like(a)
+        _lib.check(lib.lcs_fourth_order_derivative(_ptr(a), a.shape[0], a.shape[1], int(dim), int(bool(isglobal)),
+                                                   _ptr(out), _stream(device)), 'lcs_fourth_order_derivative')
+    return out
+
+
+def spectral_norm_3x3_device(vals, device='cuda:0'):
+    """scipy.linalg.norm(vals[3,3,N], axis=(0,1), ord=2) (LCS.py:154)."""
+    lib = _lib.load()
+    device = torch.device(device)
+    v = np.ascontiguousarray(vals, dtype=np.float64)
+    n = v.shape[-1]
+    with torch.cuda.device(device):
+        t = torch.as_tensor(v.reshape(9, n)).to(device)
+        out = torch.empty(n, dtype=torch.float64, device=device)
+        _lib.check(lib.lcs_spectral_norm_3x3(_ptr(t), n, _ptr(out), _stream(device)), 'lcs_spectral_norm_3x3')
+    return out
