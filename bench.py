@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Headline benchmark: particle-steps/s and FTLE fields/s on the 0.25 deg ERA5-shape regional
+configuration (BASELINE.json configs[1], "C2": 281x321, 6-hourly u,v, 48 h backward FTLE,
+SETTLS_order=4, cubic interpolation, f64).
+
+A *step* is one batch of B independent start times (a rolling series of B+8 six-hourly levels;
+every window is exactly configs[1]) pushed through the whole hot path:
+prefilter + pack (new levels only once) -> departure-point integration -> fused FTLE epilogue.
+
+  python bench.py --gpus N --steps K --warmup W            # this repository (CUDA, sm_100a)
+  python bench.py --impl reference ...                     # the reference's CPU arithmetic (oracle port)
+
+`value` is whole-job particle-steps/s with the winds already resident in HBM; `e2e` is the same
+metric through the public rolling API with host (pinned) buffers, H2D and D2H inside the timed
+region.  One JSON line is printed by rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S_ORDER = 4
+NT = 9                   # 48 h at 6 h
+DT = -21600
+METRIC = 'particle-steps/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=64, help='start times per step and per GPU')
+    ap.add_argument('--xclamp', default='outer', choices=['outer', 'pointwise'],
+                    help="x-boundary: 'outer' = what the reference executes (quirk Q6)")
+    ap.add_argument('--order', type=int, default=3, choices=[1, 3])
+    ap.add_argument('--precision', default='f64', choices=['f64', 'f32'])
+    ap.add_argument('--workload', default='C2', choices=['C2', 'C3'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def workload(name):
+    from lagrangiancoherence_b200 import synthetic as S
+    if name == 'C2':
+        lat, lon = S.grid_c2()
+        return lat, lon, NT, DT, 'C2 regional 0.25deg 281x321, 6-hourly, 48 h backward (nt=9)'
+    lat, lon = S.grid_c3()
+    return lat, lon, 13, -3600, 'C3 near-global 0.25deg 721x1440, hourly, 12 h backward (nt=13)'
+
+
+def config_dict(args, desc, B, world):
+    return {'workload': f'{desc}, SETTLS_order={S_ORDER}, interp_order={args.order}, {args.precision} winds, '
+                        f'xclamp={args.xclamp}; step = {B} rolling start times per GPU ({B + NT - 1} levels)',
+            'grid': desc.split(',')[0], 'windows_per_step_per_gpu': B, 'xclamp': args.xclamp,
+            'interp_order': args.order, 'settls_order': S_ORDER, 'sharding': f'start-times x{world}',
+            'l2': 'flushed between timed steps (256 MiB write)'}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for t, line in self.rows:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 6:
+                continue
+            try:
+                clk, mx = float(parts[0]), float(parts[1])
+            except ValueError:
+                continue
+            if t0 - 0.05 <= t <= t1 + 0.05:
+                sm.append(clk)
+                for n, val in zip(names, parts[2:6]):
+                    if val.lower().startswith('active'):
+                        reasons.add(n)
+        if not sm:      # timed region shorter than the sampling period: take the nearest samples
+            sm = [float(l.split(',')[0]) for _, l in self.rows[-3:] if l.split(',')[0].strip().replace('.', '').isdigit()]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm / CPU baseline
+def _oracle_window(job):
+    """One configs[1] window through the CPU oracle (scipy map_coordinates + numba-typed stencil +
+    scipy.linalg.norm, i.e. the reference's arithmetic without xarray bookkeeping)."""
+    s, name, order, xclamp = job
+    from oracle import lcs_oracle as O
+    from lagrangiancoherence_b200 import synthetic as S
+    lat, lon, nt, dt, _ = workload(name)
+    u, v = S.era5_like_winds(lat, lon, nt, t0=s)
+    t = time.perf_counter()
+    O.lcs_field(u, v, lat, lon, dt, SETTLS_order=S_ORDER, traj_interp_order=order, xclamp=xclamp)
+    return time.perf_counter() - t
+
+
+def cpu_pool_run(name, order, xclamp, cores, nwindows, first=0):
+    """`nwindows` independent windows over `cores` worker processes; returns wall seconds."""
+    import multiprocessing as mp
+    jobs = [(first + i, name, order, xclamp) for i in range(nwindows)]
+    t = time.perf_counter()
+    if cores == 1:
+        for j in jobs:
+            _oracle_window(j)
+    else:
+        with mp.get_context('fork').Pool(cores) as pool:
+            pool.map(_oracle_window, jobs, chunksize=1)
+    return time.perf_counter() - t
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    lat, lon, nt, dt, desc = workload(args.workload)
+    cores = os.cpu_count() or 1
+    psteps_window = lat.size * lon.size * (nt - 1)
+    for _ in range(args.warmup):
+        cpu_pool_run(args.workload, args.order, args.xclamp, cores, cores)
+    times = [cpu_pool_run(args.workload, args.order, args.xclamp, cores, cores, first=100 * (k + 1))
+             for k in range(args.steps)]
+    total = float(np.sum(times))
+    value = psteps_window * cores * args.steps / total
+    sample = f'{cores} windows of {desc} per step (one per worker process), {args.steps} steps'
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'particle-steps/s', 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': config_dict(args, desc, cores, 1),
+            'fields_per_s': cores * args.steps / total,
+            'cpu_baseline': {'value': value, 'unit': 'particle-steps/s', 'cores': cores, 'kind': 'port',
+                             'sample': sample},
+            'e2e': {'value': value, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0,
+            'note': 'oracle port of the reference arithmetic (scipy.ndimage.map_coordinates + numba-typed stencil + '
+                    'scipy.linalg.norm); the reference itself needs xarray, absent from this image'}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- CUDA arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from lagrangiancoherence_b200 import synthetic as S, _lib, rolling
+    from lagrangiancoherence_b200.engine import FtleEngine, _ptr, _stream
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+    lat, lon, nt, dt, desc = workload(args.workload)
+    B = args.batch
+    nlev = B + nt - 1
+    npts = lat.size * lon.size
+    # rank r owns start times [r*B, (r+1)*B) of one long synthetic series (start-time sharding)
+    u, v = S.era5_like_winds(lat, lon, nlev, t0=rank * B)
+    if args.precision == 'f32':
+        u, v = u.astype(np.float32), v.astype(np.float32)
+    h_u = torch.from_numpy(u).pin_memory()
+    h_v = torch.from_numpy(v).pin_memory()
+    d_u, d_v = h_u.to(dev), h_v.to(dev)
+    eng = FtleEngine(lat, lon, dt, SETTLS_order=S_ORDER, interp_order=args.order, xmode=args.xclamp,
+                     pair_dtype=args.precision, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    gathered = [torch.empty((B, lat.size, lon.size), dtype=torch.float64, device=dev) for _ in range(world)] \
+        if world > 1 else None
+    x = torch.empty((B, lat.size, lon.size), dtype=torch.float64, device=dev)
+    y = torch.empty_like(x)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    adv_ms = []
+
+    def step(timed):
+        st = eng.stage(d_u, d_v)
+        a, b = ev(), ev()
+        a.record()
+        eng.advect(st, nsteps=nt - 1, nwindows=B, out=(x, y))
+        b.record()
+        sigma = eng.epilogue(x, y)
+        if world > 1:
+            dist.all_gather(gathered, sigma)
+        if timed:
+            adv_ms.append((a, b))
+        return sigma
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_wall0 = time.time()
+    step_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)                              # evict L2 between timed iterations
+        barrier()
+        a, b = ev(), ev()
+        a.record()
+        step(True)
+        b.record()
+        barrier()
+        step_ms.append(a.elapsed_time(b))
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    total_ms = float(np.sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    advect_ms = float(np.mean([a.elapsed_time(b) for a, b in adv_ms]))
+    psteps_step = world * B * npts * (nt - 1)
+    value = psteps_step * args.steps / (total_ms * 1e-3)
+
+    # ---- end to end through the public rolling API: pinned host winds in, host fields out
+    h_out = torch.empty((B, lat.size, lon.size), dtype=torch.float64).pin_memory()
+    e2e_ms = []
+    for i in range(args.warmup + args.steps):
+        flush.fill_(1)
+        barrier()
+        a, b = ev(), ev()
+        a.record()
+        rolling.rolling_ftle(h_u, h_v, lat, lon, nt, dt, SETTLS_order=S_ORDER, interp_order=args.order,
+                             xclamp=args.xclamp, precision=args.precision, device=dev, chunk=B, out=h_out,
+                             engine=eng)
+        b.record()
+        barrier()
+        if i >= args.warmup:
+            e2e_ms.append(a.elapsed_time(b))
+    e2e_total = float(np.sum(e2e_ms))
+    if world > 1:
+        t = torch.tensor([e2e_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_total = float(t.item())
+    e2e_value = psteps_step * args.steps / (e2e_total * 1e-3)
+    elt = 8 if args.precision == 'f64' else 4
+    h2d = 2 * nlev * npts * elt
+    d2h = B * npts * 8
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel(s): the departure-point integrator
+    taps = (args.order + 1) ** 2
+    gather_bytes_pstep = (2 + 4 * S_ORDER) * taps * elt            # 2304 B at p=3, f64
+    alg_bytes = B * npts * (nt - 1) * gather_bytes_pstep
+    achieved = alg_bytes / (advect_ms * 1e-3) / 1e9
+    # measured ceiling: same tap pattern on the same packed pairs, coherent positions, no dependent maths
+    st = eng.stage(d_u, d_v)
+    sink = torch.zeros(1, dtype=torch.float64, device=dev)
+    iters = 40
+    pairs = st.coef_pairs if args.order == 3 else st.raw_pairs
+    gp = lambda: _lib.check(lib.lcs_gather_peak(_ptr(pairs), eng.pair_dtype, lat.size, lon.size, lat.size, lon.size,
+                                                B, args.order + 1, 0.0, iters, _ptr(sink), _stream(dev)), 'lcs_gather_peak')
+    for _ in range(3):
+        gp()
+    torch.cuda.synchronize(dev)
+    best = 1e30
+    for _ in range(5):
+        a, b = ev(), ev()
+        a.record(); gp(); b.record()
+        torch.cuda.synchronize(dev)
+        best = min(best, a.elapsed_time(b))
+    gather_peak = B * npts * iters * taps * 4 * elt / (best * 1e-3) / 1e9
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except OSError:
+        pass
+    hbm_peak = peaks.get('hbm_gbs', 6650.0)
+    hbm_src = 'MEASURED_PEAKS.json (measured copy)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
+    # compulsory HBM traffic of the integrator: every packed pair level read once, final positions written once
+    hbm_bytes = (nlev - 1) * npts * 4 * elt + B * 2 * npts * 8
+    launches = 4 if args.order == 3 else 1
+    launches += (2 * (nt - 1) * (1 + S_ORDER) + 1) if args.xclamp == 'outer' else 1
+    launches += 1
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'particle-steps/s', 'n_gpus': world, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64' if args.precision == 'f64' else 'f32 winds / f64 positions',
+        'data': 'synthetic', 'config': config_dict(args, desc, B, world),
+        'fields_per_s': world * B * args.steps / (total_ms * 1e-3),
+        'interpolations_per_s': value * (2 + 4 * S_ORDER),
+        'e2e': {'value': e2e_value, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                'ms_per_step': e2e_total / args.steps, 'fields_per_s': world * B * args.steps / (e2e_total * 1e-3),
+                'api': 'lagrangiancoherence_b200.rolling.rolling_ftle (pinned host winds in, pinned host fields out)'},
+        'gpu_launches': launches * args.steps,
+        'gpu_launches_per_step': launches,
+        'clocks': clocks,
+        'roofline': {
+            'bound': 'gather (L1/L2 -> SM); not hbm, not tensor: nothing on this path is a dense contraction',
+            'kernel': 'advect_phase_move x%d + gtpass (lcs_advect call)' % ((nt - 1) * (1 + S_ORDER))
+                      if args.xclamp == 'outer' else 'advect_fused_kernel (one launch)',
+            'achieved': achieved, 'peak': gather_peak, 'unit': 'GB/s', 'frac': achieved / gather_peak,
+            'peak_source': 'lcs_gather_peak measured in this run: same %dx%d-tap %d-B vector gathers on the same packed '
+                           'pairs, coherent positions, no dependent arithmetic' % (args.order + 1, args.order + 1, 4 * elt),
+            'algorithmic_bytes_per_particle_step': gather_bytes_pstep,
+            'advect_ms_per_step': advect_ms,
+            'traffic': None,
+            'hbm': {'achieved': hbm_bytes / (advect_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+                    'frac': hbm_bytes / (advect_ms * 1e-3) / 1e9 / hbm_peak, 'peak_source': hbm_src,
+                    'compulsory_bytes': hbm_bytes},
+        },
+    }
+    if not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        lat2, lon2, nt2, _, desc2 = workload(args.workload)
+        secs = cpu_pool_run(args.workload, args.order, args.xclamp, cores, cores)
+        line['cpu_baseline'] = {'value': lat2.size * lon2.size * (nt2 - 1) * cores / secs, 'unit': 'particle-steps/s',
+                                'cores': cores, 'kind': 'port',
+                                'sample': f'{cores} windows of the same workload, one per worker process '
+                                          f'({secs:.1f} s wall): oracle = scipy map_coordinates + numba-typed stencil '
+                                          f'+ scipy.linalg.norm'}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_b200(a)

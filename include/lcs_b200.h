@@ -72,12 +72,14 @@ int lcs_abi_version(void);
 const char* lcs_last_error(void);
 
 /* ---------------------------------------------------------------- wind staging
- * lcs_prefilter: cubic B-spline coefficients of every level, mirror boundary, axis 0 then axis 1,
- * f64 -- what scipy.ndimage.map_coordinates(order=3, mode='wrap') recomputes inside every call at
- * tools.py:26-30; here it runs once per level.  u, v: device [nlev][nlat][nlon] of `in_dtype`;
- * coef_u, coef_v: device f64 planes of the same shape (may not alias the inputs). */
+ * lcs_prefilter: cubic B-spline coefficients of every level, mirror boundary, latitude axis then
+ * longitude axis, f64 -- what scipy.ndimage.map_coordinates(order=3, mode='wrap') recomputes inside
+ * every call at tools.py:26-30; here it runs once per level.  u, v: device [nlev][nlat][nlon] of
+ * `in_dtype`; coef_u, coef_v: device f64 planes of the same shape (may not alias the inputs);
+ * scratch: device buffer of lcs_prefilter_scratch_bytes() bytes. */
+size_t lcs_prefilter_scratch_bytes(int nlev, int nlat, int nlon);
 int lcs_prefilter(const void* u, const void* v, int in_dtype, double* coef_u, double* coef_v,
-                  int nlev, int nlat, int nlon, void* stream);
+                  void* scratch, size_t scratch_bytes, int nlev, int nlat, int nlon, void* stream);
 
 /* lcs_pack_pairs: interleave two planar series into the gather layout
  * pairs[k][lat][lon] = (u_k, v_k, u_{k+1}, v_{k+1}), k = 0..nlev-2, one 32-byte (f64) or 16-byte

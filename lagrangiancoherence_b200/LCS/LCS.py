@@ -1,0 +1,142 @@
+"""``LCS`` and ``flowmap_gradient`` with the reference's signatures (LCS.py:19-225), executed by the
+CUDA engine: ``lcs_prefilter`` + ``lcs_pack_pairs`` + ``lcs_advect`` + ``lcs_ftle_epilogue``."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ..engine import FtleEngine
+from ..labelled import coord_values, is_dataset, make_like
+from .trajectory import propagate, XCLAMP_DEFAULT
+
+DERIVATIVE_NAMES = ['dxdx', 'dxdy', 'dydx', 'dydy', 'dzdx', 'dzdy', 'dxdr', 'dydr', 'dzdr']   # LCS.py:210-218
+
+
+def _crop_index(coord, sl):
+    """Strict-inequality crop (tools.py:184-186); the ``xr_tools.latlonsel`` the reference imports
+    (LCS.py:13) is not in its tree, its in-tree analogue is the model."""
+    keep = np.ones(coord.shape, bool)
+    if sl is not None:
+        if sl.start is not None:
+            keep &= coord > sl.start
+        if sl.stop is not None:
+            keep &= coord < sl.stop
+    return keep
+
+
+class LCS:
+    """API to compute the finite-time Lyapunov exponent field of 2-D winds (drop-in for LCS.py:19-168).
+
+    ``LCS(timestep, timedim, SETTLS_order, subdomain, return_dpts, gauss_sigma)`` then
+    ``lcs(ds)`` or ``lcs(u=u, v=v)``.  Returns the largest singular value of the as-executed
+    3x3 (quirk Q7) as a ``(timedim=1, latitude, longitude)`` array; callers apply
+    ``0.5*np.log(.)`` themselves, as with the reference (examples/ideal_vortex.py:282).
+    """
+    earth_r = 6371000  # metres
+
+    def __init__(self, timestep=1, timedim='time', SETTLS_order=0, subdomain=None, return_dpts=False,
+                 gauss_sigma=None):
+        self.timestep = timestep
+        self.SETTLS_order = SETTLS_order
+        self.timedim = timedim
+        self.subdomain = subdomain
+        self.gauss_sigma = gauss_sigma
+        self.return_dpts = return_dpts
+
+    def __call__(self, ds=None, u=None, v=None, verbose=True, s=None, resample=None, s_is_error=False,
+                 isglobal=False, return_traj=False, interp_to_common_grid=True, traj_interp_order=3,
+                 truncation=20, *, xclamp=XCLAMP_DEFAULT, device='cuda:0', precision='f64'):
+        print('!' * 100)                                             # LCS.py:74 (unconditional upstream)
+        verboseprint = print if verbose else (lambda *a, **k: None)
+        timestep, timedim = self.timestep, self.timedim
+        self.verbose = verbose
+        if is_dataset(ds):                                           # LCS.py:81-83
+            u, v = ds.u.copy(), ds.v.copy()
+        elif isinstance(ds, str):                                    # LCS.py:84-87
+            raise NotImplementedError('opening NetCDF paths needs xarray/netCDF4, which this image lacks; '
+                                      'pass u= and v= arrays')
+        if isinstance(resample, str):                                # LCS.py:88-91
+            raise NotImplementedError("resample= (linear time refinement) is not implemented yet")
+        assert set(u.dims) == set(v.dims), "u and v dims are different"                      # LCS.py:95
+        assert set(u.dims) == {'latitude', 'longitude', timedim}, \
+            'array dims should be latitude and longitude only'                               # LCS.py:96
+        if isglobal:                                                 # LCS.py:105-120
+            if interp_to_common_grid or truncation is not None:
+                raise NotImplementedError(
+                    'isglobal=True with interp_to_common_grid/truncation needs the 360x721 regrid and a T20 '
+                    'spherical-harmonic truncation (windspharm upstream); pass interp_to_common_grid=False, '
+                    'truncation=None to run the cyclic path on the native grid')
+            cyclic_xboundary = True
+            self.subdomain = None
+        else:
+            cyclic_xboundary = False
+        if s is None:                                                # LCS.py:124-126 (printed, never used)
+            u0 = np.asarray(u.isel({timedim: 0}).values)
+            s = int(10 * u0.size * u0.std())
+            print('using s = ' + str(s / 1e6) + '1e6')
+        verboseprint("*---- Parcel propagation ----*")
+        engine, out, Us, lat, lon, times = propagate(u, v, timestep, timedim, return_traj, self.SETTLS_order,
+                                                     traj_interp_order, cyclic_xboundary, xclamp, device, precision)
+        x_dep, y_dep = out[0], out[1]
+        verboseprint("*---- Computing deformation tensor ----*")
+        if isinstance(self.gauss_sigma, (float, int)):               # LCS.py:187-190
+            raise NotImplementedError('gauss_sigma smoothing of the departure points is not implemented yet')
+        latkeep = lonkeep = None
+        out_rows = None
+        if isinstance(self.subdomain, dict):                         # LCS.py:143-144 (crop after the derivatives)
+            latkeep = _crop_index(lat, self.subdomain.get('latitude'))
+            lonkeep = _crop_index(lon, self.subdomain.get('longitude'))
+            rows = np.flatnonzero(latkeep)
+            if rows.size:
+                out_rows = (int(rows[0]), int(rows[-1]) + 1)         # only these rows are computed
+        verboseprint("*---- Computing eigenvalues ----*")
+        sigma = engine.epilogue(x_dep, y_dep, out_rows=out_rows)
+        engine.check_finite()                                        # ValueError on inf, as scipy.linalg.norm (LCS.py:154)
+        sigma = sigma[0].cpu().numpy()
+        verboseprint("*---- Done eigenvalues ----*")
+        olat, olon = lat, lon
+        if latkeep is not None:
+            r0 = out_rows[0] if out_rows else 0
+            sigma = sigma[latkeep[r0:r0 + sigma.shape[0]]][:, lonkeep] if out_rows else sigma[:0, :0]
+            olat, olon = lat[latkeep], lon[lonkeep]
+        tvals = coord_values(Us, timedim)
+        timestamp = tvals[-1] if np.sign(timestep) == 1 else tvals[0]                         # LCS.py:158
+        coords = {'latitude': olat, 'longitude': olon, 'time': np.asarray(timestamp)}        # LCS.py:159
+        if timedim == 'time':
+            coords['time'] = np.asarray(timestamp)[None]
+        eigenvalues = make_like(u, sigma[None], (timedim, 'latitude', 'longitude'), coords)  # LCS.py:160
+        dims2 = ('latitude', 'longitude')
+        c2 = {'latitude': lat, 'longitude': lon, timedim: np.asarray(times[-1])}
+        xd = make_like(u, x_dep[0].cpu().numpy(), dims2, c2) if (self.return_dpts or return_traj) else None
+        yd = make_like(u, y_dep[0].cpu().numpy(), dims2, c2) if (self.return_dpts or return_traj) else None
+        if return_traj:
+            import pandas as pd
+            tc = {timedim: np.asarray(pd.to_datetime(times)), 'latitude': lat, 'longitude': lon}
+            d3 = (timedim, 'latitude', 'longitude')
+            x_trajs = make_like(u, out[2][0].cpu().numpy(), d3, tc)
+            y_trajs = make_like(u, out[3][0].cpu().numpy(), d3, tc)
+        if self.return_dpts and return_traj:                         # LCS.py:161-168
+            return eigenvalues, xd, yd, x_trajs, y_trajs
+        elif self.return_dpts:
+            return eigenvalues, xd, yd
+        elif return_traj:
+            return eigenvalues, x_trajs, y_trajs
+        return eigenvalues
+
+
+def flowmap_gradient(x_departure, y_departure, sigma=None, *, device='cuda:0'):
+    """The nine stacked 'derivatives' ``(derivatives, latitude, longitude)`` of LCS.py:171-225."""
+    if isinstance(sigma, (float, int)):
+        raise NotImplementedError('gauss_sigma smoothing of the departure points is not implemented yet')
+    xd = x_departure.transpose('latitude', 'longitude')
+    yd = y_departure.transpose('latitude', 'longitude')
+    lat, lon = coord_values(xd, 'latitude'), coord_values(xd, 'longitude')
+    engine = FtleEngine(lat, lon, 1, device=device)
+    dev = torch.device(device)
+    tx = torch.from_numpy(np.ascontiguousarray(xd.values, dtype=np.float64)).to(dev)
+    ty = torch.from_numpy(np.ascontiguousarray(yd.values, dtype=np.float64)).to(dev)
+    _, jac = engine.epilogue(tx, ty, return_jac=True)
+    jac = jac[0]
+    full = torch.cat([jac, torch.zeros((3,) + tuple(jac.shape[1:]), dtype=jac.dtype, device=dev)])   # LCS.py:206-208
+    coords = {'derivatives': np.array(DERIVATIVE_NAMES), 'latitude': lat, 'longitude': lon}
+    return make_like(x_departure, full.cpu().numpy(), ('derivatives', 'latitude', 'longitude'), coords)

@@ -1,0 +1,68 @@
+"""``parcel_propagation`` with the reference's signature (trajectory.py:8-18), executed by the
+CUDA integrator ``lcs_advect``.  Labelled-array bookkeeping happens here on the host; every
+per-particle operation runs on the device."""
+from __future__ import annotations
+
+import numpy as np
+import pandas as pd
+
+from ..engine import FtleEngine
+from ..labelled import coord_values, make_like
+
+XCLAMP_DEFAULT = 'outer'     # what the reference executes for cyclic_xboundary=False (quirk Q6)
+
+
+def _sorted_winds(U, V, propdim):
+    """sortby longitude then latitude (trajectory.py:49-52) and a (time, lat, lon) view."""
+    U = U.sortby('longitude').sortby('latitude')
+    V = V.sortby('longitude').sortby('latitude')
+    return U.transpose(propdim, 'latitude', 'longitude'), V.transpose(propdim, 'latitude', 'longitude')
+
+
+def propagate(U, V, timestep, propdim, return_traj, SETTLS_order, interp_order, cyclic_xboundary,
+              xclamp=XCLAMP_DEFAULT, device='cuda:0', precision='f64', engine=None):
+    """Shared by parcel_propagation and LCS.__call__: returns device tensors plus the metadata the
+    callers need to label them."""
+    U, V = _sorted_winds(U, V, propdim)
+    lat = coord_values(U, 'latitude')
+    lon = coord_values(U, 'longitude')
+    times = coord_values(U, propdim).tolist()                      # trajectory.py:58
+    if timestep < 0:
+        times.reverse()                                            # labels only (quirk Q2), :59-60
+    xmode = 'cyclic' if cyclic_xboundary else xclamp
+    if engine is None:
+        engine = FtleEngine(lat, lon, timestep, SETTLS_order=SETTLS_order, interp_order=interp_order,
+                            xmode=xmode, pair_dtype=precision, device=device)
+    staged = engine.stage(np.asarray(U.values), np.asarray(V.values))
+    out = engine.advect(staged, return_traj=return_traj)
+    return engine, out, U, lat, lon, times
+
+
+def parcel_propagation(U, V, timestep=1, propdim='time', verbose=True, return_traj=False,
+                       SETTLS_order=0, copy=False, interp_order=3, cyclic_xboundary=False,
+                       *, xclamp=XCLAMP_DEFAULT, device='cuda:0', precision='f64'):
+    """Lagrangian 2-time-level advection (drop-in for trajectory.py:8-144).
+
+    Same arguments, defaults and return convention as the reference: final
+    ``(positions_x, positions_y)`` on the arrival grid carrying the scalar coordinate
+    ``propdim = times[-1]``, or with ``return_traj`` the ``(propdim, latitude, longitude)`` stacks
+    (level 0 = the start grid) labelled ``pd.to_datetime(times)`` -- ``times`` reversed when
+    ``timestep < 0`` (trajectory.py:58-60,138-142).  ``copy`` is accepted for compatibility: inputs
+    are never mutated.  Keyword-only extras select the engine: ``xclamp`` ('outer' = as executed,
+    or 'pointwise'), ``device``, ``precision`` ('f64' | 'f32' packed-wind storage).
+    """
+    verboseprint = print if verbose else (lambda *a, **k: None)
+    _, out, Us, lat, lon, times = propagate(U, V, timestep, propdim, return_traj, SETTLS_order, interp_order,
+                                            cyclic_xboundary, xclamp, device, precision)
+    for t in times[:-1]:
+        verboseprint(f'Propagating time {t}')                       # trajectory.py:81
+    if return_traj:
+        xt, yt = out[2][0].cpu().numpy(), out[3][0].cpu().numpy()
+        tcoord = np.asarray(pd.to_datetime(times))                  # trajectory.py:138
+        coords = {propdim: tcoord, 'latitude': lat, 'longitude': lon}
+        dims = (propdim, 'latitude', 'longitude')
+        return make_like(U, xt, dims, coords), make_like(U, yt, dims, coords)
+    x, y = out[0][0].cpu().numpy(), out[1][0].cpu().numpy()
+    coords = {'latitude': lat, 'longitude': lon, propdim: np.asarray(times[-1])}   # trajectory.py:141-142
+    dims = ('latitude', 'longitude')
+    return make_like(U, x, dims, coords), make_like(U, y, dims, coords)

@@ -38,7 +38,9 @@ class AdvectOpts(C.Structure):
 SIGNATURES = {
     'lcs_abi_version': (c_int, []),
     'lcs_last_error': (C.c_char_p, []),
-    'lcs_prefilter': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    'lcs_prefilter_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'lcs_prefilter': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                              c_int, c_int, c_int, c_void_p]),
     'lcs_pack_pairs': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'lcs_advect_workspace_bytes': (c_size_t, [C.POINTER(Particles), C.POINTER(AdvectOpts)]),
     'lcs_advect': (c_int, [C.POINTER(Grid), C.POINTER(Particles), C.POINTER(AdvectOpts), c_void_p, c_void_p,

@@ -26,7 +26,7 @@ struct AdvectParams {
     double lat_min, lat_span, lon_min, lon_span, lat_max, lon_max;
     // particles
     int nrow, ncol, row0, nrow_global;
-    long long np;                 // nrow*ncol
+    int np;                       // nrow*ncol (< 2^31)
     const double* lat;
     const double* lon;
     const double* kx;
@@ -37,23 +37,26 @@ struct AdvectParams {
     double* y_out;
     double* x_traj;
     double* y_traj;
-    // phased (outer clamp) state
-    double* sx; double* sy; double* sua; double* sva;   // [nwindows][np]
-    unsigned char* flags;                                // [nwindows][nsub][2][nrow+ncol]
+    // phased (outer clamp) state, indexed by the particle's enumeration index p
+    d2* spos;                     // [nwindows][np] (x, y)
+    d2* swind;                    // [nwindows][np] (ua, va) of the interval's Euler stage
+    int* cand;                    // [nwindows][np] particles with x > lon_max after the current sub-step
+    int* cand_count;              // [nwindows][nsub]
+    unsigned char* flags;         // [nwindows][nsub][2][nrow+ncol]
     int nsub;
 };
 
 // Particle enumeration: bands of `band` rows, column-major inside a band, so that a warp covers
 // a (band x 32/band) patch -- smaller unique tap footprint than a 1x32 strip, no idle tail lanes.
-__device__ __forceinline__ void particle_rc(const AdvectParams& P, long long p, int& row, int& col) {
-    const long long per_band = (long long)P.band * P.ncol;
+__device__ __forceinline__ void particle_rc(const AdvectParams& P, int p, int& row, int& col) {
+    const int per_band = P.band * P.ncol;
     const int nbands = (P.nrow + P.band - 1) / P.band;
-    int b = (int)(p / per_band);
+    int b = p / per_band;
     if (b > nbands - 1) b = nbands - 1;
-    const long long q = p - (long long)b * per_band;
+    const int q = p - b * per_band;
     const int h = (b == nbands - 1) ? (P.nrow - b * P.band) : P.band;
-    col = (int)(q / h);
-    row = b * P.band + (int)(q - (long long)col * h);
+    col = q / h;
+    row = b * P.band + (q - col * h);
 }
 
 template <typename T, bool STRICT, int ORDER, int NV>
@@ -105,7 +108,7 @@ __device__ __forceinline__ void bounds_local(const AdvectParams& P, double& x, d
 template <typename T, bool STRICT, int ORDER>
 __global__ void __launch_bounds__(256)
 advect_fused_kernel(const AdvectParams P) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int w = blockIdx.y;
     if (p >= P.np) return;
     int row, col;
@@ -135,20 +138,33 @@ advect_fused_kernel(const AdvectParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Outer-product clamp (trajectory.py:96-97): after each sub-step
-//   A: x_new computed, y clamped, flag rows/cols with x_new < x_min         (advect_phase_move)
-//   B: x' = x_min where rowflag&colflag; flag rows/cols with x' > x_max      (advect_phase_lt)
-//   next A (or the final launch) first applies x'' = x_max where rowflag&colflag of B.
-// Flag slot for sub-step q of window w: flags + ((w*nsub + q)*2 + which) * (nrow+ncol);
-// bytes [0,nrow) are row flags, [nrow, nrow+ncol) column flags.  All slots start at zero.
+// Outer-product clamp (trajectory.py:96-97 / 122-123).  `px[np.where(px < x_min)] = x_min` on a
+// DataArray is an ORTHOGONAL assignment: every (row, col) with row in {rows holding an exit} and
+// col in {columns holding an exit} is set, then the same for x_max on the updated array.  This
+// couples all particles of a window after every sub-step, so a sub-step q is
+//   move(q)  : apply the pending x_min / x_max passes of q-1 (flags are complete by then), run the
+//              stage, clamp y, store the state, raise the (row, col) "<x_min" flags of q and append
+//              particles with x > x_max to the window's candidate list;
+//   gtpass(q): tiny launch over the candidates: x' = x_min if rowflag&colflag, and if still
+//              x' > x_max raise the ">x_max" flags of q.
+// Flags of sub-step q, window w: flags + ((w*nsub + q)*2 + which)*(nrow+ncol); bytes [0,nrow) rows,
+// [nrow,nrow+ncol) columns.  Flags and candidate counters start at zero (cleared by lcs_advect).
 __device__ __forceinline__ unsigned char* flag_slot(const AdvectParams& P, int w, int q, int which) {
     return P.flags + ((size_t)((size_t)w * P.nsub + q) * 2 + which) * (size_t)(P.nrow + P.ncol);
+}
+
+__device__ __forceinline__ double apply_pending(const AdvectParams& P, int w, int q_prev, int row, int col, double x) {
+    const unsigned char* lt = flag_slot(P, w, q_prev, 0);
+    const unsigned char* gt = flag_slot(P, w, q_prev, 1);
+    if (lt[row] && lt[P.nrow + col]) x = P.lon_min;           // trajectory.py:96
+    if (gt[row] && gt[P.nrow + col]) x = P.lon_max;           // trajectory.py:97
+    return x;
 }
 
 template <typename T, bool STRICT, int ORDER>
 __global__ void __launch_bounds__(256)
 advect_phase_move(const AdvectParams P, int q /* global sub-step index */) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int w = blockIdx.y;
     if (p >= P.np) return;
     int row, col;
@@ -157,72 +173,72 @@ advect_phase_move(const AdvectParams P, int q /* global sub-step index */) {
     const int t = q / per, k = q - t * per;          // k == 0: Euler stage
     const int grow = P.row0 + row;
     const bool pole = (grow < ORDER) || (grow >= P.nrow_global - ORDER);
-    const size_t o = (size_t)w * P.np + (size_t)row * P.ncol + col;
+    const size_t o = (size_t)w * P.np + p;
     double x, y;
     if (q == 0) {
         x = __ldg(P.lon + col); y = __ldg(P.lat + row);
-        if (P.x_traj) {
-            const size_t to = (size_t)w * P.np * (P.nsteps + 1) + (size_t)row * P.ncol + col;
-            P.x_traj[to] = x; P.y_traj[to] = y;
-        }
     } else {
-        x = P.sx[o]; y = P.sy[o];
-        const unsigned char* g = flag_slot(P, w, q - 1, 1);           // pending x_max pass
-        if (g[row] && g[P.nrow + col]) x = P.lon_max;
-        if (k == 0 && P.x_traj) {                                      // level t is now final
-            const size_t to = ((size_t)w * (P.nsteps + 1) + t) * P.np + (size_t)row * P.ncol + col;
-            P.x_traj[to] = x; P.y_traj[to] = y;
-        }
+        const d2 s = P.spos[o];
+        x = apply_pending(P, w, q - 1, row, col, s.x); y = s.y;
+    }
+    if (k == 0 && P.x_traj) {                         // level t is final once the pending passes ran
+        const size_t to = ((size_t)w * (P.nsteps + 1) + t) * P.np + (size_t)row * P.ncol + col;
+        P.x_traj[to] = x; P.y_traj[to] = y;
     }
     const int pair = P.level0 + w * P.level_stride + t;
     if (k == 0) {
         double ua, va;
         stage_euler<T, STRICT, ORDER>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
-        P.sua[o] = ua; P.sva[o] = va;
+        d2 e; e.x = ua; e.y = va;
+        P.swind[o] = e;
     } else {
-        stage_settls<T, STRICT, ORDER>(P, pair, pole, __ldg(P.hx + row), P.sua[o], P.sva[o], x, y);
+        const d2 e = P.swind[o];
+        stage_settls<T, STRICT, ORDER>(P, pair, pole, __ldg(P.hx + row), e.x, e.y, x, y);
     }
     y = clamp_y(y, P.lat_min, P.lat_max);
-    P.sx[o] = x; P.sy[o] = y;
+    d2 s; s.x = x; s.y = y;
+    P.spos[o] = s;
     if (x < P.lon_min) {
         unsigned char* f = flag_slot(P, w, q, 0);
         f[row] = 1; f[P.nrow + col] = 1;
+    } else if (x > P.lon_max) {
+        const int slot = atomicAdd(P.cand_count + (size_t)w * P.nsub + q, 1);
+        P.cand[(size_t)w * P.np + slot] = p;
     }
 }
 
 __global__ void __launch_bounds__(256)
-advect_phase_lt(const AdvectParams P, int q) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+advect_phase_gtpass(const AdvectParams P, int q) {
     const int w = blockIdx.y;
-    if (p >= P.np) return;
-    const int row = (int)(p / P.ncol), col = (int)(p - (long long)row * P.ncol);
-    const size_t o = (size_t)w * P.np + (size_t)p;
-    const unsigned char* f = flag_slot(P, w, q, 0);
-    double x = P.sx[o];
-    if (f[row] && f[P.nrow + col]) { x = P.lon_min; P.sx[o] = x; }
-    if (x > P.lon_max) {
-        unsigned char* g = flag_slot(P, w, q, 1);
-        g[row] = 1; g[P.nrow + col] = 1;
+    const int n = P.cand_count[(size_t)w * P.nsub + q];
+    const unsigned char* lt = flag_slot(P, w, q, 0);
+    unsigned char* gt = flag_slot(P, w, q, 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int p = P.cand[(size_t)w * P.np + i];
+        int row, col;
+        particle_rc(P, p, row, col);
+        // x > lon_max here; it survives the x_min pass unless its row and column both hold an exit
+        if (!(lt[row] && lt[P.nrow + col])) { gt[row] = 1; gt[P.nrow + col] = 1; }
     }
 }
 
 __global__ void __launch_bounds__(256)
 advect_phase_final(const AdvectParams P) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
     const int w = blockIdx.y;
     if (p >= P.np) return;
-    const int row = (int)(p / P.ncol), col = (int)(p - (long long)row * P.ncol);
-    const size_t o = (size_t)w * P.np + (size_t)p;
+    int row, col;
+    particle_rc(P, p, row, col);
     double x, y;
     if (P.nsub == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
     else {
-        x = P.sx[o]; y = P.sy[o];
-        const unsigned char* g = flag_slot(P, w, P.nsub - 1, 1);
-        if (g[row] && g[P.nrow + col]) x = P.lon_max;
+        const d2 s = P.spos[(size_t)w * P.np + p];
+        x = apply_pending(P, w, P.nsub - 1, row, col, s.x); y = s.y;
     }
-    P.x_out[o] = x; P.y_out[o] = y;
+    const size_t o = (size_t)row * P.ncol + col;
+    P.x_out[(size_t)w * P.np + o] = x; P.y_out[(size_t)w * P.np + o] = y;
     if (P.x_traj) {
-        const size_t to = ((size_t)w * (P.nsteps + 1) + P.nsteps) * P.np + (size_t)p;
+        const size_t to = ((size_t)w * (P.nsteps + 1) + P.nsteps) * P.np + o;
         P.x_traj[to] = x; P.y_traj[to] = y;
     }
 }
@@ -236,9 +252,10 @@ static cudaError_t launch_advect(const AdvectParams& P, int nwindows, cudaStream
         advect_fused_kernel<T, STRICT, ORDER><<<grid, block, 0, st>>>(P);
         return cudaGetLastError();
     }
+    const dim3 ggrid(4, (unsigned)nwindows);
     for (int q = 0; q < P.nsub; ++q) {
         advect_phase_move<T, STRICT, ORDER><<<grid, block, 0, st>>>(P, q);
-        advect_phase_lt<<<grid, block, 0, st>>>(P, q);
+        advect_phase_gtpass<<<ggrid, block, 0, st>>>(P, q);
     }
     advect_phase_final<<<grid, block, 0, st>>>(P);
     return cudaGetLastError();
@@ -250,13 +267,26 @@ using namespace lcs;
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-extern "C" size_t lcs_advect_workspace_bytes(const lcs_particles* p, const lcs_advect_opts* o) {
-    if (!p || !o || o->xmode != LCS_X_CLAMP_OUTER) return 0;
+// workspace of the outer-clamp path: [pos | wind | cand | cleared: cand_count, flags]
+struct WsLayout { size_t pos, wind, cand, count, flags, clear_bytes, total; };
+static WsLayout ws_layout(const lcs_particles* p, const lcs_advect_opts* o) {
     const size_t np = (size_t)p->nrow * p->ncol;
     const size_t nsub = (size_t)o->nsteps * (1 + o->settls_order);
-    const size_t state = align_up((size_t)o->nwindows * np * sizeof(double), 256);
-    const size_t flags = align_up((size_t)o->nwindows * nsub * 2 * (size_t)(p->nrow + p->ncol), 256);
-    return 4 * state + flags;
+    WsLayout L;
+    L.pos = 0;
+    L.wind = L.pos + align_up((size_t)o->nwindows * np * sizeof(d2), 256);
+    L.cand = L.wind + align_up((size_t)o->nwindows * np * sizeof(d2), 256);
+    L.count = L.cand + align_up((size_t)o->nwindows * np * sizeof(int), 256);
+    L.flags = L.count + align_up((size_t)o->nwindows * nsub * sizeof(int), 256);
+    L.total = L.flags + align_up((size_t)o->nwindows * nsub * 2 * (size_t)(p->nrow + p->ncol), 256);
+    L.clear_bytes = L.total - L.count;
+    return L;
+}
+
+extern "C" size_t lcs_advect_workspace_bytes(const lcs_particles* p, const lcs_advect_opts* o) {
+    if (!p || !o || o->xmode != LCS_X_CLAMP_OUTER) return 0;
+    const WsLayout L = ws_layout(p, o);
+    return L.total;
 }
 
 extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_advect_opts* o,
@@ -283,7 +313,8 @@ extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_a
     P.lat_min = g->lat_min; P.lat_max = g->lat_max; P.lat_span = g->lat_max - g->lat_min;
     P.lon_min = g->lon_min; P.lon_max = g->lon_max; P.lon_span = g->lon_max - g->lon_min;
     P.nrow = p->nrow; P.ncol = p->ncol; P.row0 = p->row0; P.nrow_global = p->nrow_global;
-    P.np = (long long)p->nrow * p->ncol;
+    if ((long long)p->nrow * p->ncol >= (1LL << 31)) return lcs_fail(LCS_E_INVALID, "lcs_advect: too many particles per window");
+    P.np = p->nrow * p->ncol;
     P.lat = p->lat; P.lon = p->lon; P.kx = p->kx; P.hx = p->hx; P.ky = p->ky; P.hy = p->hy;
     P.nsteps = o->nsteps; P.S = o->settls_order; P.xmode = o->xmode;
     P.level0 = o->level0; P.level_stride = o->level_stride;
@@ -292,20 +323,20 @@ extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_a
     if (P.band > 32) P.band = 32;
     P.x_out = x_out; P.y_out = y_out; P.x_traj = x_traj; P.y_traj = y_traj;
     P.nsub = o->nsteps * (1 + o->settls_order);
-    if (o->xmode == LCS_X_CLAMP_OUTER) {
-        const size_t state = align_up((size_t)o->nwindows * (size_t)P.np * sizeof(double), 256);
-        char* w = static_cast<char*>(workspace);
-        P.sx = reinterpret_cast<double*>(w);
-        P.sy = reinterpret_cast<double*>(w + state);
-        P.sua = reinterpret_cast<double*>(w + 2 * state);
-        P.sva = reinterpret_cast<double*>(w + 3 * state);
-        P.flags = reinterpret_cast<unsigned char*>(w + 4 * state);
-    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    if (o->xmode == LCS_X_CLAMP_OUTER && P.nsub > 0) {       // exit flags start cleared
-        e = cudaMemsetAsync(P.flags, 0, (size_t)o->nwindows * P.nsub * 2 * (size_t)(P.nrow + P.ncol), st);
-        if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_advect(memset)");
+    if (o->xmode == LCS_X_CLAMP_OUTER) {
+        const WsLayout L = ws_layout(p, o);
+        char* w = static_cast<char*>(workspace);
+        P.spos = reinterpret_cast<d2*>(w + L.pos);
+        P.swind = reinterpret_cast<d2*>(w + L.wind);
+        P.cand = reinterpret_cast<int*>(w + L.cand);
+        P.cand_count = reinterpret_cast<int*>(w + L.count);
+        P.flags = reinterpret_cast<unsigned char*>(w + L.flags);
+        if (P.nsub > 0) {                                     // exit flags and candidate counters start cleared
+            e = cudaMemsetAsync(w + L.count, 0, L.clear_bytes, st);
+            if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_advect(memset)");
+        }
     }
     const bool strict = o->strict != 0;
     const int ord = o->interp_order;

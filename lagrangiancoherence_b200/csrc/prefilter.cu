@@ -2,83 +2,75 @@
 //
 // scipy.ndimage.map_coordinates(order=3, mode='wrap') re-runs spline_filter over the whole field
 // inside every call (tools.py:26-30: 18 calls per wind interval at SETTLS_order=4).  The
-// coefficients depend only on the level, so here they are computed once per level:
-// per axis  c *= (1-z)(1-1/z);  exact mirror causal initialisation;  c[i] += z c[i-1];
-// c[n-1] = (z c[n-2] + c[n-1]) z/(z^2-1);  c[i] = z (c[i+1] - c[i]),  z = sqrt(3)-2, axis 0 first.
-// Each operation is a separate IEEE f64 op in that order (no FMA) so the result equals the numpy
-// restatement in oracle/lcs_oracle.py bit for bit (which is within a few ulp of scipy).
+// coefficients depend only on the level, so here they are computed once per level.
+//
+// scipy's filter is, per axis, gain (1-z)(1-1/z) times a causal and an anticausal one-pole
+// recursion (z = sqrt(3)-2) with the *exact* initialisation for the mirror extension.  That
+// recursion is sequential along a line; its closed form is a symmetric two-sided exponential
+//      c[i] = sum_k  sqrt(3) * z^|k| * s[mirror(i + k)]
+// over the mirror-extended signal (d c b | a b c d | c b a).  |z| = 0.268, so truncating at
+// |k| <= 32 leaves a relative remainder < 1e-18, far below one f64 ulp: every output is
+// independent and the filter becomes a 65-tap FIR.  Each thread slides a register window down
+// KR consecutive outputs (65+KR-1 loads for KR*65 FMAs); both passes filter along axis 0 of their
+// input with threads along axis 1 (coalesced) and write their result transposed, so two
+// applications filter axis 0 (lat) then axis 1 (lon) -- scipy's order -- and restore the layout.
+// Agreement with scipy.ndimage.spline_filter is ~1e-15 of the field magnitude
+// (tests/test_gpu_engine.py), not bitwise: the summation order differs from the recursion.
 #include <math.h>
 #include "lcs_internal.h"
 #include "lcs_device.cuh"
 
 namespace lcs {
 
-template <typename Tin>
-__device__ __forceinline__ void filter_line(const Tin* src, size_t sstride,
-                                            double* dst, size_t dstride, int n,
-                                            double z, double gain, double zn1) {
-    if (n < 2) { if (n == 1) dst[0] = (double)src[0]; return; }
-    // exact causal initialisation for the mirror extension
-    double c0 = __dadd_rn(__dmul_rn((double)src[0], gain), __dmul_rn(zn1, __dmul_rn((double)src[(size_t)(n - 1) * sstride], gain)));
-    double zi = z;
-    for (int i = 1; i < n - 1; ++i) {
-        if (zi == 0.0) break;                      // z^i underflowed: every later term adds exactly 0
-        const double a = __dmul_rn((double)src[(size_t)i * sstride], gain);
-        const double b = __dmul_rn((double)src[(size_t)(n - 1 - i) * sstride], gain);
-        c0 = __dadd_rn(c0, __dmul_rn(zi, __dadd_rn(a, __dmul_rn(zn1, b))));
-        zi = __dmul_rn(zi, z);
-    }
-    c0 = __ddiv_rn(c0, __dsub_rn(1.0, __dmul_rn(zn1, zn1)));
-    // causal pass
-    double prev = c0, prev2 = 0.0;
-    // src may alias dst (the row pass is in place): element i is read before it is written
-    double cur = c0;
-    dst[0] = c0;
-    for (int i = 1; i < n; ++i) {
-        const double a = __dmul_rn((double)src[(size_t)i * sstride], gain);
-        prev2 = prev;
-        cur = __dadd_rn(a, __dmul_rn(z, prev));
-        dst[(size_t)i * dstride] = cur;
-        prev = cur;
-    }
-    // anticausal initialisation and pass
-    double nxt = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(z, prev2), cur), z), __dsub_rn(__dmul_rn(z, z), 1.0));
-    dst[(size_t)(n - 1) * dstride] = nxt;
-    for (int i = n - 2; i >= 0; --i) {
-        nxt = __dmul_rn(z, __dsub_rn(nxt, dst[(size_t)i * dstride]));
-        dst[(size_t)i * dstride] = nxt;
-    }
-}
+constexpr int KH = 32;    // half width of the truncated impulse response
+constexpr int KR = 8;     // consecutive outputs per thread
 
-// axis 0: one thread per (plane, column); adjacent threads walk adjacent columns (coalesced)
+struct FirTaps { double h[KH + 1]; };
+
+// in : [plane][n0][n1]  (plane p of the first pass: level p>>1, component p&1 -> u or v)
+// out: [plane][n1][n0]  filtered along n0, transposed
 template <typename Tin>
 __global__ void __launch_bounds__(128)
-prefilter_cols_kernel(const Tin* __restrict__ u, const Tin* __restrict__ v, double* cu, double* cv,
-                      int nlev, int nlat, int nlon, double z, double gain, double zn1) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)2 * nlev * nlon;
-    if (idx >= total) return;
-    const int col = (int)(idx % nlon);
-    const int pl = (int)(idx / nlon);
-    const int lev = pl >> 1;
-    const size_t off = (size_t)lev * nlat * nlon + col;
-    const Tin* src = ((pl & 1) ? v : u) + off;
-    double* dst = ((pl & 1) ? cv : cu) + off;
-    filter_line<Tin>(src, (size_t)nlon, dst, (size_t)nlon, nlat, z, gain, zn1);
-}
-
-// axis 1, in place: one thread per (plane, row).  Accesses are line-strided; every 128-B line
-// a warp touches is reused by its next 15 iterations out of L1.
-__global__ void __launch_bounds__(128)
-prefilter_rows_kernel(double* cu, double* cv, int nlev, int nlat, int nlon, double z, double gain, double zn1) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)2 * nlev * nlat;
-    if (idx >= total) return;
-    const int row = (int)(idx % nlat);
-    const int pl = (int)(idx / nlat);
-    const int lev = pl >> 1;
-    double* line = ((pl & 1) ? cv : cu) + ((size_t)lev * nlat + row) * nlon;
-    filter_line<double>(line, 1, line, 1, nlon, z, gain, zn1);
+fir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b, int interleaved_planes,
+                           double* __restrict__ out_a, double* __restrict__ out_b, int split_out,
+                           int n0, int n1, const FirTaps taps) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n1) return;
+    const int r0 = blockIdx.y * KR;
+    const int p = blockIdx.z;
+    const size_t plane = (size_t)n0 * n1;
+    // first pass reads planes alternately from u and v; second pass reads one contiguous scratch
+    const Tin* src = interleaved_planes ? ((p & 1) ? in_b : in_a) + (size_t)(p >> 1) * plane + c
+                                        : in_a + (size_t)p * plane + c;
+    double* dst = split_out ? ((p & 1) ? out_b : out_a) + (size_t)(p >> 1) * plane
+                            : out_a + (size_t)p * plane;
+    // mirror-reflected start index, then walk with direction flips at the two ends
+    const int period = 2 * n0 - 2;
+    int ii = (r0 - KH) % period;
+    if (ii < 0) ii += period;
+    int dir = 1;
+    if (ii >= n0) { ii = period - ii; dir = -1; }
+    if (ii == n0 - 1) dir = -1;
+    if (ii == 0) dir = 1;
+    double acc[KR];
+#pragma unroll
+    for (int j = 0; j < KR; ++j) acc[j] = 0.0;
+#pragma unroll
+    for (int m = 0; m < KR + 2 * KH; ++m) {
+        const double s = (double)__ldg(src + (size_t)ii * n1);
+#pragma unroll
+        for (int j = 0; j < KR; ++j) {
+            const int k = m - KH - j;                      // source index minus output index
+            if (k >= -KH && k <= KH) acc[j] = fma(taps.h[k < 0 ? -k : k], s, acc[j]);
+        }
+        ii += dir;
+        if (ii == n0 - 1) dir = -1;
+        else if (ii == 0) dir = 1;
+    }
+    double* o = dst + (size_t)c * n0 + r0;
+#pragma unroll
+    for (int j = 0; j < KR; ++j)
+        if (r0 + j < n0) o[j] = acc[j];
 }
 
 template <typename Tin, typename Tout>
@@ -99,30 +91,46 @@ pack_pairs_kernel(const Tin* __restrict__ u, const Tin* __restrict__ v,
 
 using namespace lcs;
 
+static FirTaps make_taps() {
+    FirTaps t;
+    const double z = sqrt(3.0) - 2.0;
+    const double h0 = (1.0 - z) * (1.0 - 1.0 / z) * (-z) / (1.0 - z * z);   // = sqrt(3)
+    for (int k = 0; k <= KH; ++k) t.h[k] = h0 * pow(z, k);
+    return t;
+}
+
+extern "C" size_t lcs_prefilter_scratch_bytes(int nlev, int nlat, int nlon) {
+    if (nlev < 1 || nlat < 1 || nlon < 1) return 0;
+    return (size_t)2 * nlev * nlat * nlon * sizeof(double);
+}
+
 extern "C" int lcs_prefilter(const void* u, const void* v, int in_dtype, double* coef_u, double* coef_v,
-                             int nlev, int nlat, int nlon, void* stream) {
-    if (!u || !v || !coef_u || !coef_v) return lcs_fail(LCS_E_INVALID, "lcs_prefilter: null argument");
+                             void* scratch, size_t scratch_bytes, int nlev, int nlat, int nlon, void* stream) {
+    if (!u || !v || !coef_u || !coef_v || !scratch) return lcs_fail(LCS_E_INVALID, "lcs_prefilter: null argument");
     if (nlev < 1 || nlat < 2 || nlon < 2) return lcs_fail(LCS_E_INVALID, "lcs_prefilter: bad sizes");
     if (u == coef_u || v == coef_v) return lcs_fail(LCS_E_INVALID, "lcs_prefilter: outputs may not alias inputs");
+    if (scratch_bytes < lcs_prefilter_scratch_bytes(nlev, nlat, nlon))
+        return lcs_fail(LCS_E_WORKSPACE, "lcs_prefilter: scratch too small");
+    if (2 * nlev > 65535) return lcs_fail(LCS_E_INVALID, "lcs_prefilter: at most 32767 levels per call");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const double z = sqrt(3.0) - 2.0;
-    const double gain = (1.0 - z) * (1.0 - 1.0 / z);
-    const long long ncol_threads = (long long)2 * nlev * nlon;
-    const unsigned gb = (unsigned)((ncol_threads + 127) / 128);
+    const FirTaps taps = make_taps();
+    double* tmp = static_cast<double*>(scratch);
+    // pass 1: along latitude; [plane][lat][lon] -> scratch [plane][lon][lat]
+    const dim3 g1((nlon + 127) / 128, (nlat + KR - 1) / KR, 2 * nlev);
     if (in_dtype == LCS_F64)
-        prefilter_cols_kernel<double><<<gb, 128, 0, st>>>((const double*)u, (const double*)v, coef_u, coef_v,
-                                                          nlev, nlat, nlon, z, gain, pow(z, nlat - 1));
+        fir_axis0_transpose_kernel<double><<<g1, 128, 0, st>>>((const double*)u, (const double*)v, 1, tmp, nullptr, 0,
+                                                               nlat, nlon, taps);
     else if (in_dtype == LCS_F32)
-        prefilter_cols_kernel<float><<<gb, 128, 0, st>>>((const float*)u, (const float*)v, coef_u, coef_v,
-                                                         nlev, nlat, nlon, z, gain, pow(z, nlat - 1));
+        fir_axis0_transpose_kernel<float><<<g1, 128, 0, st>>>((const float*)u, (const float*)v, 1, tmp, nullptr, 0,
+                                                              nlat, nlon, taps);
     else return lcs_fail(LCS_E_INVALID, "lcs_prefilter: bad in_dtype");
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_prefilter(cols)");
-    const long long nrow_threads = (long long)2 * nlev * nlat;
-    prefilter_rows_kernel<<<(unsigned)((nrow_threads + 127) / 128), 128, 0, st>>>(coef_u, coef_v, nlev, nlat, nlon,
-                                                                                  z, gain, pow(z, nlon - 1));
+    if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_prefilter(lat pass)");
+    // pass 2: along longitude; scratch [plane][lon][lat] -> coef [lat][lon] of u / v
+    const dim3 g2((nlat + 127) / 128, (nlon + KR - 1) / KR, 2 * nlev);
+    fir_axis0_transpose_kernel<double><<<g2, 128, 0, st>>>(tmp, nullptr, 0, coef_u, coef_v, 1, nlon, nlat, taps);
     e = cudaGetLastError();
-    if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_prefilter(rows)");
+    if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_prefilter(lon pass)");
     return LCS_OK;
 }
 

@@ -119,7 +119,9 @@ class FtleEngine:
             if self.order == 3:
                 cu = torch.empty((nlev, self.nlat, self.nlon), dtype=torch.float64, device=self.device)
                 cv = torch.empty_like(cu)
+                scratch = torch.empty((2,) + tuple(cu.shape), dtype=torch.float64, device=self.device)
                 _lib.check(self.lib.lcs_prefilter(_ptr(u), _ptr(v), _dtype_code(u), _ptr(cu), _ptr(cv),
+                                                  _ptr(scratch), scratch.numel() * 8,
                                                   nlev, self.nlat, self.nlon, st), 'lcs_prefilter')
                 coef = torch.empty_like(raw)
                 _lib.check(self.lib.lcs_pack_pairs(_ptr(cu), _ptr(cv), _lib.LCS_F64, _ptr(coef), self.pair_dtype,
@@ -235,8 +237,9 @@ def map_coordinates_device(field, pos_x, pos_y, lat, lon, order=1, device='cuda:
         if order == 3:
             coef = torch.empty_like(f)
             dummy = torch.empty_like(f)
-            _lib.check(lib.lcs_prefilter(_ptr(f), _ptr(f), _lib.LCS_F64, _ptr(coef), _ptr(dummy), 1,
-                                         lat.size, lon.size, _stream(device)), 'lcs_prefilter')
+            scratch = torch.empty((2,) + tuple(f.shape), dtype=torch.float64, device=device)
+            _lib.check(lib.lcs_prefilter(_ptr(f), _ptr(f), _lib.LCS_F64, _ptr(coef), _ptr(dummy), _ptr(scratch),
+                                         scratch.numel() * 8, 1, lat.size, lon.size, _stream(device)), 'lcs_prefilter')
         out = torch.empty_like(px)
         _lib.check(lib.lcs_map_coordinates(C.byref(grid), _ptr(f), _ptr(coef), order, _ptr(px), _ptr(py),
                                            nrow, ncol, 0, nrow, _ptr(out), _stream(device)), 'lcs_map_coordinates')
@@ -253,8 +256,9 @@ def prefilter_device(u, v, device='cuda:0'):
         nlev, nlat, nlon = tu.shape
         cu = torch.empty(tu.shape, dtype=torch.float64, device=device)
         cv = torch.empty_like(cu)
-        _lib.check(lib.lcs_prefilter(_ptr(tu), _ptr(tv), _dtype_code(tu), _ptr(cu), _ptr(cv), nlev, nlat, nlon,
-                                     _stream(device)), 'lcs_prefilter')
+        scratch = torch.empty((2,) + tuple(cu.shape), dtype=torch.float64, device=device)
+        _lib.check(lib.lcs_prefilter(_ptr(tu), _ptr(tv), _dtype_code(tu), _ptr(cu), _ptr(cv), _ptr(scratch),
+                                     scratch.numel() * 8, nlev, nlat, nlon, _stream(device)), 'lcs_prefilter')
     return cu, cv
 
 

@@ -1,0 +1,121 @@
+"""Rolling FTLE time series and multi-GPU sharding.
+
+The reference has no library function for this: its application script loops one ``LCS`` call per
+start time (area_of_influence.py:168-184) and its CLI is driven by an external per-start-time job
+array (LCS.py:236-268).  Here the whole series is staged once (each level is prefiltered and
+packed once, not once per window) and all start times of a chunk are integrated by one launch.
+
+Sharding, one process per GPU, no data-path collective:
+  * start times  -- rank r owns a contiguous block of windows (``shard_starts``);
+  * row bands    -- rank r integrates particle rows [r0-2, r1+2) (2-row recomputed halo for the
+                    +-2 y-stencil, tools.py:204-207) and writes rows [r0, r1) (``shard_rows``);
+                    valid for the cyclic / pointwise x-boundary only: the as-executed outer-product
+                    clamp (quirk Q6) couples rows through the per-sub-step column flags.
+NCCL is used only to gather the finished fields (``gather_fields`` / ``gather_bands``).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .engine import FtleEngine
+
+
+# ------------------------------------------------------------------ pure planning helpers (CPU-testable)
+def shard_starts(nstarts, world_size, rank):
+    """Contiguous block of start times for ``rank``: returns ``(first, count)``."""
+    base, extra = divmod(nstarts, world_size)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def shard_rows(nrows, world_size, rank, halo=2):
+    """Row band of ``rank``: ``(out0, out1, in0, in1)`` -- rows written and rows integrated."""
+    base, extra = divmod(nrows, world_size)
+    out0 = rank * base + min(rank, extra)
+    out1 = out0 + base + (1 if rank < extra else 0)
+    return out0, out1, max(0, out0 - halo), min(nrows, out1 + halo)
+
+
+def chunk_starts(first, count, chunk):
+    """Split a block of start times into launches of at most ``chunk`` windows."""
+    return [(s, min(chunk, first + count - s)) for s in range(first, first + count, chunk)]
+
+
+# ------------------------------------------------------------------ single-GPU rolling series
+def rolling_ftle(u, v, lat, lon, window_levels, timestep, SETTLS_order=4, interp_order=3, xclamp='outer',
+                 cyclic_xboundary=False, precision='f64', device='cuda:0', starts=None, chunk=64,
+                 log_scale=False, out=None, engine=None, return_device=False):
+    """sigma_max fields for every start time of a wind series.
+
+    ``u, v``: ``[nlev, nlat, nlon]`` (numpy, pinned or not, or device tensors).  Window ``s`` uses
+    levels ``s .. s+window_levels-1`` exactly as ``LCS(...)(u.isel(time=slice(s, s+window_levels)))``
+    would.  Returns ``[nstarts, nlat, nlon]`` (numpy unless ``return_device``).
+    """
+    lat = np.asarray(lat, dtype=np.float64)
+    lon = np.asarray(lon, dtype=np.float64)
+    nlev = u.shape[0]
+    nsteps = window_levels - 1
+    first, count = (0, nlev - window_levels + 1) if starts is None else starts
+    if count < 1 or first + count + nsteps > nlev:
+        raise ValueError('start-time range runs past the wind series')
+    if engine is None:
+        engine = FtleEngine(lat, lon, timestep, SETTLS_order=SETTLS_order, interp_order=interp_order,
+                            xmode='cyclic' if cyclic_xboundary else xclamp, pair_dtype=precision, device=device)
+    dev = engine.device
+    # stage only the levels this block of windows touches
+    lo, hi = first, first + count + nsteps
+    staged = engine.stage(u[lo:hi], v[lo:hi])
+    sigma = torch.empty((count, lat.size, lon.size), dtype=torch.float64, device=dev)
+    for s, n in chunk_starts(0, count, chunk):
+        x, y = engine.advect(staged, nsteps=nsteps, nwindows=n, level0=s, level_stride=1)
+        sigma[s:s + n] = engine.epilogue(x, y, log_scale=log_scale)
+    engine.check_finite()
+    if return_device:
+        return sigma
+    if out is not None:
+        out.copy_(sigma, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out
+    return sigma.cpu().numpy()
+
+
+# ------------------------------------------------------------------ collectives (gather only)
+def gather_fields(local, counts, group=None, dst=None):
+    """All ranks contribute ``[count_r, nlat, nlon]``; returns the concatenation on every rank
+    (``dst=None``, all_gather) or on ``dst`` only.  Works on NCCL (device tensors) and gloo (CPU)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    maxc = max(counts)
+    pad = local
+    if local.shape[0] < maxc:
+        pad = torch.zeros((maxc,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad.contiguous(), group=group)
+    if dst is not None and dist.get_rank(group) != dst:
+        return None
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+
+
+def gather_bands(local_band, nrows, group=None):
+    """Row bands ``[..., rows_r, nlon]`` -> full ``[..., nrows, nlon]`` on every rank."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    counts = [shard_rows(nrows, world, r)[1] - shard_rows(nrows, world, r)[0] for r in range(world)]
+    moved = local_band.movedim(-2, 0).contiguous()
+    full = gather_fields(moved, counts, group=group)
+    return full.movedim(0, -2).contiguous()
+
+
+def band_ftle(engine, staged, world_size, rank, nsteps=None, nwindows=1, level0=0, log_scale=False):
+    """Row-band shard of one (or several) fields: integrate own rows + 2-row halo, run the epilogue
+    on own rows.  Returns ``(sigma_band [nwindows, rows, nlon], (out0, out1))``."""
+    from . import _lib
+    if engine.xmode == _lib.LCS_X_CLAMP_OUTER and world_size > 1:
+        raise ValueError("row-band sharding needs xmode 'cyclic' or 'pointwise': the as-executed outer-product "
+                         'x-clamp couples all rows each sub-step (use start-time sharding instead)')
+    out0, out1, in0, in1 = shard_rows(engine.nlat, world_size, rank)
+    x, y = engine.advect(staged, nsteps=nsteps, nwindows=nwindows, level0=level0, rows=(in0, in1))
+    sigma = engine.epilogue(x, y, log_scale=log_scale, in_row0=in0, out_rows=(out0, out1))
+    return sigma, (out0, out1)

@@ -1,0 +1,153 @@
+"""The reference-shaped Python API (LCS, parcel_propagation, flowmap_gradient, tools seams) on the GPU
+against the oracle, written the way a test of the reference would read."""
+import numpy as np
+import pytest
+
+from oracle import lcs_oracle as O
+from lagrangiancoherence_b200 import DataArray, Dataset, synthetic as S
+
+pytestmark = pytest.mark.gpu
+
+FTLE_REL = 1e-5     # north_star tolerance on the FTLE field (f32 noise floor of the reference's own stencil)
+
+
+def winds(nt=5, nlat=41, nlon=57, flip=False, dims=('time', 'latitude', 'longitude')):
+    lat = np.linspace(-30.0, 10.0, nlat)
+    lon = np.linspace(-80.0, -24.0, nlon)
+    u, v = S.era5_like_winds(lat, lon, nt)
+    time = np.datetime64('2000-01-01T00') + np.arange(nt) * np.timedelta64(6, 'h')
+    coords = {'time': time.astype('datetime64[ns]'), 'latitude': lat, 'longitude': lon}
+    du = DataArray(u, ('time', 'latitude', 'longitude'), coords)
+    dv = DataArray(v, ('time', 'latitude', 'longitude'), coords)
+    if flip:                       # descending latitude, as ERA5 ships it: the API must sort (LCS.py:101-104)
+        du = du.isel(latitude=np.arange(nlat)[::-1])
+        dv = dv.isel(latitude=np.arange(nlat)[::-1])
+    du, dv = du.transpose(*dims), dv.transpose(*dims)
+    return du, dv, u, v, lat, lon, time
+
+
+def close_fraction(a, b, rel):
+    return (np.abs(a - b) <= rel * np.abs(b) + 1e-12).mean()
+
+
+@pytest.mark.parametrize('flip,dims', [(False, ('time', 'latitude', 'longitude')),
+                                       (True, ('latitude', 'time', 'longitude'))])
+def test_lcs_call_matches_oracle(cuda_device, flip, dims, capsys):
+    from lagrangiancoherence_b200.LCS.LCS import LCS
+    du, dv, u, v, lat, lon, time = winds(flip=flip, dims=dims)
+    out = LCS(timestep=-6 * 3600, timedim='time', SETTLS_order=4)(u=du, v=dv, verbose=False)
+    assert '!' * 100 in capsys.readouterr().out                       # LCS.py:74
+    assert out.dims == ('time', 'latitude', 'longitude') and out.shape == (1, lat.size, lon.size)
+    assert np.array_equal(out.coords['latitude'], lat)                # ascending arrival grid
+    assert out.coords['time'][0] == time[0].astype('datetime64[ns]')  # backward: stamped with time[0], LCS.py:158
+    ref = O.lcs_field(u, v, lat, lon, -21600, SETTLS_order=4)
+    assert close_fraction(out.values[0], ref, FTLE_REL) >= 0.995
+
+
+def test_lcs_forward_dataset_return_tuples(cuda_device):
+    from lagrangiancoherence_b200.LCS.LCS import LCS
+    du, dv, u, v, lat, lon, time = winds()
+    ds = Dataset({'u': du, 'v': dv})
+    res = LCS(timestep=6 * 3600, SETTLS_order=2, return_dpts=True)(ds, verbose=False, return_traj=True)
+    assert len(res) == 5                                              # LCS.py:161-162
+    eig, xd, yd, xt, yt = res
+    assert eig.coords['time'][0] == time[-1].astype('datetime64[ns]')  # forward: time[-1]
+    rx, ry = O.parcel_propagation(u, v, lat, lon, 21600, SETTLS_order=2, return_traj=True)
+    assert xt.shape == rx.shape and xt.dims == ('time', 'latitude', 'longitude')
+    assert np.abs(xt.values - rx).max() <= 1e-10 * np.abs(lon).max()
+    assert np.abs(yt.values - ry).max() <= 1e-10 * np.abs(lat).max()
+    assert np.array_equal(xd.values, xt.values[-1])
+    assert len(LCS(timestep=21600, SETTLS_order=2, return_dpts=True)(ds, verbose=False)) == 3
+    assert len(LCS(timestep=21600, SETTLS_order=2)(ds, verbose=False, return_traj=True)) == 3
+
+
+def test_lcs_subdomain_crops_like_latlonsel(cuda_device):
+    from lagrangiancoherence_b200.LCS.LCS import LCS
+    du, dv, u, v, lat, lon, _ = winds()
+    sub = {'latitude': slice(-20, 0), 'longitude': slice(-70, -40)}
+    out = LCS(timestep=-21600, SETTLS_order=4, subdomain=sub)(u=du, v=dv, verbose=False)
+    keep_lat = (lat > -20) & (lat < 0)
+    keep_lon = (lon > -70) & (lon < -40)
+    assert np.array_equal(out.coords['latitude'], lat[keep_lat]) and np.array_equal(out.coords['longitude'], lon[keep_lon])
+    ref = O.lcs_field(u, v, lat, lon, -21600, SETTLS_order=4)[keep_lat][:, keep_lon]
+    assert close_fraction(out.values[0], ref, FTLE_REL) >= 0.995
+
+
+def test_lcs_asserts_on_bad_dims(cuda_device):
+    from lagrangiancoherence_b200.LCS.LCS import LCS
+    du, dv, *_ = winds()
+    bad = DataArray(du.values, ('time', 'lat', 'lon'))
+    with pytest.raises(AssertionError):
+        LCS(timestep=-21600)(u=bad, v=bad, verbose=False)
+
+
+def test_parcel_propagation_cyclic_ideal_vortex(cuda_device):
+    """configs[0]: the example's idealised vortex, backward S=4 and forward S=2, cyclic (ideal_vortex.py:262-279)."""
+    from lagrangiancoherence_b200.LCS.trajectory import parcel_propagation
+    u, v, lat, lon = S.ideal_vortex(**S.vortex_config_subtropical)
+    time = (np.datetime64('2000-01-01T00') + np.arange(u.shape[0]) * np.timedelta64(6, 'h')).astype('datetime64[ns]')
+    coords = {'time': time, 'latitude': lat, 'longitude': lon}
+    du, dv = DataArray(u, ('time', 'latitude', 'longitude'), coords), DataArray(v, ('time', 'latitude', 'longitude'), coords)
+    for dt, s_order in ((-21600, 4), (21600, 2)):
+        x, y = parcel_propagation(du, dv, timestep=dt, propdim='time', SETTLS_order=s_order, copy=True,
+                                  return_traj=True, cyclic_xboundary=True, verbose=False)
+        rx, ry = O.parcel_propagation(u, v, lat, lon, dt, SETTLS_order=s_order, cyclic_xboundary=True, return_traj=True)
+        ex = np.abs(x.values - rx) / 180.0
+        ey = np.abs(y.values - ry) / 90.0
+        # the vortex core winds are not smooth (|u| jumps across the centre): allow a handful of particles that sit
+        # on the wrap / pole-row discontinuities to differ, everything else within 1e-10
+        assert (ex > 1e-10).mean() <= 1e-3 and (ey > 1e-10).mean() <= 1e-3, ((ex > 1e-10).mean(), ex.max())
+        assert x.dims == ('time', 'latitude', 'longitude')
+        expect_t = time[::-1] if dt < 0 else time                     # labels reversed when backward, trajectory.py:59-60
+        assert np.array_equal(x.coords['time'], expect_t)
+    xf, yf = parcel_propagation(du, dv, timestep=-21600, SETTLS_order=4, cyclic_xboundary=True, verbose=False)
+    assert xf.dims == ('latitude', 'longitude') and np.asarray(xf.coords['time']).ndim == 0
+
+
+def test_flowmap_gradient_and_tools(cuda_device):
+    from lagrangiancoherence_b200.LCS.LCS import flowmap_gradient
+    from lagrangiancoherence_b200.LCS import tools
+    du, dv, u, v, lat, lon, _ = winds()
+    rx, ry = O.parcel_propagation(u, v, lat, lon, -21600, SETTLS_order=4)
+    c2 = {'latitude': lat, 'longitude': lon}
+    xd, yd = DataArray(rx, ('latitude', 'longitude'), c2), DataArray(ry, ('latitude', 'longitude'), c2)
+    dt = flowmap_gradient(xd, yd)
+    ref = O.flowmap_gradient(rx, ry, lat, lon)
+    assert dt.dims == ('derivatives', 'latitude', 'longitude') and dt.shape == ref.shape
+    assert list(dt.coords['derivatives'][:2]) == ['dxdx', 'dxdy']
+    assert (dt.values != ref).mean() <= 1e-3 and np.all(dt.values[6:] == 0)
+    # seams
+    X = (O.EARTH_R * np.sin((ry - 90) * np.pi / 180) * np.cos(rx * np.pi / 180))
+    for dim in (0, 1):
+        got = tools.derivative_spherical_coords(DataArray(X, ('latitude', 'longitude'), c2), dim=dim)
+        assert np.array_equal(got.values, O.derivative_spherical_coords(X, lat, lon, dim=dim))
+        a32 = X.astype('float32')
+        for isglobal in (True, False):
+            assert np.array_equal(tools.fourth_order_derivative(a32, dim=dim, isglobal=isglobal),
+                                  O.fourth_order_derivative(a32, dim=dim, isglobal=isglobal))
+    got = tools.xr_map_coordinates(du.isel(time=0), xd, yd, order=3)
+    assert np.abs(got.values - O.xr_map_coordinates(u[0], rx, ry, lat, lon, order=3)).max() <= 1e-12 * np.abs(u).max()
+
+
+def test_spectral_norm_seam(cuda_device):
+    from scipy.linalg import norm
+    from lagrangiancoherence_b200.engine import spectral_norm_3x3_device
+    rng = np.random.default_rng(0)
+    vals = rng.normal(size=(3, 3, 500))
+    got = spectral_norm_3x3_device(vals).cpu().numpy()
+    assert np.abs(got - norm(vals, axis=(0, 1), ord=2)).max() <= 1e-12
+    vals[2] = 0                                                       # the hot path's layout (LCS.py:206-208)
+    got = spectral_norm_3x3_device(vals).cpu().numpy()
+    assert np.abs(got - norm(vals, axis=(0, 1), ord=2)).max() <= 1e-13
+
+
+def test_rolling_matches_per_window_calls(cuda_device):
+    from lagrangiancoherence_b200.rolling import rolling_ftle
+    lat = np.linspace(-30.0, 10.0, 41)
+    lon = np.linspace(-80.0, -24.0, 57)
+    u, v = S.era5_like_winds(lat, lon, 9)
+    fields = rolling_ftle(u, v, lat, lon, 5, -21600, SETTLS_order=4, chunk=2)
+    assert fields.shape == (5, lat.size, lon.size)
+    for s in (0, 3, 4):
+        ref = O.lcs_field(u[s:s + 5], v[s:s + 5], lat, lon, -21600, SETTLS_order=4)
+        assert close_fraction(fields[s], ref, FTLE_REL) >= 0.995
