@@ -1,7 +1,14 @@
-python -m pytest tests -m gpu -q 2>&1 | tail -30
-python bench.py --steps 3 --warmup 2 --xclamp pointwise --no-cpu-baseline 2>&1 | tail -3
-python bench.py --steps 3 --warmup 2 --no-cpu-baseline 2>&1 | tail -3
-python scripts/probe_perf.py 2>&1 | grep -E '"B": (1|64), "xmode": "(pointwise|outer)", "order": 3, "pair": "f64", "strict": false' | head -4
-python bench.py --steps 2 --warmup 1 --xclamp pointwise --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:advect_fused -s 1 -c 1 -o gpurun_out/prof_fused -f python bench.py --steps 2 --warmup 1 --xclamp pointwise --no-cpu-baseline > gpurun_out/ncu.log 2>&1
-tail -3 gpurun_out/ncu.log
+timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -5
+timeout 600 python - <<'PY'
+import sys; sys.path.insert(0,'scripts'); sys.path.insert(0,'.')
+import probe_perf as p
+for B in (1, 24, 64, 74, 148, 296):
+    p.run('C2', B, 'outer')
+p.run('C2', 148, 'pointwise')
+PY
+for cs in 1 2 8; do LCS_OUTER_CLUSTER=$cs timeout 300 python - <<'PY'
+import sys; sys.path.insert(0,'scripts'); sys.path.insert(0,'.')
+import probe_perf as p
+p.run('C2', 64, 'outer')
+PY
+done

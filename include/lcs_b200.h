@@ -30,6 +30,8 @@ extern "C" {
 
 enum { LCS_OK = 0, LCS_E_INVALID = -1, LCS_E_CUDA = -2, LCS_E_WORKSPACE = -3, LCS_E_UNSUPPORTED = -4 };
 enum { LCS_F64 = 0, LCS_F32 = 1 };
+/* device layouts of a staged wind series, see lcs_pack_pairs / lcs_pack_es */
+enum { LCS_LAYOUT_PAIR4 = 0, LCS_LAYOUT_ES = 1 };
 /* x-boundary of the integrator: trajectory.py:92-97 / 118-123 */
 enum { LCS_X_CYCLIC = 0,          /* cyclic_xboundary=True: the two `where` with Python-sign % 180 */
        LCS_X_CLAMP_POINTWISE = 1, /* per-particle clamp to [lon_min, lon_max] */
@@ -61,11 +63,26 @@ typedef struct lcs_advect_opts {
     int32_t settls_order;   /* accumulating sub-iterations per interval (trajectory.py:100)      */
     int32_t interp_order;   /* 1 or 3 (tools.py:11 `order`)                                       */
     int32_t xmode;          /* LCS_X_*                                                            */
-    int32_t pair_dtype;     /* LCS_F64 or LCS_F32: storage of the packed wind/coefficient pairs   */
-    int32_t strict;         /* 1: accumulate taps as scipy does ((c*wy)*wx, no fused multiply-add) */
+    int32_t strict;         /* 1: accumulate taps as scipy does ((c*wy)*wx, no fused multiply-add,
+                               true divisions); needs LCS_LAYOUT_PAIR4                            */
     int32_t nwindows;       /* independent start times integrated by this call (rolling series)  */
     int32_t level0, level_stride; /* window b starts at packed pair index level0 + b*level_stride  */
 } lcs_advect_opts;
+
+/* Staged winds handed to the integrator.
+ *   LCS_LAYOUT_PAIR4: raw_a / coef_a = pairs[k][lat][lon] = (u_k, v_k, u_{k+1}, v_{k+1}), k < nlev-1;
+ *                     raw_b / coef_b unused.
+ *   LCS_LAYOUT_ES   : raw_a / coef_a = E[k][lat][lon] = (u_k, v_k), k < nlev;
+ *                     raw_b / coef_b = S[k][lat][lon] = (2u_k - u_{k+1}, 2v_k - v_{k+1}), k < nlev-1.
+ * raw_* hold the winds themselves (order-1 pole rows, or interp_order == 1); coef_* their cubic
+ * B-spline coefficients (interp_order == 3, else NULL).  dtype is the element storage type. */
+typedef struct lcs_winds {
+    int32_t layout, dtype;
+    const void* raw_a;
+    const void* raw_b;
+    const void* coef_a;
+    const void* coef_b;
+} lcs_winds;
 
 /* ---------------------------------------------------------------- housekeeping */
 int lcs_abi_version(void);
@@ -88,11 +105,18 @@ int lcs_prefilter(const void* u, const void* v, int in_dtype, double* coef_u, do
 int lcs_pack_pairs(const void* u, const void* v, int in_dtype, void* pairs, int pair_dtype,
                    int nlev, int nlat, int nlon, void* stream);
 
+/* lcs_pack_es: the fast gather layout.  The SETTLS increment needs 2*f_k(pos) - f_{k+1}(pos)
+ * (trajectory.py:110-112); interpolation is linear in the field, so the combination is formed once
+ * per grid point: E[k] = (u_k, v_k) for k < nlev and S[k] = (2u_k - u_{k+1}, 2v_k - v_{k+1}) for
+ * k < nlev-1 (evaluated in f64, then stored as es_dtype).  A SETTLS stage then gathers 16 B (f64)
+ * per tap instead of 32 B. */
+int lcs_pack_es(const void* u, const void* v, int in_dtype, void* e_out, void* s_out, int es_dtype,
+                int nlev, int nlat, int nlon, void* stream);
+
 /* ---------------------------------------------------------------- integrator
  * lcs_advect replaces parcel_propagation's loop, trajectory.py:80-126, together with the
  * xr_map_coordinates calls inside it (tools.py:11-41).
- *   raw_pairs : packed raw winds (always needed: order-1 pole rows, or interp_order == 1)
- *   coef_pairs: packed cubic coefficients (interp_order == 3), else NULL
+ *   w         : staged winds (lcs_pack_pairs or lcs_pack_es, raw and -- for order 3 -- coefficients)
  *   x_out,y_out: device f64 [nwindows][nrow][ncol] final positions
  *   x_traj,y_traj: NULL, or device f64 [nwindows][nsteps+1][nrow][ncol] (level 0 = start grid,
  *                  trajectory.py:76-77,125-126)
@@ -100,7 +124,7 @@ int lcs_pack_pairs(const void* u, const void* v, int in_dtype, void* pairs, int 
  *               needs any: positions, Euler samples and per-sub-step row/column exit flags) */
 size_t lcs_advect_workspace_bytes(const lcs_particles* p, const lcs_advect_opts* o);
 int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_advect_opts* o,
-               const void* raw_pairs, const void* coef_pairs,
+               const lcs_winds* w,
                double* x_out, double* y_out, double* x_traj, double* y_traj,
                void* workspace, size_t workspace_bytes, void* stream);
 
@@ -144,10 +168,11 @@ int lcs_fourth_order_derivative(const float* arr, int n0, int n1, int dim, int i
 int lcs_spectral_norm_3x3(const double* vals, int64_t n, double* out, void* stream);
 
 /* ---------------------------------------------------------------- roofline microbenchmark
- * Same 16-tap x 32-byte (or 4-tap) gather pattern as the integrator on packed pairs, no
- * dependent arithmetic: the measured upper bound for the L1/L2 gather roofline.
- * jitter: displacement amplitude in grid cells applied to the start grid (smooth field). */
-int lcs_gather_peak(const void* pairs, int pair_dtype, int nlat, int nlon, int nrow, int ncol,
+ * Same taps x taps vector-gather pattern as the integrator, no dependent arithmetic: the measured
+ * upper bound for the L1/L2 gather roofline.  vec_width = values per tap (4: PAIR4 elements, 32 B
+ * in f64 -- the reference formulation's bytes; 2: ES elements).  jitter: displacement amplitude in
+ * grid cells applied to the start grid (smooth field). */
+int lcs_gather_peak(const void* pairs, int pair_dtype, int vec_width, int nlat, int nlon, int nrow, int ncol,
                     int nwindows, int taps, double jitter, int iters, double* sink, void* stream);
 
 #ifdef __cplusplus

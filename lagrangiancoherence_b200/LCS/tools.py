@@ -43,7 +43,7 @@ def derivative_spherical_coords(da, dim=0, isglobal=True, *, device='cuda:0'):
     deriv = _engine.fourth_order_derivative_device(np.asarray(da.values).astype('float32'), dim=dim,
                                                    isglobal=isglobal, device=device).double()   # f32 stencil, tools.py:258
     if dim == 0:
-        deriv = deriv / float(dy)                                                              # tools.py:262
+        deriv = deriv / torch.tensor(float(dy), dtype=torch.float64, device=deriv.device)      # tools.py:262 (true division)
     else:
         deriv = deriv / torch.from_numpy(np.ascontiguousarray(dx, dtype=np.float64)).to(deriv.device)[:, None]  # :264
     return make_like(da, deriv.cpu().numpy(), ('latitude', 'longitude'), {'latitude': lat, 'longitude': lon})

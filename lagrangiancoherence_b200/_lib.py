@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, 'liblcs_b200.so')
 
 LCS_F64, LCS_F32 = 0, 1
 LCS_X_CYCLIC, LCS_X_CLAMP_POINTWISE, LCS_X_CLAMP_OUTER = 0, 1, 2
+LCS_LAYOUT_PAIR4, LCS_LAYOUT_ES = 0, 1
 ABI_VERSION = 1
 
 c_void_p, c_int, c_double, c_size_t, c_int64 = C.c_void_p, C.c_int, C.c_double, C.c_size_t, C.c_int64
@@ -30,8 +31,13 @@ class Particles(C.Structure):
 
 class AdvectOpts(C.Structure):
     _fields_ = [('nsteps', C.c_int32), ('settls_order', C.c_int32), ('interp_order', C.c_int32),
-                ('xmode', C.c_int32), ('pair_dtype', C.c_int32), ('strict', C.c_int32),
+                ('xmode', C.c_int32), ('strict', C.c_int32),
                 ('nwindows', C.c_int32), ('level0', C.c_int32), ('level_stride', C.c_int32)]
+
+
+class Winds(C.Structure):
+    _fields_ = [('layout', C.c_int32), ('dtype', C.c_int32),
+                ('raw_a', c_void_p), ('raw_b', c_void_p), ('coef_a', c_void_p), ('coef_b', c_void_p)]
 
 
 # name -> (restype, argtypes): every symbol include/lcs_b200.h declares
@@ -43,7 +49,8 @@ SIGNATURES = {
                               c_int, c_int, c_int, c_void_p]),
     'lcs_pack_pairs': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'lcs_advect_workspace_bytes': (c_size_t, [C.POINTER(Particles), C.POINTER(AdvectOpts)]),
-    'lcs_advect': (c_int, [C.POINTER(Grid), C.POINTER(Particles), C.POINTER(AdvectOpts), c_void_p, c_void_p,
+    'lcs_pack_es': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'lcs_advect': (c_int, [C.POINTER(Grid), C.POINTER(Particles), C.POINTER(AdvectOpts), C.POINTER(Winds),
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     'lcs_ftle_epilogue': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                   c_void_p, c_double, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -51,7 +58,7 @@ SIGNATURES = {
                                     c_int, c_int, c_void_p, c_void_p]),
     'lcs_fourth_order_derivative': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'lcs_spectral_norm_3x3': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
-    'lcs_gather_peak': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int,
+    'lcs_gather_peak': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int,
                                 c_void_p, c_void_p]),
 }
 

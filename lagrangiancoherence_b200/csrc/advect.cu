@@ -8,22 +8,35 @@
 //    particles of a window after every sub-step, so each sub-step is a pair of launches that
 //    meet through per-substep row/column exit flags.
 //
-// Data: packed pairs[k][lat][lon] = (u_k, v_k, u_{k+1}, v_{k+1}); one 32-B (f64) vector load per
-// tap feeds the four operands of a SETTLS stage.  Positions stay in registers in the fused
-// kernel.  Gathers go through the read-only L1 path; the wind pairs of the two active levels
-// are L2-resident (2.9 MB at 281x321, 33 MB at 721x1440).
+// Data, two layouts (include/lcs_b200.h):
+//  * PAIR4: pairs[k][lat][lon] = (u_k, v_k, u_{k+1}, v_{k+1}); one 32-B (f64) vector load per tap
+//    feeds the four operands of a SETTLS stage, which are combined in the reference's order
+//    (bit-faithful `strict` evaluation is only offered here);
+//  * ES   : E[k] = (u_k, v_k) and S[k] = (2u_k - u_{k+1}, 2v_k - v_{k+1}); a SETTLS stage needs one
+//    16-B load per tap -- the kernel is bound by L1 data-pipe wavefronts (ncu: 79 % of peak with
+//    PAIR4), so halving the bytes per tap is the lever that matters.
+// Positions stay in registers in the fused kernel.  Gathers go through the read-only L1 path (L1
+// hit rate 91 %, L2 throughput 5 % in ncu: staging tiles through shared memory/TMA would move the
+// same bytes through the same 128 B/clk port and was not pursued).
+#include <cooperative_groups.h>
 #include "lcs_internal.h"
 #include "lcs_device.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace lcs {
 
 struct AdvectParams {
-    const void* raw;
-    const void* coef;
-    size_t plane;                 // nlat*nlon (elements per packed level)
+    // winds: PAIR4 layout -> raw_a/coef_a = packed pairs; ES layout -> *_a = E levels, *_b = S intervals
+    const void* raw_a;
+    const void* raw_b;
+    const void* coef_a;
+    const void* coef_b;
+    size_t plane;                 // nlat*nlon (elements per level)
     int nlat, nlon;
     double nlat_d, nlon_d;
     double lat_min, lat_span, lon_min, lon_span, lat_max, lon_max;
+    double nlat_over_span, nlon_over_span;
     // particles
     int nrow, ncol, row0, nrow_global;
     int np;                       // nrow*ncol (< 2^31)
@@ -32,7 +45,7 @@ struct AdvectParams {
     const double* kx;
     const double* hx;
     double ky, hy;
-    int nsteps, S, xmode, level0, level_stride, band;
+    int nsteps, S, xmode, level0, level_stride, band, band_log2;
     double* x_out;
     double* y_out;
     double* x_traj;
@@ -44,58 +57,79 @@ struct AdvectParams {
     int* cand_count;              // [nwindows][nsub]
     unsigned char* flags;         // [nwindows][nsub][2][nrow+ncol]
     int nsub;
+    unsigned ncol_magic; int ncol_shift;   // p / ncol for 0 <= p < 2^31, see div_ncol
 };
 
-// Particle enumeration: bands of `band` rows, column-major inside a band, so that a warp covers
-// a (band x 32/band) patch -- smaller unique tap footprint than a 1x32 strip, no idle tail lanes.
-__device__ __forceinline__ void particle_rc(const AdvectParams& P, int p, int& row, int& col) {
-    const int per_band = P.band * P.ncol;
-    const int nbands = (P.nrow + P.band - 1) / P.band;
-    int b = p / per_band;
-    if (b > nbands - 1) b = nbands - 1;
-    const int q = p - b * per_band;
-    const int h = (b == nbands - 1) ? (P.nrow - b * P.band) : P.band;
-    col = q / h;
-    row = b * P.band + (q - col * h);
+constexpr int kPair4 = LCS_LAYOUT_PAIR4, kES = LCS_LAYOUT_ES;
+
+// Thread -> particle: a block is a (band x 256/band) tile of the particle grid, a warp a
+// (band x 32/band) patch (smaller unique tap footprint than a 1x32 strip: better L1 hit rate);
+// grid = (column tiles, row bands, windows), so no integer division is needed.
+__device__ __forceinline__ bool particle_rc(const AdvectParams& P, int& row, int& col) {
+    const int r = threadIdx.x & (P.band - 1);
+    const int c = threadIdx.x >> P.band_log2;
+    row = blockIdx.y * P.band + r;
+    col = blockIdx.x * (256 >> P.band_log2) + c;
+    return row < P.nrow && col < P.ncol;
 }
 
-template <typename T, bool STRICT, int ORDER, int NV>
-__device__ __forceinline__ void sample(const AdvectParams& P, int pair_idx, bool pole, double x, double y,
-                                       double (&out)[NV]) {
-    using PT = typename PairOf<T>::type;
-    const double iy = index_map(y, P.lat_min, P.lat_span, P.nlat_d);
-    const double ix = index_map(x, P.lon_min, P.lon_span, P.nlon_d);
-    if (pole) {
-        gather_linear_constant<T, STRICT, NV>(reinterpret_cast<const PT*>(P.raw) + (size_t)pair_idx * P.plane,
-                                              P.nlat, P.nlon, iy, ix, out);
-    } else if (ORDER == 3) {
-        gather_cubic_wrap<T, STRICT, NV>(reinterpret_cast<const PT*>(P.coef) + (size_t)pair_idx * P.plane,
-                                         P.nlat, P.nlon, iy, ix, out);
+// One xr_map_coordinates evaluation (tools.py:19-41) of the element policy E at (x, y):
+// index map, then the order-1/'constant' branch on pole rows, else order ORDER/'wrap'.
+template <typename E, bool STRICT, int ORDER>
+__device__ __forceinline__ void sample(const AdvectParams& P, const void* raw, const void* coef, int level,
+                                       bool pole, double x, double y, double (&out)[E::NV]) {
+    using ET = typename E::type;
+    double iy, ix;
+    if (STRICT) {
+        iy = index_map(y, P.lat_min, P.lat_span, P.nlat_d);
+        ix = index_map(x, P.lon_min, P.lon_span, P.nlon_d);
     } else {
-        gather_linear_wrap<T, STRICT, NV>(reinterpret_cast<const PT*>(P.raw) + (size_t)pair_idx * P.plane,
+        iy = index_map_fast(y, P.lat_min, P.nlat_over_span);
+        ix = index_map_fast(x, P.lon_min, P.nlon_over_span);
+    }
+    if (pole) {
+        gather_linear_constant<E, STRICT>(reinterpret_cast<const ET*>(raw) + (size_t)level * P.plane,
                                           P.nlat, P.nlon, iy, ix, out);
+    } else if (ORDER == 3) {
+        gather_cubic_wrap<E, STRICT>(reinterpret_cast<const ET*>(coef) + (size_t)level * P.plane,
+                                     P.nlat, P.nlon, iy, ix, out);
+    } else {
+        gather_linear_wrap<E, STRICT>(reinterpret_cast<const ET*>(raw) + (size_t)level * P.plane,
+                                      P.nlat, P.nlon, iy, ix, out);
     }
 }
 
-// Euler stage, trajectory.py:82-87 (sample level k only), boundaries excluded.
-template <typename T, bool STRICT, int ORDER>
-__device__ __forceinline__ void stage_euler(const AdvectParams& P, int pair_idx, bool pole, double kx,
+// Euler stage, trajectory.py:82-87 (samples level k only), boundaries excluded.
+template <typename T, bool STRICT, int ORDER, int LAYOUT>
+__device__ __forceinline__ void stage_euler(const AdvectParams& P, int k, bool pole, double kx,
                                             double& x, double& y, double& ua, double& va) {
     double s[2];
-    sample<T, STRICT, ORDER, 2>(P, pair_idx, pole, x, y, s);
+    if (LAYOUT == kPair4) sample<Pair4Lo<T>, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, s);
+    else sample<Vec2<T>, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, s);
     ua = s[0]; va = s[1];
     y = __dadd_rn(y, __dmul_rn(P.ky, va));
     x = __dadd_rn(x, __dmul_rn(kx, ua));
 }
 
-// SETTLS stage, trajectory.py:105-112: pos += 0.5*dt*conv*(va + 2*v_k(pos) - v_{k+1}(pos))
-template <typename T, bool STRICT, int ORDER>
-__device__ __forceinline__ void stage_settls(const AdvectParams& P, int pair_idx, bool pole, double hx,
+// SETTLS stage, trajectory.py:105-112: pos += 0.5*dt*conv*(va + 2*v_k(pos) - v_{k+1}(pos)).
+// PAIR4: the four samples are taken separately and combined in the reference's order.
+// ES   : interpolation is linear in the field, so S_k = 2*c_k - c_{k+1} is combined once per grid
+//        point at staging time and a single 2-value sample yields 2*v_k(pos) - v_{k+1}(pos):
+//        half the gather bytes and half the FMAs of the stage (results differ by rounding only).
+template <typename T, bool STRICT, int ORDER, int LAYOUT>
+__device__ __forceinline__ void stage_settls(const AdvectParams& P, int k, bool pole, double hx,
                                              double ua, double va, double& x, double& y) {
-    double s[4];
-    sample<T, STRICT, ORDER, 4>(P, pair_idx, pole, x, y, s);
-    y = __dadd_rn(y, __dmul_rn(P.hy, __dsub_rn(__dadd_rn(va, __dmul_rn(2.0, s[1])), s[3])));
-    x = __dadd_rn(x, __dmul_rn(hx, __dsub_rn(__dadd_rn(ua, __dmul_rn(2.0, s[0])), s[2])));
+    if (LAYOUT == kPair4) {
+        double s[4];
+        sample<Pair4<T>, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, s);
+        y = __dadd_rn(y, __dmul_rn(P.hy, __dsub_rn(__dadd_rn(va, __dmul_rn(2.0, s[1])), s[3])));
+        x = __dadd_rn(x, __dmul_rn(hx, __dsub_rn(__dadd_rn(ua, __dmul_rn(2.0, s[0])), s[2])));
+    } else {
+        double s[2];
+        sample<Vec2<T>, STRICT, ORDER>(P, P.raw_b, P.coef_b, k, pole, x, y, s);
+        y = __dadd_rn(y, __dmul_rn(P.hy, __dadd_rn(va, s[1])));
+        x = __dadd_rn(x, __dmul_rn(hx, __dadd_rn(ua, s[0])));
+    }
 }
 
 __device__ __forceinline__ void bounds_local(const AdvectParams& P, double& x, double& y) {
@@ -105,14 +139,12 @@ __device__ __forceinline__ void bounds_local(const AdvectParams& P, double& x, d
 }
 
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool STRICT, int ORDER>
+template <typename T, bool STRICT, int ORDER, int LAYOUT>
 __global__ void __launch_bounds__(256)
 advect_fused_kernel(const AdvectParams P) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int w = blockIdx.y;
-    if (p >= P.np) return;
+    const int w = blockIdx.z;
     int row, col;
-    particle_rc(P, p, row, col);
+    if (!particle_rc(P, row, col)) return;
     const int grow = P.row0 + row;
     const bool pole = (grow < ORDER) || (grow >= P.nrow_global - ORDER);   // tools.py:31-33
     const double kx = __ldg(P.kx + row), hx = __ldg(P.hx + row);
@@ -125,10 +157,10 @@ advect_fused_kernel(const AdvectParams P) {
     const int pair0 = P.level0 + w * P.level_stride;
     for (int t = 0; t < P.nsteps; ++t) {
         double ua, va;
-        stage_euler<T, STRICT, ORDER>(P, pair0 + t, pole, kx, x, y, ua, va);
+        stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair0 + t, pole, kx, x, y, ua, va);
         bounds_local(P, x, y);
         for (int k = 0; k < P.S; ++k) {
-            stage_settls<T, STRICT, ORDER>(P, pair0 + t, pole, hx, ua, va, x, y);
+            stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair0 + t, pole, hx, ua, va, x, y);
             bounds_local(P, x, y);
         }
         if (xt) { xt[(size_t)(t + 1) * P.np] = x; yt[(size_t)(t + 1) * P.np] = y; }
@@ -161,16 +193,13 @@ __device__ __forceinline__ double apply_pending(const AdvectParams& P, int w, in
     return x;
 }
 
-template <typename T, bool STRICT, int ORDER>
+template <typename T, bool STRICT, int ORDER, int LAYOUT>
 __global__ void __launch_bounds__(256)
-advect_phase_move(const AdvectParams P, int q /* global sub-step index */) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int w = blockIdx.y;
-    if (p >= P.np) return;
+advect_phase_move(const AdvectParams P, int q /* global sub-step index */, int t /* interval */, int k /* 0: Euler */) {
+    const int w = blockIdx.z;
     int row, col;
-    particle_rc(P, p, row, col);
-    const int per = 1 + P.S;
-    const int t = q / per, k = q - t * per;          // k == 0: Euler stage
+    if (!particle_rc(P, row, col)) return;
+    const int p = row * P.ncol + col;
     const int grow = P.row0 + row;
     const bool pole = (grow < ORDER) || (grow >= P.nrow_global - ORDER);
     const size_t o = (size_t)w * P.np + p;
@@ -182,18 +211,18 @@ advect_phase_move(const AdvectParams P, int q /* global sub-step index */) {
         x = apply_pending(P, w, q - 1, row, col, s.x); y = s.y;
     }
     if (k == 0 && P.x_traj) {                         // level t is final once the pending passes ran
-        const size_t to = ((size_t)w * (P.nsteps + 1) + t) * P.np + (size_t)row * P.ncol + col;
+        const size_t to = ((size_t)w * (P.nsteps + 1) + t) * P.np + p;
         P.x_traj[to] = x; P.y_traj[to] = y;
     }
     const int pair = P.level0 + w * P.level_stride + t;
     if (k == 0) {
         double ua, va;
-        stage_euler<T, STRICT, ORDER>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
+        stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
         d2 e; e.x = ua; e.y = va;
         P.swind[o] = e;
     } else {
         const d2 e = P.swind[o];
-        stage_settls<T, STRICT, ORDER>(P, pair, pole, __ldg(P.hx + row), e.x, e.y, x, y);
+        stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.hx + row), e.x, e.y, x, y);
     }
     y = clamp_y(y, P.lat_min, P.lat_max);
     d2 s; s.x = x; s.y = y;
@@ -215,8 +244,7 @@ advect_phase_gtpass(const AdvectParams P, int q) {
     unsigned char* gt = flag_slot(P, w, q, 1);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const int p = P.cand[(size_t)w * P.np + i];
-        int row, col;
-        particle_rc(P, p, row, col);
+        const int row = p / P.ncol, col = p - row * P.ncol;
         // x > lon_max here; it survives the x_min pass unless its row and column both hold an exit
         if (!(lt[row] && lt[P.nrow + col])) { gt[row] = 1; gt[P.nrow + col] = 1; }
     }
@@ -224,18 +252,17 @@ advect_phase_gtpass(const AdvectParams P, int q) {
 
 __global__ void __launch_bounds__(256)
 advect_phase_final(const AdvectParams P) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int w = blockIdx.y;
-    if (p >= P.np) return;
+    const int w = blockIdx.z;
     int row, col;
-    particle_rc(P, p, row, col);
+    if (!particle_rc(P, row, col)) return;
+    const int p = row * P.ncol + col;
     double x, y;
     if (P.nsub == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
     else {
         const d2 s = P.spos[(size_t)w * P.np + p];
         x = apply_pending(P, w, P.nsub - 1, row, col, s.x); y = s.y;
     }
-    const size_t o = (size_t)row * P.ncol + col;
+    const size_t o = (size_t)p;
     P.x_out[(size_t)w * P.np + o] = x; P.y_out[(size_t)w * P.np + o] = y;
     if (P.x_traj) {
         const size_t to = ((size_t)w * (P.nsteps + 1) + P.nsteps) * P.np + o;
@@ -244,17 +271,164 @@ advect_phase_final(const AdvectParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool STRICT, int ORDER>
+// Outer-product clamp, persistent form: one thread-block CLUSTER owns one window for its whole
+// integration.  The cluster's threads stride over the window's particles (state in an L2-resident
+// per-window array, touched only by its owner thread), and the two global dependencies of every
+// sub-step -- "rows/columns holding an exit below x_min" and, after that pass, "... above x_max" --
+// are resolved with hardware cluster barriers (barrier.cluster, ~0.2 us) instead of kernel
+// boundaries.  A cluster of 1 degenerates to __syncthreads().  The exit flags of the current
+// sub-step are mirrored into shared memory after each barrier so the per-particle tests are LDS.
+constexpr int kClusterThreads = 512;
+
+__device__ __forceinline__ int div_ncol(const AdvectParams& P, int p) {
+    return P.ncol_magic ? (int)(__umulhi((unsigned)p, P.ncol_magic) >> P.ncol_shift) : (p >> P.ncol_shift);
+}
+
+template <int CS>
+__device__ __forceinline__ void window_sync() {
+    if (CS > 1) cg::this_cluster().sync();     // release/acquire at cluster scope: global writes become visible
+    else __syncthreads();
+}
+
+template <typename T, bool STRICT, int ORDER, int LAYOUT, int CS>
+__global__ void __launch_bounds__(kClusterThreads, 2)
+advect_outer_cluster_kernel(const AdvectParams P) {
+    extern __shared__ unsigned char s_flags[];            // [lt rows | lt cols | gt rows | gt cols]
+    const int w = blockIdx.x / CS;
+    const int rank = blockIdx.x - w * CS;
+    const int tid_w = rank * kClusterThreads + threadIdx.x;
+    const int nthr_w = CS * kClusterThreads;
+    const int nflag = P.nrow + P.ncol;
+    unsigned char* s_lt = s_flags;
+    unsigned char* s_gt = s_flags + nflag;
+    d2* spos = P.spos + (size_t)w * P.np;
+    d2* swind = P.swind + (size_t)w * P.np;
+    int* cand = P.cand + (size_t)w * P.np;
+    const int pair0 = P.level0 + w * P.level_stride;
+    const int per = 1 + P.S;
+    for (int q = 0; q < P.nsub; ++q) {
+        const int t = q / per, k = q - t * per;
+        unsigned char* g_lt = flag_slot(P, w, q, 0);
+        unsigned char* g_gt = flag_slot(P, w, q, 1);
+        int* g_cnt = P.cand_count + (size_t)w * P.nsub + q;
+        // ---- phase A: pending clamps of q-1 (mirrored in smem), stage, y clamp, raise "< x_min" flags
+        for (int p = tid_w; p < P.np; p += nthr_w) {
+            const int row = div_ncol(P, p);
+            const int col = p - row * P.ncol;
+            const int grow = P.row0 + row;
+            const bool pole = (grow < ORDER) || (grow >= P.nrow_global - ORDER);
+            double x, y;
+            if (q == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
+            else {
+                const d2 s = spos[p];
+                x = s.x; y = s.y;
+                if (s_lt[row] && s_lt[P.nrow + col]) x = P.lon_min;      // trajectory.py:96
+                if (s_gt[row] && s_gt[P.nrow + col]) x = P.lon_max;      // trajectory.py:97
+            }
+            if (k == 0 && P.x_traj) {
+                const size_t to = ((size_t)w * (P.nsteps + 1) + t) * P.np + p;
+                P.x_traj[to] = x; P.y_traj[to] = y;
+            }
+            if (k == 0) {
+                double ua, va;
+                stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair0 + t, pole, __ldg(P.kx + row), x, y, ua, va);
+                d2 e; e.x = ua; e.y = va;
+                swind[p] = e;
+            } else {
+                const d2 e = swind[p];
+                stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair0 + t, pole, __ldg(P.hx + row), e.x, e.y, x, y);
+            }
+            y = clamp_y(y, P.lat_min, P.lat_max);
+            d2 s; s.x = x; s.y = y;
+            spos[p] = s;
+            if (x < P.lon_min) { g_lt[row] = 1; g_lt[P.nrow + col] = 1; }
+            else if (x > P.lon_max) cand[atomicAdd(g_cnt, 1)] = p;
+        }
+        window_sync<CS>();
+        // ---- phase B: mirror the "< x_min" flags; candidates that survive that pass raise "> x_max" flags
+        for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_lt[i] = __ldcg(g_lt + i);
+        __syncthreads();
+        const int ncand = __ldcg(g_cnt);
+        for (int i = tid_w; i < ncand; i += nthr_w) {
+            const int p = __ldcg(cand + i);
+            const int row = div_ncol(P, p);
+            const int col = p - row * P.ncol;
+            if (!(s_lt[row] && s_lt[P.nrow + col])) { g_gt[row] = 1; g_gt[P.nrow + col] = 1; }
+        }
+        window_sync<CS>();
+        for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_gt[i] = __ldcg(g_gt + i);
+        __syncthreads();
+    }
+    // ---- final: pending clamps of the last sub-step, outputs
+    for (int p = tid_w; p < P.np; p += nthr_w) {
+        const int row = div_ncol(P, p);
+        const int col = p - row * P.ncol;
+        double x, y;
+        if (P.nsub == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
+        else {
+            const d2 s = spos[p];
+            x = s.x; y = s.y;
+            if (s_lt[row] && s_lt[P.nrow + col]) x = P.lon_min;
+            if (s_gt[row] && s_gt[P.nrow + col]) x = P.lon_max;
+        }
+        P.x_out[(size_t)w * P.np + p] = x; P.y_out[(size_t)w * P.np + p] = y;
+        if (P.x_traj) {
+            const size_t to = ((size_t)w * (P.nsteps + 1) + P.nsteps) * P.np + p;
+            P.x_traj[to] = x; P.y_traj[to] = y;
+        }
+    }
+}
+
+template <typename T, bool STRICT, int ORDER, int LAYOUT, int CS>
+static cudaError_t launch_outer_cluster(const AdvectParams& P, int nwindows, cudaStream_t st) {
+    auto kern = advect_outer_cluster_kernel<T, STRICT, ORDER, LAYOUT, CS>;
+    const size_t smem = 2 * (size_t)(P.nrow + P.ncol);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nwindows * CS));
+    cfg.blockDim = dim3(kClusterThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, P);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool STRICT, int ORDER, int LAYOUT>
 static cudaError_t launch_advect(const AdvectParams& P, int nwindows, cudaStream_t st) {
     const dim3 block(256);
-    const dim3 grid((unsigned)((P.np + 255) / 256), (unsigned)nwindows);
+    const int tw = 256 >> P.band_log2;
+    const dim3 grid((unsigned)((P.ncol + tw - 1) / tw), (unsigned)((P.nrow + P.band - 1) / P.band), (unsigned)nwindows);
     if (P.xmode != LCS_X_CLAMP_OUTER) {
-        advect_fused_kernel<T, STRICT, ORDER><<<grid, block, 0, st>>>(P);
+        advect_fused_kernel<T, STRICT, ORDER, LAYOUT><<<grid, block, 0, st>>>(P);
         return cudaGetLastError();
+    }
+    // Enough windows to fill the machine: one persistent cluster per window (cluster barriers).
+    // Few windows: one launch pair per sub-step over all particles (kernel-boundary barriers).
+    const int mode = lcs_env_int("LCS_OUTER_MODE", 0);          // 0 auto, 1 phased launches, 2 clusters
+    const int slots = lcs_sm_count() * 2;                        // two 512-thread CTAs per SM
+    if (P.nsub > 0 && 2 * (size_t)(P.nrow + P.ncol) <= 64 * 1024 && mode != 1) {
+        int cs = 8;
+        while (cs > 1 && nwindows * cs > slots) cs >>= 1;
+        const int forced = lcs_env_int("LCS_OUTER_CLUSTER", 0);
+        if (forced == 1 || forced == 2 || forced == 4 || forced == 8) cs = forced;
+        if (mode == 2 || nwindows * cs * 2 >= slots) {
+            switch (cs) {
+                case 8: return launch_outer_cluster<T, STRICT, ORDER, LAYOUT, 8>(P, nwindows, st);
+                case 4: return launch_outer_cluster<T, STRICT, ORDER, LAYOUT, 4>(P, nwindows, st);
+                case 2: return launch_outer_cluster<T, STRICT, ORDER, LAYOUT, 2>(P, nwindows, st);
+                default: return launch_outer_cluster<T, STRICT, ORDER, LAYOUT, 1>(P, nwindows, st);
+            }
+        }
     }
     const dim3 ggrid(4, (unsigned)nwindows);
     for (int q = 0; q < P.nsub; ++q) {
-        advect_phase_move<T, STRICT, ORDER><<<grid, block, 0, st>>>(P, q);
+        advect_phase_move<T, STRICT, ORDER, LAYOUT><<<grid, block, 0, st>>>(P, q, q / (1 + P.S), q % (1 + P.S));
         advect_phase_gtpass<<<ggrid, block, 0, st>>>(P, q);
     }
     advect_phase_final<<<grid, block, 0, st>>>(P);
@@ -290,51 +464,72 @@ extern "C" size_t lcs_advect_workspace_bytes(const lcs_particles* p, const lcs_a
 }
 
 extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_advect_opts* o,
-                          const void* raw_pairs, const void* coef_pairs,
+                          const lcs_winds* w,
                           double* x_out, double* y_out, double* x_traj, double* y_traj,
                           void* workspace, size_t workspace_bytes, void* stream) {
-    if (!g || !p || !o || !raw_pairs || !x_out || !y_out) return lcs_fail(LCS_E_INVALID, "lcs_advect: null argument");
+    if (!g || !p || !o || !w || !x_out || !y_out) return lcs_fail(LCS_E_INVALID, "lcs_advect: null argument");
     if (o->interp_order != 1 && o->interp_order != 3)
         return lcs_fail(LCS_E_UNSUPPORTED, "lcs_advect: interp_order must be 1 or 3");
-    if (o->interp_order == 3 && !coef_pairs) return lcs_fail(LCS_E_INVALID, "lcs_advect: coef_pairs required for order 3");
+    if (w->layout != LCS_LAYOUT_PAIR4 && w->layout != LCS_LAYOUT_ES) return lcs_fail(LCS_E_INVALID, "lcs_advect: bad wind layout");
+    if (o->strict && w->layout != LCS_LAYOUT_PAIR4)
+        return lcs_fail(LCS_E_INVALID, "lcs_advect: strict evaluation needs the PAIR4 layout");
+    if (o->nsteps > 0) {
+        if (!w->raw_a || (w->layout == LCS_LAYOUT_ES && !w->raw_b)) return lcs_fail(LCS_E_INVALID, "lcs_advect: raw winds missing");
+        if (o->interp_order == 3 && (!w->coef_a || (w->layout == LCS_LAYOUT_ES && !w->coef_b)))
+            return lcs_fail(LCS_E_INVALID, "lcs_advect: spline coefficients required for order 3");
+    }
     if (g->nlat < 4 || g->nlon < 4) return lcs_fail(LCS_E_INVALID, "lcs_advect: grid must be at least 4x4");
     if (p->nrow < 1 || p->ncol < 1 || o->nwindows < 1 || o->nsteps < 0 || o->settls_order < 0)
         return lcs_fail(LCS_E_INVALID, "lcs_advect: bad sizes");
+    if (o->nwindows > 65535) return lcs_fail(LCS_E_INVALID, "lcs_advect: at most 65535 windows per call");
     if (o->xmode < LCS_X_CYCLIC || o->xmode > LCS_X_CLAMP_OUTER) return lcs_fail(LCS_E_INVALID, "lcs_advect: bad xmode");
     if ((x_traj == nullptr) != (y_traj == nullptr)) return lcs_fail(LCS_E_INVALID, "lcs_advect: x_traj/y_traj must both be set");
     const size_t need = lcs_advect_workspace_bytes(p, o);
     if (need > workspace_bytes || (need && !workspace)) return lcs_fail(LCS_E_WORKSPACE, "lcs_advect: workspace too small");
 
     AdvectParams P{};
-    P.raw = raw_pairs; P.coef = coef_pairs;
+    P.raw_a = w->raw_a; P.raw_b = w->raw_b; P.coef_a = w->coef_a; P.coef_b = w->coef_b;
     P.plane = (size_t)g->nlat * g->nlon;
     P.nlat = g->nlat; P.nlon = g->nlon;
     P.nlat_d = (double)g->nlat; P.nlon_d = (double)g->nlon;
     P.lat_min = g->lat_min; P.lat_max = g->lat_max; P.lat_span = g->lat_max - g->lat_min;
     P.lon_min = g->lon_min; P.lon_max = g->lon_max; P.lon_span = g->lon_max - g->lon_min;
+    P.nlat_over_span = P.nlat_d / P.lat_span; P.nlon_over_span = P.nlon_d / P.lon_span;
     P.nrow = p->nrow; P.ncol = p->ncol; P.row0 = p->row0; P.nrow_global = p->nrow_global;
     if ((long long)p->nrow * p->ncol >= (1LL << 31)) return lcs_fail(LCS_E_INVALID, "lcs_advect: too many particles per window");
     P.np = p->nrow * p->ncol;
     P.lat = p->lat; P.lon = p->lon; P.kx = p->kx; P.hx = p->hx; P.ky = p->ky; P.hy = p->hy;
     P.nsteps = o->nsteps; P.S = o->settls_order; P.xmode = o->xmode;
     P.level0 = o->level0; P.level_stride = o->level_stride;
-    P.band = lcs_env_int("LCS_ADVECT_BAND", 4);
-    if (P.band < 1) P.band = 1;
-    if (P.band > 32) P.band = 32;
+    P.band_log2 = lcs_env_int("LCS_ADVECT_BAND_LOG2", 2);      // tile = 4 rows x 64 columns by default
+    if (P.band_log2 < 0) P.band_log2 = 0;
+    if (P.band_log2 > 5) P.band_log2 = 5;
+    P.band = 1 << P.band_log2;
+    if ((P.nrow + P.band - 1) / P.band > 65535) return lcs_fail(LCS_E_INVALID, "lcs_advect: too many row bands");
     P.x_out = x_out; P.y_out = y_out; P.x_traj = x_traj; P.y_traj = y_traj;
     P.nsub = o->nsteps * (1 + o->settls_order);
+    {   // p / ncol for 0 <= p < 2^31 as a multiply-high: k = floor(log2 ncol), magic = ceil(2^(32+k) / ncol) < 2^32;
+        // the rounding error p*e/(ncol*2^(32+k)) stays below 1/ncol because e < ncol < 2^(k+1) and p < 2^31
+        int k = 0;
+        while ((2LL << k) <= P.ncol) ++k;
+        if ((1LL << k) == P.ncol) { P.ncol_magic = 0; P.ncol_shift = k; }
+        else {
+            P.ncol_magic = (unsigned)(((1ULL << (32 + k)) + (unsigned long long)P.ncol - 1) / (unsigned long long)P.ncol);
+            P.ncol_shift = k;
+        }
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (o->xmode == LCS_X_CLAMP_OUTER) {
         const WsLayout L = ws_layout(p, o);
-        char* w = static_cast<char*>(workspace);
-        P.spos = reinterpret_cast<d2*>(w + L.pos);
-        P.swind = reinterpret_cast<d2*>(w + L.wind);
-        P.cand = reinterpret_cast<int*>(w + L.cand);
-        P.cand_count = reinterpret_cast<int*>(w + L.count);
-        P.flags = reinterpret_cast<unsigned char*>(w + L.flags);
+        char* wsb = static_cast<char*>(workspace);
+        P.spos = reinterpret_cast<d2*>(wsb + L.pos);
+        P.swind = reinterpret_cast<d2*>(wsb + L.wind);
+        P.cand = reinterpret_cast<int*>(wsb + L.cand);
+        P.cand_count = reinterpret_cast<int*>(wsb + L.count);
+        P.flags = reinterpret_cast<unsigned char*>(wsb + L.flags);
         if (P.nsub > 0) {                                     // exit flags and candidate counters start cleared
-            e = cudaMemsetAsync(w + L.count, 0, L.clear_bytes, st);
+            e = cudaMemsetAsync(wsb + L.count, 0, L.clear_bytes, st);
             if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_advect(memset)");
         }
     }
@@ -342,14 +537,20 @@ extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_a
     const int ord = o->interp_order;
 #define LCS_DISPATCH(TT)                                                                      \
     do {                                                                                      \
-        if (ord == 3) e = strict ? launch_advect<TT, true, 3>(P, o->nwindows, st)             \
-                                 : launch_advect<TT, false, 3>(P, o->nwindows, st);           \
-        else e = strict ? launch_advect<TT, true, 1>(P, o->nwindows, st)                      \
-                        : launch_advect<TT, false, 1>(P, o->nwindows, st);                    \
+        if (w->layout == LCS_LAYOUT_ES) {                                                     \
+            e = (ord == 3) ? launch_advect<TT, false, 3, kES>(P, o->nwindows, st)             \
+                           : launch_advect<TT, false, 1, kES>(P, o->nwindows, st);            \
+        } else if (ord == 3) {                                                                \
+            e = strict ? launch_advect<TT, true, 3, kPair4>(P, o->nwindows, st)               \
+                       : launch_advect<TT, false, 3, kPair4>(P, o->nwindows, st);             \
+        } else {                                                                              \
+            e = strict ? launch_advect<TT, true, 1, kPair4>(P, o->nwindows, st)               \
+                       : launch_advect<TT, false, 1, kPair4>(P, o->nwindows, st);             \
+        }                                                                                     \
     } while (0)
-    if (o->pair_dtype == LCS_F64) LCS_DISPATCH(double);
-    else if (o->pair_dtype == LCS_F32) LCS_DISPATCH(float);
-    else return lcs_fail(LCS_E_INVALID, "lcs_advect: bad pair_dtype");
+    if (w->dtype == LCS_F64) LCS_DISPATCH(double);
+    else if (w->dtype == LCS_F32) LCS_DISPATCH(float);
+    else return lcs_fail(LCS_E_INVALID, "lcs_advect: bad wind dtype");
 #undef LCS_DISPATCH
     if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_advect");
     return LCS_OK;

@@ -15,47 +15,78 @@
 
 namespace lcs {
 
-// ------------------------------------------------------------------ packed pair types
-struct __align__(32) d4 { double x, y, z, w; };   // (u_k, v_k, u_{k+1}, v_{k+1}) f64: one 32-B sector
+// ------------------------------------------------------------------ gather element policies
+// A policy names the storage element of one grid point (`type`), how many values a tap yields
+// (`NV`) and how to load them through the read-only path.
+struct __align__(32) d4 { double x, y, z, w; };   // 32-B sector
 struct __align__(16) d2 { double x, y; };
 
-template <typename T> struct PairOf;
-template <> struct PairOf<double> {
-    using type = d4;
-    // 256-bit read-only load (LDG.E.256.CONSTANT on sm_100a): all four SETTLS operands of a tap.
-    static __device__ __forceinline__ void load4(const type* p, double (&o)[4]) {
-        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
-            : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
+template <typename T> struct PairOf;                // 4-wide element (u_k, v_k, u_{k+1}, v_{k+1})
+template <> struct PairOf<double> { using type = d4; };
+template <> struct PairOf<float> { using type = float4; };
+template <typename T> struct Vec2Of;                // 2-wide element
+template <> struct Vec2Of<double> { using type = d2; };
+template <> struct Vec2Of<float> { using type = float2; };
+
+// all four SETTLS operands of a tap with one load (256-bit LDG.E.256.CONSTANT for f64)
+template <typename T> struct Pair4;
+template <> struct Pair4<double> {
+    using type = d4; static constexpr int NV = 4;
+    static __device__ __forceinline__ void ld(const type* p, double (&o)[4]) {
+        asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
     }
-    // first half only (u_k, v_k): the Euler stage samples a single level (trajectory.py:82-84)
-    static __device__ __forceinline__ void load2(const type* p, double (&o)[2]) {
+};
+template <> struct Pair4<float> {
+    using type = float4; static constexpr int NV = 4;
+    static __device__ __forceinline__ void ld(const type* p, double (&o)[4]) {
+        const float4 t = __ldg(p);
+        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+    }
+};
+// first half (u_k, v_k) of a 4-wide element: the Euler stage samples one level (trajectory.py:82-84)
+template <typename T> struct Pair4Lo;
+template <> struct Pair4Lo<double> {
+    using type = d4; static constexpr int NV = 2;
+    static __device__ __forceinline__ void ld(const type* p, double (&o)[2]) {
         asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "l"(p));
     }
 };
-template <> struct PairOf<float> {
-    using type = float4;
-    static __device__ __forceinline__ void load4(const type* p, double (&o)[4]) {
-        float4 t = __ldg(p);
-        o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
-    }
-    static __device__ __forceinline__ void load2(const type* p, double (&o)[2]) {
-        float2 t = __ldg(reinterpret_cast<const float2*>(p));
+template <> struct Pair4Lo<float> {
+    using type = float4; static constexpr int NV = 2;
+    static __device__ __forceinline__ void ld(const type* p, double (&o)[2]) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(p));
         o[0] = t.x; o[1] = t.y;
     }
 };
-
-template <typename T, int NV> struct Loader;
-template <typename T> struct Loader<T, 4> {
-    static __device__ __forceinline__ void ld(const typename PairOf<T>::type* p, double (&o)[4]) { PairOf<T>::load4(p, o); }
+// dense 2-wide element (the E / S arrays of the fast layout): 16 B (f64) or 8 B (f32) per tap
+template <typename T> struct Vec2;
+template <> struct Vec2<double> {
+    using type = d2; static constexpr int NV = 2;
+    static __device__ __forceinline__ void ld(const type* p, double (&o)[2]) {
+        asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "l"(p));
+    }
 };
-template <typename T> struct Loader<T, 2> {
-    static __device__ __forceinline__ void ld(const typename PairOf<T>::type* p, double (&o)[2]) { PairOf<T>::load2(p, o); }
+template <> struct Vec2<float> {
+    using type = float2; static constexpr int NV = 2;
+    static __device__ __forceinline__ void ld(const type* p, double (&o)[2]) {
+        const float2 t = __ldg(p);
+        o[0] = t.x; o[1] = t.y;
+    }
+};
+// planar f64 field, one value per tap (the map_coordinates seam)
+struct Scalar64 {
+    using type = double; static constexpr int NV = 1;
+    static __device__ __forceinline__ void ld(const double* p, double (&o)[1]) { o[0] = __ldg(p); }
 };
 
 // ------------------------------------------------------------------ index arithmetic
 // tools.py:21-22: n * (pos - cmin) / (cmax - cmin)   (n points, not n-1: quirk Q4)
 __device__ __forceinline__ double index_map(double pos, double cmin, double span, double n) {
     return __ddiv_rn(__dmul_rn(n, __dsub_rn(pos, cmin)), span);
+}
+// fast variant: one multiply by the precomputed n/span (differs from the above by <= 1 ulp)
+__device__ __forceinline__ double index_map_fast(double pos, double cmin, double n_over_span) {
+    return (pos - cmin) * n_over_span;
 }
 
 // scipy mode='wrap' coordinate fold: period n-1, result in [0, n-1]
@@ -108,11 +139,14 @@ __device__ __forceinline__ double tap_acc(double t, double c, double wy, double 
 
 // ------------------------------------------------------------------ gathers
 // Cubic B-spline, mode='wrap' (fold period n-1, mirror taps), 4x4 taps in scipy's order
-// (axis-0 index outer, axis-1 inner).  NV = 2: level k only; NV = 4: levels k and k+1.
-template <typename T, bool STRICT, int NV>
-__device__ __forceinline__ void gather_cubic_wrap(const typename PairOf<T>::type* __restrict__ f,
+// (axis-0 index outer, axis-1 inner).  Interior positions (all 16 taps inside the grid, the
+// overwhelmingly common case) take a path with one base address and immediate offsets; the
+// general path reflects every tap index.
+template <typename E, bool STRICT>
+__device__ __forceinline__ void gather_cubic_wrap(const typename E::type* __restrict__ f,
                                                   int nlat, int nlon, double iy, double ix,
-                                                  double (&out)[NV]) {
+                                                  double (&out)[E::NV]) {
+    constexpr int NV = E::NV;
     const double cy = fold_wrap(iy, nlat);
     const double cx = fold_wrap(ix, nlon);
     const double fy = floor(cy), fx = floor(cx);
@@ -120,17 +154,34 @@ __device__ __forceinline__ void gather_cubic_wrap(const typename PairOf<T>::type
     cubic_weights<STRICT>(__dsub_rn(cy, fy), wy);
     cubic_weights<STRICT>(__dsub_rn(cx, fx), wx);
     const int sy = (int)fy - 1, sx = (int)fx - 1;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) out[v] = 0.0;
+    if (sy >= 0 && sy + 3 < nlat && sx >= 0 && sx + 3 < nlon) {
+        const typename E::type* base = f + (size_t)sy * nlon + sx;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            double c[4][NV];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) E::ld(base + j, c[j]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double wyx = wy[i] * wx[j];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) out[v] = tap_acc<STRICT>(out[v], c[j][v], wy[i], wx[j], wyx);
+            }
+            base += nlon;
+        }
+        return;
+    }
     int col[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) col[j] = mirror_idx(sx + j, nlon);
-#pragma unroll
-    for (int v = 0; v < NV; ++v) out[v] = 0.0;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < 4; ++i) {
-        const typename PairOf<T>::type* rowp = f + (size_t)mirror_idx(sy + i, nlat) * nlon;
+        const typename E::type* rowp = f + (size_t)mirror_idx(sy + i, nlat) * nlon;
         double c[4][NV];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) Loader<T, NV>::ld(rowp + col[j], c[j]);
+        for (int j = 0; j < 4; ++j) E::ld(rowp + col[j], c[j]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const double wyx = wy[i] * wx[j];
@@ -141,10 +192,11 @@ __device__ __forceinline__ void gather_cubic_wrap(const typename PairOf<T>::type
 }
 
 // Shared 2x2 tap sum of the order-1 branches (weights (1-y, 1-(1-y)), mirror taps).
-template <typename T, bool STRICT, int NV>
-__device__ __forceinline__ void bilinear_taps(const typename PairOf<T>::type* __restrict__ f,
+template <typename E, bool STRICT>
+__device__ __forceinline__ void bilinear_taps(const typename E::type* __restrict__ f,
                                               int nlat, int nlon, double cy, double cx,
-                                              double (&out)[NV]) {
+                                              double (&out)[E::NV]) {
+    constexpr int NV = E::NV;
     const double fy = floor(cy), fx = floor(cx);
     const double y = __dsub_rn(cy, fy), x = __dsub_rn(cx, fx);
     // scipy: weights[0] = 1 - x; weights[order] = 1 - sum(others)
@@ -157,10 +209,10 @@ __device__ __forceinline__ void bilinear_taps(const typename PairOf<T>::type* __
     for (int v = 0; v < NV; ++v) out[v] = 0.0;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const typename PairOf<T>::type* rowp = f + (size_t)mirror_idx(iy0 + i, nlat) * nlon;
+        const typename E::type* rowp = f + (size_t)mirror_idx(iy0 + i, nlat) * nlon;
         double c[2][NV];
 #pragma unroll
-        for (int j = 0; j < 2; ++j) Loader<T, NV>::ld(rowp + col[j], c[j]);
+        for (int j = 0; j < 2; ++j) E::ld(rowp + col[j], c[j]);
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const double wyx = wy[i] * wx[j];
@@ -171,25 +223,25 @@ __device__ __forceinline__ void bilinear_taps(const typename PairOf<T>::type* __
 }
 
 // order=1, mode='wrap' (interior rows when interp_order == 1)
-template <typename T, bool STRICT, int NV>
-__device__ __forceinline__ void gather_linear_wrap(const typename PairOf<T>::type* __restrict__ f,
+template <typename E, bool STRICT>
+__device__ __forceinline__ void gather_linear_wrap(const typename E::type* __restrict__ f,
                                                    int nlat, int nlon, double iy, double ix,
-                                                   double (&out)[NV]) {
-    bilinear_taps<T, STRICT, NV>(f, nlat, nlon, fold_wrap(iy, nlat), fold_wrap(ix, nlon), out);
+                                                   double (&out)[E::NV]) {
+    bilinear_taps<E, STRICT>(f, nlat, nlon, fold_wrap(iy, nlat), fold_wrap(ix, nlon), out);
 }
 
 // order=1, mode='constant', cval=0: coordinates outside [0, n-1] sample 0 (tools.py:35-39)
-template <typename T, bool STRICT, int NV>
-__device__ __forceinline__ void gather_linear_constant(const typename PairOf<T>::type* __restrict__ f,
+template <typename E, bool STRICT>
+__device__ __forceinline__ void gather_linear_constant(const typename E::type* __restrict__ f,
                                                        int nlat, int nlon, double iy, double ix,
-                                                       double (&out)[NV]) {
+                                                       double (&out)[E::NV]) {
     // written so that NaN coordinates also take the constant branch
     if (!(iy >= 0.0 && iy <= (double)(nlat - 1) && ix >= 0.0 && ix <= (double)(nlon - 1))) {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) out[v] = 0.0;
+        for (int v = 0; v < E::NV; ++v) out[v] = 0.0;
         return;
     }
-    bilinear_taps<T, STRICT, NV>(f, nlat, nlon, iy, ix, out);
+    bilinear_taps<E, STRICT>(f, nlat, nlon, iy, ix, out);
 }
 
 // ------------------------------------------------------------------ boundaries (trajectory.py:89-97)

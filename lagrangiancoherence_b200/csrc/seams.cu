@@ -21,17 +21,20 @@ int lcs_env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
 }
+int lcs_sm_count() {
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
+        else cached = 148;
+    }
+    return cached;
+}
 extern "C" int lcs_abi_version(void) { return LCS_ABI_VERSION; }
 extern "C" const char* lcs_last_error(void) { return g_err; }
 
 namespace lcs {
-
-// planar f64 field viewed through the same gather templates (one value per tap)
-struct scalar64 {};
-template <> struct PairOf<scalar64> { using type = double; };
-template <> struct Loader<scalar64, 1> {
-    static __device__ __forceinline__ void ld(const double* p, double (&o)[1]) { o[0] = __ldg(p); }
-};
 
 struct MapParams {
     const double* field;
@@ -54,9 +57,9 @@ map_coordinates_kernel(const MapParams P) {
     const double iy = index_map(P.pos_y[idx], P.lat_min, P.lat_span, P.nlat_d);   // tools.py:22
     const double ix = index_map(P.pos_x[idx], P.lon_min, P.lon_span, P.nlon_d);   // tools.py:21
     double o[1];
-    if (pole) gather_linear_constant<scalar64, true, 1>(P.field, P.nlat, P.nlon, iy, ix, o);
-    else if (P.order == 3) gather_cubic_wrap<scalar64, true, 1>(P.coef, P.nlat, P.nlon, iy, ix, o);
-    else gather_linear_wrap<scalar64, true, 1>(P.field, P.nlat, P.nlon, iy, ix, o);
+    if (pole) gather_linear_constant<Scalar64, true>(P.field, P.nlat, P.nlon, iy, ix, o);
+    else if (P.order == 3) gather_cubic_wrap<Scalar64, true>(P.coef, P.nlat, P.nlon, iy, ix, o);
+    else gather_linear_wrap<Scalar64, true>(P.field, P.nlat, P.nlon, iy, ix, o);
     P.out[idx] = o[0];
 }
 
@@ -65,26 +68,28 @@ map_coordinates_kernel(const MapParams P) {
 // displaced copy of the start grid), no index folding, no dependent position update: the loads of
 // all `iters` rounds are independent, so the measured rate is what L1/L2 can deliver for this
 // access pattern.  Bytes counted = particles * iters * TAPS^2 * sizeof(pair).
-template <typename T, int TAPS>
+template <typename E, int TAPS>
 __global__ void __launch_bounds__(256)
-gather_peak_kernel(const typename PairOf<T>::type* __restrict__ pairs, int nlat, int nlon,
+gather_peak_kernel(const typename E::type* __restrict__ pairs, int nlat, int nlon,
                    int nrow, int ncol, double jitter, int iters, int band, double* sink) {
-    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long np = (long long)nrow * ncol;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    const int np = nrow * ncol;
     if (p >= np) return;
     const int w = blockIdx.y;
     // banded enumeration identical to the integrator's
-    const long long per_band = (long long)band * ncol;
+    const int per_band = band * ncol;
     const int nbands = (nrow + band - 1) / band;
-    int b = (int)(p / per_band);
+    int b = p / per_band;
     if (b > nbands - 1) b = nbands - 1;
-    const long long q = p - (long long)b * per_band;
+    const int q = p - b * per_band;
     const int h = (b == nbands - 1) ? (nrow - b * band) : band;
-    const int col = (int)(q / h);
-    const int row = b * band + (int)(q - (long long)col * h);
+    const int col = q / h;
+    const int row = b * band + (q - col * h);
     const double sy = (double)(nlat - 1) / (double)(nrow > 1 ? nrow - 1 : 1);
     const double sx = (double)(nlon - 1) / (double)(ncol > 1 ? ncol - 1 : 1);
-    double acc[4] = {0, 0, 0, 0};
+    double acc[E::NV];
+#pragma unroll
+    for (int v = 0; v < E::NV; ++v) acc[v] = 0.0;
     for (int it = 0; it < iters; ++it) {
         const double ph = 0.37 * (it + 1) + 0.11 * w;
         const double fy = row * sy + jitter * sin(0.05 * col + ph);
@@ -92,20 +97,22 @@ gather_peak_kernel(const typename PairOf<T>::type* __restrict__ pairs, int nlat,
         int iy = (int)floor(fy) - (TAPS / 2 - 1), ix = (int)floor(fx) - (TAPS / 2 - 1);
         iy = max(0, min(iy, nlat - TAPS));
         ix = max(0, min(ix, nlon - TAPS));
-        const typename PairOf<T>::type* base = pairs + (size_t)iy * nlon + ix;
+        const typename E::type* base = pairs + (size_t)iy * nlon + ix;
 #pragma unroll
         for (int i = 0; i < TAPS; ++i) {
-            double c[TAPS][4];
+            double c[TAPS][E::NV];
 #pragma unroll
-            for (int j = 0; j < TAPS; ++j) Loader<T, 4>::ld(base + (size_t)i * nlon + j, c[j]);
+            for (int j = 0; j < TAPS; ++j) E::ld(base + (size_t)i * nlon + j, c[j]);
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) {
 #pragma unroll
-                for (int v = 0; v < 4; ++v) acc[v] += c[j][v];
+                for (int v = 0; v < E::NV; ++v) acc[v] += c[j][v];
             }
         }
     }
-    const double s = acc[0] + acc[1] + acc[2] + acc[3];
+    double s = 0.0;
+#pragma unroll
+    for (int v = 0; v < E::NV; ++v) s += acc[v];
     if (s == 1.2345e308) sink[0] = s;                     // keeps the loads alive, never true
 }
 
@@ -134,26 +141,28 @@ extern "C" int lcs_map_coordinates(const lcs_grid* g, const double* field, const
     return LCS_OK;
 }
 
-extern "C" int lcs_gather_peak(const void* pairs, int pair_dtype, int nlat, int nlon, int nrow, int ncol,
+extern "C" int lcs_gather_peak(const void* pairs, int pair_dtype, int vec_width, int nlat, int nlon, int nrow, int ncol,
                                int nwindows, int taps, double jitter, int iters, double* sink, void* stream) {
     if (!pairs || !sink) return lcs_fail(LCS_E_INVALID, "lcs_gather_peak: null argument");
     if (nlat < 4 || nlon < 4 || nrow < 1 || ncol < 1 || nwindows < 1 || iters < 1)
         return lcs_fail(LCS_E_INVALID, "lcs_gather_peak: bad sizes");
+    if ((taps != 2 && taps != 4) || (vec_width != 2 && vec_width != 4) || (pair_dtype != LCS_F64 && pair_dtype != LCS_F32))
+        return lcs_fail(LCS_E_INVALID, "lcs_gather_peak: taps and vec_width must be 2 or 4");
     const long long np = (long long)nrow * ncol;
     const dim3 grid((unsigned)((np + 255) / 256), (unsigned)nwindows);
     int band = lcs_env_int("LCS_ADVECT_BAND", 4);
     if (band < 1) band = 1;
     if (band > 32) band = 32;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (pair_dtype == LCS_F64 && taps == 4)
-        gather_peak_kernel<double, 4><<<grid, 256, 0, st>>>((const d4*)pairs, nlat, nlon, nrow, ncol, jitter, iters, band, sink);
-    else if (pair_dtype == LCS_F64 && taps == 2)
-        gather_peak_kernel<double, 2><<<grid, 256, 0, st>>>((const d4*)pairs, nlat, nlon, nrow, ncol, jitter, iters, band, sink);
-    else if (pair_dtype == LCS_F32 && taps == 4)
-        gather_peak_kernel<float, 4><<<grid, 256, 0, st>>>((const float4*)pairs, nlat, nlon, nrow, ncol, jitter, iters, band, sink);
-    else if (pair_dtype == LCS_F32 && taps == 2)
-        gather_peak_kernel<float, 2><<<grid, 256, 0, st>>>((const float4*)pairs, nlat, nlon, nrow, ncol, jitter, iters, band, sink);
-    else return lcs_fail(LCS_E_INVALID, "lcs_gather_peak: taps must be 2 or 4");
+#define LCS_GP(EL, TP) gather_peak_kernel<EL, TP><<<grid, 256, 0, st>>>((const EL::type*)pairs, nlat, nlon, nrow, ncol, jitter, iters, band, sink)
+    if (pair_dtype == LCS_F64) {
+        if (vec_width == 4) { if (taps == 4) LCS_GP(Pair4<double>, 4); else LCS_GP(Pair4<double>, 2); }
+        else { if (taps == 4) LCS_GP(Vec2<double>, 4); else LCS_GP(Vec2<double>, 2); }
+    } else {
+        if (vec_width == 4) { if (taps == 4) LCS_GP(Pair4<float>, 4); else LCS_GP(Pair4<float>, 2); }
+        else { if (taps == 4) LCS_GP(Vec2<float>, 4); else LCS_GP(Vec2<float>, 2); }
+    }
+#undef LCS_GP
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_gather_peak");
     return LCS_OK;

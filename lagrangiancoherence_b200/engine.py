@@ -41,10 +41,22 @@ def _dtype_code(t):
 
 @dataclass
 class StagedWinds:
-    """Packed gather layouts of a wind series on the device (see lcs_pack_pairs)."""
-    raw_pairs: torch.Tensor            # [nlev-1, nlat, nlon, 4]
-    coef_pairs: torch.Tensor | None    # same, cubic B-spline coefficients (interp_order == 3)
+    """Gather layouts of a wind series on the device (lcs_pack_pairs / lcs_pack_es).
+
+    PAIR4: ``raw_a``/``coef_a`` = ``[nlev-1, nlat, nlon, 4]`` pairs.
+    ES   : ``raw_a``/``coef_a`` = E ``[nlev, nlat, nlon, 2]``, ``raw_b``/``coef_b`` = S ``[nlev-1, nlat, nlon, 2]``.
+    """
+    layout: int
+    dtype: int
     nlev: int
+    raw_a: torch.Tensor | None = None
+    raw_b: torch.Tensor | None = None
+    coef_a: torch.Tensor | None = None
+    coef_b: torch.Tensor | None = None
+
+    def struct(self):
+        p = lambda t: t.data_ptr() if t is not None else None
+        return _lib.Winds(self.layout, self.dtype, p(self.raw_a), p(self.raw_b), p(self.coef_a), p(self.coef_b))
 
 
 class FtleEngine:
@@ -59,7 +71,7 @@ class FtleEngine:
     """
 
     def __init__(self, lat, lon, timestep, SETTLS_order=0, interp_order=3, xmode='outer',
-                 pair_dtype='f64', strict=False, device='cuda:0', part_lat=None, part_lon=None):
+                 pair_dtype='f64', strict=False, device='cuda:0', part_lat=None, part_lon=None, layout='es'):
         if not torch.cuda.is_available():
             raise _lib.LcsError('lagrangiancoherence_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
         self.lib = _lib.load()
@@ -78,6 +90,7 @@ class FtleEngine:
         self.xmode = XMODES[xmode]
         self.pair_dtype = DTYPES[pair_dtype]
         self.strict = int(bool(strict))
+        self.layout = _lib.LCS_LAYOUT_PAIR4 if self.strict or layout == 'pair4' else _lib.LCS_LAYOUT_ES
         self.grid = _lib.Grid(self.nlat, self.nlon, self.lat.min(), self.lat.max(), self.lon.min(), self.lon.max())
         self.part_lat = self.lat if part_lat is None else np.ascontiguousarray(part_lat, dtype=np.float64)
         self.part_lon = self.lon if part_lon is None else np.ascontiguousarray(part_lon, dtype=np.float64)
@@ -108,25 +121,40 @@ class FtleEngine:
             raise ValueError(f'winds must be [nlev, {self.nlat}, {self.nlon}], got {tuple(u.shape)} / {tuple(v.shape)}')
         nlev = u.shape[0]
         if nlev < 2:
-            return StagedWinds(None, None, nlev)
+            return StagedWinds(self.layout, self.pair_dtype, nlev)
         tdt = torch.float64 if self.pair_dtype == _lib.LCS_F64 else torch.float32
+        shape2 = (self.nlat, self.nlon)
         with torch.cuda.device(self.device):
             st = _stream(self.device)
-            raw = torch.empty((nlev - 1, self.nlat, self.nlon, 4), dtype=tdt, device=self.device)
-            _lib.check(self.lib.lcs_pack_pairs(_ptr(u), _ptr(v), _dtype_code(u), _ptr(raw), self.pair_dtype,
-                                               nlev, self.nlat, self.nlon, st), 'lcs_pack_pairs')
-            coef = None
+            cu = cv = None
             if self.order == 3:
-                cu = torch.empty((nlev, self.nlat, self.nlon), dtype=torch.float64, device=self.device)
+                cu = torch.empty((nlev,) + shape2, dtype=torch.float64, device=self.device)
                 cv = torch.empty_like(cu)
                 scratch = torch.empty((2,) + tuple(cu.shape), dtype=torch.float64, device=self.device)
                 _lib.check(self.lib.lcs_prefilter(_ptr(u), _ptr(v), _dtype_code(u), _ptr(cu), _ptr(cv),
                                                   _ptr(scratch), scratch.numel() * 8,
                                                   nlev, self.nlat, self.nlon, st), 'lcs_prefilter')
-                coef = torch.empty_like(raw)
-                _lib.check(self.lib.lcs_pack_pairs(_ptr(cu), _ptr(cv), _lib.LCS_F64, _ptr(coef), self.pair_dtype,
-                                                   nlev, self.nlat, self.nlon, st), 'lcs_pack_pairs')
-        return StagedWinds(raw, coef, nlev)
+            if self.layout == _lib.LCS_LAYOUT_PAIR4:
+                def pack(a, b, code):
+                    out = torch.empty((nlev - 1,) + shape2 + (4,), dtype=tdt, device=self.device)
+                    _lib.check(self.lib.lcs_pack_pairs(_ptr(a), _ptr(b), code, _ptr(out), self.pair_dtype,
+                                                       nlev, self.nlat, self.nlon, st), 'lcs_pack_pairs')
+                    return out
+                raw = pack(u, v, _dtype_code(u))
+                coef = pack(cu, cv, _lib.LCS_F64) if cu is not None else None
+                return StagedWinds(self.layout, self.pair_dtype, nlev, raw_a=raw, coef_a=coef)
+
+            def pack_es(a, b, code):
+                e = torch.empty((nlev,) + shape2 + (2,), dtype=tdt, device=self.device)
+                s_ = torch.empty((nlev - 1,) + shape2 + (2,), dtype=tdt, device=self.device)
+                _lib.check(self.lib.lcs_pack_es(_ptr(a), _ptr(b), code, _ptr(e), _ptr(s_), self.pair_dtype,
+                                                nlev, self.nlat, self.nlon, st), 'lcs_pack_es')
+                return e, s_
+            re_, rs_ = pack_es(u, v, _dtype_code(u))
+            ce_ = cs_ = None
+            if cu is not None:
+                ce_, cs_ = pack_es(cu, cv, _lib.LCS_F64)
+            return StagedWinds(self.layout, self.pair_dtype, nlev, raw_a=re_, raw_b=rs_, coef_a=ce_, coef_b=cs_)
 
     def _to_device(self, a):
         if isinstance(a, torch.Tensor):
@@ -167,7 +195,7 @@ class FtleEngine:
             part = _lib.Particles(nrow, ncol, r0, self.part_lat.size,
                                   self.d_plat[r0:].data_ptr(), self.d_plon.data_ptr(),
                                   self.d_kx[r0:].data_ptr(), self.d_hx[r0:].data_ptr(), self.ky, self.hy)
-            opts = _lib.AdvectOpts(nsteps, self.S, self.order, self.xmode, self.pair_dtype, self.strict,
+            opts = _lib.AdvectOpts(nsteps, self.S, self.order, self.xmode, self.strict,
                                    nwindows, level0, level_stride)
             need = self.lib.lcs_advect_workspace_bytes(C.byref(part), C.byref(opts))
             ws = None
@@ -175,11 +203,8 @@ class FtleEngine:
                 if self._ws is None or self._ws.numel() < need:
                     self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
                 ws = self._ws
-            if nsteps > 0:
-                raw, coef = staged.raw_pairs, staged.coef_pairs
-            else:   # nothing is sampled: any valid pointer will do
-                raw = coef = x
-            _lib.check(self.lib.lcs_advect(C.byref(self.grid), C.byref(part), C.byref(opts), _ptr(raw), _ptr(coef),
+            winds = staged.struct()
+            _lib.check(self.lib.lcs_advect(C.byref(self.grid), C.byref(part), C.byref(opts), C.byref(winds),
                                            _ptr(x), _ptr(y), _ptr(xt), _ptr(yt), _ptr(ws), need,
                                            _stream(self.device)), 'lcs_advect')
         return (x, y, xt, yt) if return_traj else (x, y)

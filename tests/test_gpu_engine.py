@@ -57,14 +57,14 @@ def test_map_coordinates_seam(cuda_device, order):
 @pytest.mark.parametrize('xmode,cyclic,xclamp', [('cyclic', True, 'outer'), ('pointwise', False, 'pointwise'),
                                                  ('outer', False, 'outer')])
 @pytest.mark.parametrize('order', [1, 3])
-@pytest.mark.parametrize('strict', [True, False])
-def test_advect_matches_oracle(cuda_device, xmode, cyclic, xclamp, order, strict):
+@pytest.mark.parametrize('strict,layout', [(True, 'pair4'), (False, 'pair4'), (False, 'es')])
+def test_advect_matches_oracle(cuda_device, xmode, cyclic, xclamp, order, strict, layout):
     from lagrangiancoherence_b200.engine import FtleEngine
     u, v, lat, lon = small_case()
     dt = -21600
     rx, ry = O.parcel_propagation(u, v, lat, lon, dt, SETTLS_order=4, interp_order=order,
                                   cyclic_xboundary=cyclic, xclamp=xclamp, return_traj=True)
-    eng = FtleEngine(lat, lon, dt, SETTLS_order=4, interp_order=order, xmode=xmode, strict=strict, device=cuda_device)
+    eng = FtleEngine(lat, lon, dt, SETTLS_order=4, interp_order=order, xmode=xmode, strict=strict, layout=layout, device=cuda_device)
     st = eng.stage(u, v)
     x, y, xt, yt = eng.advect(st, return_traj=True)
     x, y, xt, yt = (t.cpu().numpy() for t in (x, y, xt, yt))
@@ -92,3 +92,25 @@ def test_epilogue_matches_oracle(cuda_device):
     ok = np.abs(sigma - ref_sigma) <= 1e-5 * np.abs(ref_sigma) + 1e-12
     assert ok.mean() >= 0.999, ok.mean()
     assert np.nanmax(np.abs(sigma - ref_sigma) / (np.abs(ref_sigma) + 1e-30)) <= 1e-3
+
+
+@pytest.mark.parametrize('cs', [1, 2, 4, 8])
+def test_outer_clamp_cluster_kernel_equals_phased_launches(cuda_device, cs, monkeypatch):
+    """The persistent cluster-per-window kernel and the launch-per-sub-step path implement the same
+    orthogonal clamp: identical arithmetic, so results must be bit-identical, and both match the oracle."""
+    from lagrangiancoherence_b200.engine import FtleEngine
+    lat = np.linspace(-30.0, 10.0, 41)
+    lon = np.linspace(-80.0, -24.0, 57)
+    u, v = S.era5_like_winds(lat, lon, 7)
+    eng = FtleEngine(lat, lon, -21600, SETTLS_order=4, xmode='outer', device=cuda_device)
+    st = eng.stage(u, v)
+    monkeypatch.setenv('LCS_OUTER_MODE', '1')
+    xa, ya, xta, yta = eng.advect(st, nsteps=4, nwindows=3, return_traj=True)
+    monkeypatch.setenv('LCS_OUTER_MODE', '2')
+    monkeypatch.setenv('LCS_OUTER_CLUSTER', str(cs))
+    xb, yb, xtb, ytb = eng.advect(st, nsteps=4, nwindows=3, return_traj=True)
+    assert torch.equal(xa, xb) and torch.equal(ya, yb) and torch.equal(xta, xtb) and torch.equal(yta, ytb)
+    for w in range(3):
+        rx, ry = O.parcel_propagation(u[w:w + 5], v[w:w + 5], lat, lon, -21600, SETTLS_order=4, xclamp='outer')
+        assert (rel_err(xb[w].cpu().numpy(), rx, np.abs(lon).max()) > REL_POS).mean() <= 1e-3
+        assert (rel_err(yb[w].cpu().numpy(), ry, np.abs(lat).max()) > REL_POS).mean() <= 1e-3
