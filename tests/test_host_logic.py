@@ -1,0 +1,112 @@
+"""CPU-only checks: the C-ABI library builds, loads and exports every symbol include/lcs_b200.h declares
+(no compute calls), the labelled-array shim, the sharding planners, and loud failure without a GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib_path():
+    from lagrangiancoherence_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    header = open(os.path.join(ROOT, 'include', 'lcs_b200.h')).read()
+    header = re.sub(r'/\*.*?\*/', '', header, flags=re.S)
+    declared = set(re.findall(r'\b(lcs_[a-z0-9_]+)\s*\(', header))
+    assert {'lcs_prefilter', 'lcs_pack_pairs', 'lcs_pack_es', 'lcs_advect', 'lcs_ftle_epilogue', 'lcs_map_coordinates',
+            'lcs_fourth_order_derivative', 'lcs_spectral_norm_3x3', 'lcs_gather_peak'} <= declared
+    handle = ctypes.CDLL(lib_path)
+    for name in declared:
+        assert hasattr(handle, name), f'{name} declared in lcs_b200.h but not exported'
+    from lagrangiancoherence_b200 import _lib
+    assert set(_lib.SIGNATURES) == declared          # the ctypes binding covers the whole header
+    handle.lcs_abi_version.restype = ctypes.c_int
+    assert handle.lcs_abi_version() == _lib.ABI_VERSION
+
+
+def test_ctypes_structs_match_the_header_layout(lib_path):
+    from lagrangiancoherence_b200 import _lib
+    assert ctypes.sizeof(_lib.Grid) == 8 + 4 * 8
+    assert ctypes.sizeof(_lib.Particles) == 16 + 4 * 8 + 2 * 8
+    assert ctypes.sizeof(_lib.AdvectOpts) == 8 * 4
+    assert ctypes.sizeof(_lib.Winds) == 8 + 4 * 8
+
+
+def test_argument_validation_without_a_gpu(lib_path):
+    """Entry points reject bad arguments before touching the device (safe to call on a CPU-only box)."""
+    from lagrangiancoherence_b200 import _lib
+    lib = _lib.load()
+    assert lib.lcs_prefilter(None, None, 0, None, None, None, 0, 1, 8, 8, None) == -1
+    assert b'null' in lib.lcs_last_error()
+    assert lib.lcs_pack_pairs(None, None, 0, None, 0, 2, 8, 8, None) == -1
+    assert lib.lcs_ftle_epilogue(None, None, 1, 8, 8, 0, 8, 0, 8, None, 1.0, None, 0, None, None, None, None) == -1
+    assert lib.lcs_prefilter_scratch_bytes(3, 10, 20) == 2 * 3 * 10 * 20 * 8
+    part = _lib.Particles(10, 20, 0, 10, None, None, None, None, 1.0, 0.5)
+    opts = _lib.AdvectOpts(8, 4, 3, _lib.LCS_X_CLAMP_POINTWISE, 0, 1, 0, 1)
+    assert lib.lcs_advect_workspace_bytes(ctypes.byref(part), ctypes.byref(opts)) == 0
+    opts.xmode = _lib.LCS_X_CLAMP_OUTER
+    assert lib.lcs_advect_workspace_bytes(ctypes.byref(part), ctypes.byref(opts)) > 10 * 20 * 32
+
+
+def test_engine_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    from lagrangiancoherence_b200 import _lib
+    from lagrangiancoherence_b200.engine import FtleEngine
+    with pytest.raises(_lib.LcsError, match='no CPU path'):
+        FtleEngine(np.linspace(0, 1, 8), np.linspace(0, 1, 8), 1.0)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'lagrangiancoherence_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f'{f} imports the oracle'
+
+
+# ------------------------------------------------------------------ labelled arrays
+def test_dataarray_shim_semantics():
+    from lagrangiancoherence_b200 import DataArray, Dataset
+    lat, lon, t = np.array([3., 1., 2.]), np.array([10., 20.]), np.arange(4)
+    a = DataArray(np.arange(24.).reshape(4, 3, 2), ('time', 'latitude', 'longitude'),
+                  {'time': t, 'latitude': lat, 'longitude': lon})
+    s = a.sortby('latitude')
+    assert np.array_equal(s.coords['latitude'], [1., 2., 3.]) and np.array_equal(s.values[0, :, 0], [2., 4., 0.])
+    assert a.transpose('latitude', 'time', 'longitude').shape == (3, 4, 2)
+    assert a.isel(time=0).dims == ('latitude', 'longitude') and a.isel({'time': slice(1, 3)}).shape == (2, 3, 2)
+    assert np.array_equal(a.latitude.values, lat) and a['time'].shape == (4,)
+    half_log = np.log(a + 1) / 2
+    assert isinstance(half_log, DataArray) and half_log.dims == a.dims
+    c = a.copy(data=np.zeros_like(a.values))
+    assert c.values.sum() == 0 and a.values.sum() != 0
+    assert a.expand_dims('x').shape == (1, 4, 3, 2)
+    ds = Dataset({'u': a, 'v': a})
+    assert ds.u is a and ds.copy().v is not a
+    with pytest.raises(ValueError):
+        DataArray(np.zeros((2, 2)), ('a',))
+
+
+# ------------------------------------------------------------------ sharding planners
+def test_shard_planners_cover_everything_exactly_once():
+    from lagrangiancoherence_b200.rolling import shard_rows, shard_starts, chunk_starts
+    for n in (1, 7, 8, 281, 721, 8760):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [shard_starts(n, world, r) for r in range(world)]
+            assert sum(c for _, c in blocks) == n
+            assert all(blocks[i][0] + blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
+            rows = [shard_rows(n, world, r) for r in range(world)]
+            assert rows[0][0] == 0 and rows[-1][1] == n
+            for o0, o1, i0, i1 in rows:
+                assert i0 == max(0, o0 - 2) and i1 == min(n, o1 + 2)        # 2-row halo: y-stencil spans +-2 rows
+    assert chunk_starts(5, 10, 4) == [(5, 4), (9, 4), (13, 2)]
