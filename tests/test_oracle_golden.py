@@ -1,0 +1,77 @@
+"""The oracle against outputs of the UNMODIFIED reference (run under oracle/refshim by oracle/make_golden.py,
+fixtures committed under tests/golden/).  The oracle calls the same scipy/numba arithmetic in the same order, so
+agreement is demanded bit for bit."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import lcs_oracle as O
+from oracle.make_golden import CASES, make_inputs
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + '.npz'))
+
+
+def test_manifest_matches_the_generator():
+    manifest = json.load(open(os.path.join(GOLDEN, 'manifest.json')))
+    assert {k: v for k, v in manifest.items() if k != '_meta'} == json.loads(json.dumps(CASES))
+    assert manifest['_meta']['scipy'] == '1.18.1'        # the oracle's pinned third-party versions
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_oracle_reproduces_reference_bitwise(name):
+    case, g = CASES[name], load(name)
+    u, v, lat, lon, time = make_inputs(case)
+    x, y = O.parcel_propagation(u, v, lat, lon, case['timestep'], SETTLS_order=case['S'], interp_order=case['order'],
+                                cyclic_xboundary=case['cyclic'], xclamp='outer', return_traj=True)
+    if 'x_traj' in g:
+        lv = g['traj_levels']
+        assert np.array_equal(x[lv], g['x_traj']) and np.array_equal(y[lv], g['y_traj'])
+        labels = time[::-1] if case['timestep'] < 0 else time              # trajectory.py:59-60
+        assert np.array_equal(g['traj_time'], labels.astype('int64'))
+    assert np.array_equal(x[-1], g['x_dep']) and np.array_equal(y[-1], g['y_dep'])
+    sigma = O.lcs_field(u, v, lat, lon, case['timestep'], SETTLS_order=case['S'], traj_interp_order=case['order'],
+                        cyclic_xboundary=case['cyclic'])
+    assert np.array_equal(sigma, g['sigma'][0], equal_nan=True)
+    assert np.array_equal(g['sigma_lat'], lat) and np.array_equal(g['sigma_lon'], lon)     # ascending, whatever came in
+    stamp = time[-1] if case['timestep'] > 0 else time[0]                    # LCS.py:158
+    assert g['sigma_time'][0] == stamp.astype('int64')
+    if 'def_tensor' in g:
+        assert np.array_equal(O.flowmap_gradient(x[-1], y[-1], lat, lon), g['def_tensor'])
+
+
+def test_seams_reproduce_reference_bitwise():
+    g = load('seams')
+    case = CASES['regional_outer_p3']
+    u, v, lat, lon, _ = make_inputs(case)
+    for order in (1, 3):
+        assert np.array_equal(O.xr_map_coordinates(u[0], g['px'], g['py'], lat, lon, order=order), g[f'map_coordinates_p{order}'])
+    for dim in (0, 1):
+        assert np.array_equal(O.derivative_spherical_coords(g['X'], lat, lon, dim=dim), g[f'derivative_spherical_dim{dim}'])
+        for isglobal in (True, False):
+            ref = g[f'fourth_order_dim{dim}_global{int(isglobal)}']      # the reference's own numba function
+            assert ref.dtype == np.float32
+            assert np.array_equal(O.fourth_order_derivative(g['X'].astype('float32'), dim=dim, isglobal=isglobal), ref)
+    sub = {'latitude': slice(-20, 0), 'longitude': slice(-70, -40)}
+    sigma = O.lcs_field(u, v, lat, lon, case['timestep'], SETTLS_order=case['S'], subdomain=sub)
+    keep = O.subdomain_mask(lat, lon, sub)
+    rows, cols = keep.any(1), keep.any(0)
+    assert np.array_equal(g['subdomain_lat'], lat[rows]) and np.array_equal(g['subdomain_lon'], lon[cols])
+    assert np.array_equal(sigma[rows][:, cols], g['subdomain_sigma'][0])
+
+
+def test_outer_clamp_is_what_the_reference_executes():
+    """On the exiting-particles case the pointwise clamp does NOT reproduce the reference, the outer-product one does."""
+    case, g = CASES['regional_outer_p3'], load('regional_outer_p3')
+    u, v, lat, lon, _ = make_inputs(case)
+    xp, _ = O.parcel_propagation(u, v, lat, lon, case['timestep'], SETTLS_order=case['S'], xclamp='pointwise')
+    assert (xp != g['x_dep']).mean() > 0.01
+    case, g = CASES['regional_contained'], load('regional_contained')
+    u, v, lat, lon, _ = make_inputs(case)
+    xp, _ = O.parcel_propagation(u, v, lat, lon, case['timestep'], SETTLS_order=case['S'], xclamp='pointwise')
+    assert np.array_equal(xp, g['x_dep'])
