@@ -87,6 +87,8 @@ typedef struct lcs_winds {
 /* ---------------------------------------------------------------- housekeeping */
 int lcs_abi_version(void);
 const char* lcs_last_error(void);
+/* kernels launched by this library since it was loaded (all threads); evidence for bench.py's gpu_launches */
+unsigned long long lcs_kernel_launches(void);
 
 /* ---------------------------------------------------------------- wind staging
  * lcs_prefilter: cubic B-spline coefficients of every level, mirror boundary, latitude axis then

@@ -44,6 +44,7 @@ class Winds(C.Structure):
 SIGNATURES = {
     'lcs_abi_version': (c_int, []),
     'lcs_last_error': (C.c_char_p, []),
+    'lcs_kernel_launches': (C.c_ulonglong, []),
     'lcs_prefilter_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
     'lcs_prefilter': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                               c_int, c_int, c_int, c_void_p]),

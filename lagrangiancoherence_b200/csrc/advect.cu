@@ -57,7 +57,8 @@ struct AdvectParams {
     int* cand_count;              // [nwindows][nsub]
     unsigned char* flags;         // [nwindows][nsub][2][nrow+ncol]
     int nsub;
-    unsigned ncol_magic; int ncol_shift;   // p / ncol for 0 <= p < 2^31, see div_ncol
+    int nslots, ntc;                       // persistent kernel: slots per window (tiles of 2x16), tile columns
+    unsigned ntc_magic; int ntc_shift;     // tile / ntc as a multiply-high, see slot_rc
 };
 
 constexpr int kPair4 = LCS_LAYOUT_PAIR4, kES = LCS_LAYOUT_ES;
@@ -280,14 +281,61 @@ advect_phase_final(const AdvectParams P) {
 // sub-step are mirrored into shared memory after each barrier so the per-particle tests are LDS.
 constexpr int kClusterThreads = 512;
 
-__device__ __forceinline__ int div_ncol(const AdvectParams& P, int p) {
-    return P.ncol_magic ? (int)(__umulhi((unsigned)p, P.ncol_magic) >> P.ncol_shift) : (p >> P.ncol_shift);
+// Slot enumeration of a window for the persistent kernel: warp-sized tiles of 2 rows x 16 columns
+// (6 L1 wavefronts per 16-B gather request instead of 8 for a 4x8 patch, better hit rate than a 1x32
+// strip); slot e -> tile e>>5, lane e&31.  Slots past the grid edge are idle.
+__device__ __forceinline__ bool slot_rc(const AdvectParams& P, int e, int& row, int& col) {
+    const int tile = e >> 5, lane = e & 31;
+    const int tr = P.ntc_magic ? (int)(__umulhi((unsigned)tile, P.ntc_magic) >> P.ntc_shift) : (tile >> P.ntc_shift);
+    const int tc = tile - tr * P.ntc;
+    row = tr * 2 + (lane >> 4);
+    col = tc * 16 + (lane & 15);
+    return row < P.nrow && col < P.ncol;
 }
 
 template <int CS>
 __device__ __forceinline__ void window_sync() {
     if (CS > 1) cg::this_cluster().sync();     // release/acquire at cluster scope: global writes become visible
     else __syncthreads();
+}
+
+// phase A of one sub-step for the slots owned by this thread
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool EULER>
+__device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, int w, int q, int t, int tid_w, int nthr_w,
+                                                const unsigned char* s_lt, const unsigned char* s_gt,
+                                                double2* spos, double2* swind, int* cand,
+                                                unsigned char* g_lt, int* g_cnt) {
+    const int pair = P.level0 + w * P.level_stride + t;
+    for (int e = tid_w; e < P.nslots; e += nthr_w) {
+        int row, col;
+        if (!slot_rc(P, e, row, col)) continue;
+        const int grow = P.row0 + row;
+        const bool pole = (grow < ORDER) || (grow >= P.nrow_global - ORDER);
+        double x, y;
+        if (q == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
+        else {
+            const double2 s = __ldcs(spos + e);               // streaming: keep L1 for the winds
+            x = s.x; y = s.y;
+            if (s_lt[row] && s_lt[P.nrow + col]) x = P.lon_min;      // trajectory.py:96
+            if (s_gt[row] && s_gt[P.nrow + col]) x = P.lon_max;      // trajectory.py:97
+        }
+        if (EULER) {
+            if (P.x_traj) {                                    // level t is final once the pending passes ran
+                const size_t to = ((size_t)w * (P.nsteps + 1) + t) * P.np + (size_t)row * P.ncol + col;
+                P.x_traj[to] = x; P.y_traj[to] = y;
+            }
+            double ua, va;
+            stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
+            __stcs(swind + e, make_double2(ua, va));
+        } else {
+            const double2 wv = __ldcs(swind + e);
+            stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.hx + row), wv.x, wv.y, x, y);
+        }
+        y = clamp_y(y, P.lat_min, P.lat_max);
+        __stcs(spos + e, make_double2(x, y));
+        if (x < P.lon_min) { g_lt[row] = 1; g_lt[P.nrow + col] = 1; }
+        else if (x > P.lon_max) cand[atomicAdd(g_cnt, 1)] = e;
+    }
 }
 
 template <typename T, bool STRICT, int ORDER, int LAYOUT, int CS>
@@ -301,10 +349,9 @@ advect_outer_cluster_kernel(const AdvectParams P) {
     const int nflag = P.nrow + P.ncol;
     unsigned char* s_lt = s_flags;
     unsigned char* s_gt = s_flags + nflag;
-    d2* spos = P.spos + (size_t)w * P.np;
-    d2* swind = P.swind + (size_t)w * P.np;
-    int* cand = P.cand + (size_t)w * P.np;
-    const int pair0 = P.level0 + w * P.level_stride;
+    double2* spos = reinterpret_cast<double2*>(P.spos) + (size_t)w * P.nslots;
+    double2* swind = reinterpret_cast<double2*>(P.swind) + (size_t)w * P.nslots;
+    int* cand = P.cand + (size_t)w * P.nslots;
     const int per = 1 + P.S;
     for (int q = 0; q < P.nsub; ++q) {
         const int t = q / per, k = q - t * per;
@@ -312,47 +359,16 @@ advect_outer_cluster_kernel(const AdvectParams P) {
         unsigned char* g_gt = flag_slot(P, w, q, 1);
         int* g_cnt = P.cand_count + (size_t)w * P.nsub + q;
         // ---- phase A: pending clamps of q-1 (mirrored in smem), stage, y clamp, raise "< x_min" flags
-        for (int p = tid_w; p < P.np; p += nthr_w) {
-            const int row = div_ncol(P, p);
-            const int col = p - row * P.ncol;
-            const int grow = P.row0 + row;
-            const bool pole = (grow < ORDER) || (grow >= P.nrow_global - ORDER);
-            double x, y;
-            if (q == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
-            else {
-                const d2 s = spos[p];
-                x = s.x; y = s.y;
-                if (s_lt[row] && s_lt[P.nrow + col]) x = P.lon_min;      // trajectory.py:96
-                if (s_gt[row] && s_gt[P.nrow + col]) x = P.lon_max;      // trajectory.py:97
-            }
-            if (k == 0 && P.x_traj) {
-                const size_t to = ((size_t)w * (P.nsteps + 1) + t) * P.np + p;
-                P.x_traj[to] = x; P.y_traj[to] = y;
-            }
-            if (k == 0) {
-                double ua, va;
-                stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair0 + t, pole, __ldg(P.kx + row), x, y, ua, va);
-                d2 e; e.x = ua; e.y = va;
-                swind[p] = e;
-            } else {
-                const d2 e = swind[p];
-                stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair0 + t, pole, __ldg(P.hx + row), e.x, e.y, x, y);
-            }
-            y = clamp_y(y, P.lat_min, P.lat_max);
-            d2 s; s.x = x; s.y = y;
-            spos[p] = s;
-            if (x < P.lon_min) { g_lt[row] = 1; g_lt[P.nrow + col] = 1; }
-            else if (x > P.lon_max) cand[atomicAdd(g_cnt, 1)] = p;
-        }
+        if (k == 0) cluster_phase_a<T, STRICT, ORDER, LAYOUT, true>(P, w, q, t, tid_w, nthr_w, s_lt, s_gt, spos, swind, cand, g_lt, g_cnt);
+        else cluster_phase_a<T, STRICT, ORDER, LAYOUT, false>(P, w, q, t, tid_w, nthr_w, s_lt, s_gt, spos, swind, cand, g_lt, g_cnt);
         window_sync<CS>();
         // ---- phase B: mirror the "< x_min" flags; candidates that survive that pass raise "> x_max" flags
         for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_lt[i] = __ldcg(g_lt + i);
         __syncthreads();
         const int ncand = __ldcg(g_cnt);
         for (int i = tid_w; i < ncand; i += nthr_w) {
-            const int p = __ldcg(cand + i);
-            const int row = div_ncol(P, p);
-            const int col = p - row * P.ncol;
+            int row, col;
+            slot_rc(P, __ldcg(cand + i), row, col);
             if (!(s_lt[row] && s_lt[P.nrow + col])) { g_gt[row] = 1; g_gt[P.nrow + col] = 1; }
         }
         window_sync<CS>();
@@ -360,20 +376,21 @@ advect_outer_cluster_kernel(const AdvectParams P) {
         __syncthreads();
     }
     // ---- final: pending clamps of the last sub-step, outputs
-    for (int p = tid_w; p < P.np; p += nthr_w) {
-        const int row = div_ncol(P, p);
-        const int col = p - row * P.ncol;
+    for (int e = tid_w; e < P.nslots; e += nthr_w) {
+        int row, col;
+        if (!slot_rc(P, e, row, col)) continue;
         double x, y;
         if (P.nsub == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
         else {
-            const d2 s = spos[p];
+            const double2 s = __ldcs(spos + e);
             x = s.x; y = s.y;
             if (s_lt[row] && s_lt[P.nrow + col]) x = P.lon_min;
             if (s_gt[row] && s_gt[P.nrow + col]) x = P.lon_max;
         }
-        P.x_out[(size_t)w * P.np + p] = x; P.y_out[(size_t)w * P.np + p] = y;
+        const size_t o = (size_t)row * P.ncol + col;
+        P.x_out[(size_t)w * P.np + o] = x; P.y_out[(size_t)w * P.np + o] = y;
         if (P.x_traj) {
-            const size_t to = ((size_t)w * (P.nsteps + 1) + P.nsteps) * P.np + p;
+            const size_t to = ((size_t)w * (P.nsteps + 1) + P.nsteps) * P.np + o;
             P.x_traj[to] = x; P.y_traj[to] = y;
         }
     }
@@ -406,6 +423,7 @@ static cudaError_t launch_advect(const AdvectParams& P, int nwindows, cudaStream
     const dim3 grid((unsigned)((P.ncol + tw - 1) / tw), (unsigned)((P.nrow + P.band - 1) / P.band), (unsigned)nwindows);
     if (P.xmode != LCS_X_CLAMP_OUTER) {
         advect_fused_kernel<T, STRICT, ORDER, LAYOUT><<<grid, block, 0, st>>>(P);
+        lcs_count_launches(1);
         return cudaGetLastError();
     }
     // Enough windows to fill the machine: one persistent cluster per window (cluster barriers).
@@ -418,6 +436,7 @@ static cudaError_t launch_advect(const AdvectParams& P, int nwindows, cudaStream
         const int forced = lcs_env_int("LCS_OUTER_CLUSTER", 0);
         if (forced == 1 || forced == 2 || forced == 4 || forced == 8) cs = forced;
         if (mode == 2 || nwindows * cs * 2 >= slots) {
+            lcs_count_launches(1);
             switch (cs) {
                 case 8: return launch_outer_cluster<T, STRICT, ORDER, LAYOUT, 8>(P, nwindows, st);
                 case 4: return launch_outer_cluster<T, STRICT, ORDER, LAYOUT, 4>(P, nwindows, st);
@@ -432,6 +451,7 @@ static cudaError_t launch_advect(const AdvectParams& P, int nwindows, cudaStream
         advect_phase_gtpass<<<ggrid, block, 0, st>>>(P, q);
     }
     advect_phase_final<<<grid, block, 0, st>>>(P);
+    lcs_count_launches(2 * P.nsub + 1);
     return cudaGetLastError();
 }
 
@@ -443,8 +463,11 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // workspace of the outer-clamp path: [pos | wind | cand | cleared: cand_count, flags]
 struct WsLayout { size_t pos, wind, cand, count, flags, clear_bytes, total; };
+static size_t lcs_slots_per_window(int nrow, int ncol) {
+    return (size_t)((nrow + 1) / 2) * (size_t)((ncol + 15) / 16) * 32;      // >= nrow*ncol
+}
 static WsLayout ws_layout(const lcs_particles* p, const lcs_advect_opts* o) {
-    const size_t np = (size_t)p->nrow * p->ncol;
+    const size_t np = lcs_slots_per_window(p->nrow, p->ncol);                // both outer paths index state by slot or p < slots
     const size_t nsub = (size_t)o->nsteps * (1 + o->settls_order);
     WsLayout L;
     L.pos = 0;
@@ -501,22 +524,22 @@ extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_a
     P.lat = p->lat; P.lon = p->lon; P.kx = p->kx; P.hx = p->hx; P.ky = p->ky; P.hy = p->hy;
     P.nsteps = o->nsteps; P.S = o->settls_order; P.xmode = o->xmode;
     P.level0 = o->level0; P.level_stride = o->level_stride;
-    P.band_log2 = lcs_env_int("LCS_ADVECT_BAND_LOG2", 2);      // tile = 4 rows x 64 columns by default
+    P.band_log2 = lcs_env_int("LCS_ADVECT_BAND_LOG2", 1);      // tile = 2 rows x 128 columns, warp = 2 x 16
     if (P.band_log2 < 0) P.band_log2 = 0;
     if (P.band_log2 > 5) P.band_log2 = 5;
     P.band = 1 << P.band_log2;
     if ((P.nrow + P.band - 1) / P.band > 65535) return lcs_fail(LCS_E_INVALID, "lcs_advect: too many row bands");
     P.x_out = x_out; P.y_out = y_out; P.x_traj = x_traj; P.y_traj = y_traj;
     P.nsub = o->nsteps * (1 + o->settls_order);
-    {   // p / ncol for 0 <= p < 2^31 as a multiply-high: k = floor(log2 ncol), magic = ceil(2^(32+k) / ncol) < 2^32;
-        // the rounding error p*e/(ncol*2^(32+k)) stays below 1/ncol because e < ncol < 2^(k+1) and p < 2^31
+    {   // persistent-kernel slot enumeration; tile / ntc for 0 <= tile < 2^31 as a multiply-high:
+        // k = floor(log2 ntc), magic = ceil(2^(32+k) / ntc) < 2^32; the rounding error stays below 1/ntc
+        P.ntc = (P.ncol + 15) / 16;
+        P.nslots = (int)lcs_slots_per_window(P.nrow, P.ncol);
         int k = 0;
-        while ((2LL << k) <= P.ncol) ++k;
-        if ((1LL << k) == P.ncol) { P.ncol_magic = 0; P.ncol_shift = k; }
-        else {
-            P.ncol_magic = (unsigned)(((1ULL << (32 + k)) + (unsigned long long)P.ncol - 1) / (unsigned long long)P.ncol);
-            P.ncol_shift = k;
-        }
+        while ((2LL << k) <= P.ntc) ++k;
+        P.ntc_shift = k;
+        P.ntc_magic = ((1LL << k) == P.ntc) ? 0u
+            : (unsigned)(((1ULL << (32 + k)) + (unsigned long long)P.ntc - 1) / (unsigned long long)P.ntc);
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;

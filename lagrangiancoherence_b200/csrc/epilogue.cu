@@ -249,6 +249,7 @@ extern "C" int lcs_ftle_epilogue(const double* x_dep, const double* y_dep, int n
     ftle_epilogue_kernel<<<blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_ftle_epilogue");
+    lcs_count_launches(1);
     return LCS_OK;
 }
 
@@ -261,6 +262,7 @@ extern "C" int lcs_fourth_order_derivative(const float* arr, int n0, int n1, int
         arr, n0, n1, dim, isglobal, out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_fourth_order_derivative");
+    lcs_count_launches(1);
     return LCS_OK;
 }
 
@@ -271,5 +273,6 @@ extern "C" int lcs_spectral_norm_3x3(const double* vals, int64_t n, double* out,
     spectral_norm_3x3_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(vals, n, out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_spectral_norm_3x3");
+    lcs_count_launches(1);
     return LCS_OK;
 }

@@ -151,6 +151,7 @@ extern "C" int lcs_prefilter(const void* u, const void* v, int in_dtype, double*
     fir_axis0_transpose_kernel<double><<<g2, 128, 0, st>>>(tmp, nullptr, 0, coef_u, coef_v, 1, nlon, nlat, taps);
     e = cudaGetLastError();
     if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_prefilter(lon pass)");
+    lcs_count_launches(2);
     return LCS_OK;
 }
 
@@ -173,6 +174,7 @@ extern "C" int lcs_pack_pairs(const void* u, const void* v, int in_dtype, void* 
     else return lcs_fail(LCS_E_INVALID, "lcs_pack_pairs: bad dtype");
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_pack_pairs");
+    lcs_count_launches(1);
     return LCS_OK;
 }
 
@@ -194,5 +196,6 @@ extern "C" int lcs_pack_es(const void* u, const void* v, int in_dtype, void* e_o
     else return lcs_fail(LCS_E_INVALID, "lcs_pack_es: bad dtype");
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_pack_es");
+    lcs_count_launches(1);
     return LCS_OK;
 }

@@ -31,6 +31,9 @@ int lcs_sm_count() {
     }
     return cached;
 }
+static unsigned long long g_launches = 0;
+void lcs_count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+extern "C" unsigned long long lcs_kernel_launches(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
 extern "C" int lcs_abi_version(void) { return LCS_ABI_VERSION; }
 extern "C" const char* lcs_last_error(void) { return g_err; }
 
@@ -136,6 +139,7 @@ extern "C" int lcs_map_coordinates(const lcs_grid* g, const double* field, const
     P.pos_x = pos_x; P.pos_y = pos_y; P.out = out;
     const long long n = (long long)nrow * ncol;
     map_coordinates_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(P);
+    lcs_count_launches(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_map_coordinates");
     return LCS_OK;
@@ -163,6 +167,7 @@ extern "C" int lcs_gather_peak(const void* pairs, int pair_dtype, int vec_width,
         else { if (taps == 4) LCS_GP(Vec2<float>, 4); else LCS_GP(Vec2<float>, 2); }
     }
 #undef LCS_GP
+    lcs_count_launches(1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_gather_peak");
     return LCS_OK;
