@@ -155,11 +155,12 @@ def run_reference(args):
              for k in range(args.steps)]
     total = float(np.sum(times))
     value = psteps_window * cores * args.steps / total
-    sample = f'{cores} windows of {desc} per step (one per worker process), {args.steps} steps'
+    sample = (f'bounded sample of the config above: {cores} of its windows per step, one per worker process '
+              f'({cores} processes), {args.steps} steps')
     line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'particle-steps/s', 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': config_dict(args, desc, cores, 1),
+            'config': config_dict(args, desc, args.batch, max(args.gpus, 1)),
             'fields_per_s': cores * args.steps / total,
             'cpu_baseline': {'value': value, 'unit': 'particle-steps/s', 'cores': cores, 'kind': 'port',
                              'sample': sample},
@@ -261,7 +262,7 @@ def run_b200(args):
         a, b = ev(), ev()
         a.record()
         rolling.rolling_ftle(h_u, h_v, lat, lon, nt, dt, SETTLS_order=S_ORDER, interp_order=args.order,
-                             xclamp=args.xclamp, precision=args.precision, device=dev, chunk=B, out=h_out,
+                             xclamp=args.xclamp, precision=args.precision, device=dev, out=h_out,
                              engine=eng)
         b.record()
         barrier()

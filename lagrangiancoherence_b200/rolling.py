@@ -43,14 +43,36 @@ def chunk_starts(first, count, chunk):
 
 
 # ------------------------------------------------------------------ single-GPU rolling series
+def _pipeline(engine, in_shape, in_dtype, need_in):
+    """Copy streams and double-buffered device staging for host-resident winds, cached on the engine
+    (fresh streams/buffers per call would defeat the caching allocator)."""
+    key = (tuple(in_shape), in_dtype, need_in)
+    pipe = getattr(engine, '_pipe', None)
+    if pipe is None or pipe['key'] != key:
+        dev = engine.device
+        pipe = {'key': key, 'up': torch.cuda.Stream(dev), 'down': torch.cuda.Stream(dev), 'in': [], 'in_free': []}
+        if need_in:
+            for _ in range(2):
+                pipe['in'].append((torch.empty(in_shape, dtype=in_dtype, device=dev),
+                                   torch.empty(in_shape, dtype=in_dtype, device=dev)))
+                pipe['in_free'].append(torch.cuda.current_stream(dev).record_event())
+        engine._pipe = pipe
+    return pipe
+
+
 def rolling_ftle(u, v, lat, lon, window_levels, timestep, SETTLS_order=4, interp_order=3, xclamp='outer',
-                 cyclic_xboundary=False, precision='f64', device='cuda:0', starts=None, chunk=64,
+                 cyclic_xboundary=False, precision='f64', device='cuda:0', starts=None, chunk=148,
                  log_scale=False, out=None, engine=None, return_device=False):
     """sigma_max fields for every start time of a wind series.
 
     ``u, v``: ``[nlev, nlat, nlon]`` (numpy, pinned or not, or device tensors).  Window ``s`` uses
     levels ``s .. s+window_levels-1`` exactly as ``LCS(...)(u.isel(time=slice(s, s+window_levels)))``
-    would.  Returns ``[nstarts, nlat, nlon]`` (numpy unless ``return_device``).
+    would.  Returns ``[nstarts, nlat, nlon]`` (numpy unless ``return_device``; ``out`` = a pinned
+    host tensor to fill).
+
+    Start times are processed in chunks of ``chunk`` windows (148 = one cluster pair per SM for the
+    outer-clamp kernel).  With host-resident winds the chunks are pipelined over three streams:
+    upload of chunk i+1's levels and download of chunk i-1's fields overlap chunk i's kernels.
     """
     lat = np.asarray(lat, dtype=np.float64)
     lon = np.asarray(lon, dtype=np.float64)
@@ -63,21 +85,52 @@ def rolling_ftle(u, v, lat, lon, window_levels, timestep, SETTLS_order=4, interp
         engine = FtleEngine(lat, lon, timestep, SETTLS_order=SETTLS_order, interp_order=interp_order,
                             xmode='cyclic' if cyclic_xboundary else xclamp, pair_dtype=precision, device=device)
     dev = engine.device
-    # stage only the levels this block of windows touches
-    lo, hi = first, first + count + nsteps
-    staged = engine.stage(u[lo:hi], v[lo:hi])
-    sigma = torch.empty((count, lat.size, lon.size), dtype=torch.float64, device=dev)
-    for s, n in chunk_starts(0, count, chunk):
-        x, y = engine.advect(staged, nsteps=nsteps, nwindows=n, level0=s, level_stride=1)
-        sigma[s:s + n] = engine.epilogue(x, y, log_scale=log_scale)
+    on_device = isinstance(u, torch.Tensor) and u.is_cuda
+    if not on_device:
+        if not isinstance(u, torch.Tensor):
+            u, v = torch.from_numpy(np.ascontiguousarray(u)), torch.from_numpy(np.ascontiguousarray(v))
+        if u.dtype not in (torch.float32, torch.float64):
+            u, v = u.double(), v.double()
+    to_host = not return_device
+    own_out = out is None
+    if to_host and own_out:
+        out = torch.empty((count, lat.size, lon.size), dtype=torch.float64).pin_memory()
+    sigma = None if to_host else torch.empty((count, lat.size, lon.size), dtype=torch.float64, device=dev)
+    chunks = chunk_starts(0, count, chunk)
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream(dev)
+        pipe = _pipeline(engine, (min(chunk, count) + nsteps,) + tuple(u.shape[1:]), u.dtype, need_in=not on_device)
+        up, down = pipe['up'], pipe['down']
+        for i, (s, n) in enumerate(chunks):
+            lo, hi = first + s, first + s + n + nsteps          # levels this chunk touches
+            if on_device:
+                du, dv = u[lo:hi], v[lo:hi]
+            else:
+                bu, bv = pipe['in'][i % 2]
+                up.wait_event(pipe['in_free'][i % 2])            # kernels of chunk i-2 are done with this buffer
+                with torch.cuda.stream(up):
+                    du, dv = bu[:hi - lo], bv[:hi - lo]
+                    du.copy_(u[lo:hi], non_blocking=True)
+                    dv.copy_(v[lo:hi], non_blocking=True)
+                main.wait_event(up.record_event())
+            staged = engine.stage(du, dv)
+            if not on_device:
+                pipe['in_free'][i % 2] = main.record_event()     # staging has consumed the raw levels
+            x, y = engine.advect(staged, nsteps=nsteps, nwindows=n, level0=0, level_stride=1)
+            sig = engine.epilogue(x, y, log_scale=log_scale)
+            if to_host:
+                down.wait_event(main.record_event())
+                with torch.cuda.stream(down):
+                    out[s:s + n].copy_(sig, non_blocking=True)
+                sig.record_stream(down)
+            else:
+                sigma[s:s + n] = sig
+        if to_host:
+            down.synchronize()
     engine.check_finite()
     if return_device:
         return sigma
-    if out is not None:
-        out.copy_(sigma, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        return out
-    return sigma.cpu().numpy()
+    return out.numpy() if own_out else out
 
 
 # ------------------------------------------------------------------ collectives (gather only)
