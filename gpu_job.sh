@@ -1,1 +1,1 @@
-python scripts/probe_f32.py
+timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -8

@@ -115,6 +115,13 @@ int lcs_pack_pairs(const void* u, const void* v, int in_dtype, void* pairs, int 
 int lcs_pack_es(const void* u, const void* v, int in_dtype, void* e_out, void* s_out, int es_dtype,
                 int nlev, int nlat, int nlon, void* stream);
 
+/* lcs_time_lerp: `u.resample({timedim: freq}).interpolate('linear')` of LCS.py:88-91 on the device.  New level k
+ * = w_hi[k] * in[lo[k]+1] + w_lo[k] * in[lo[k]], the form scipy 1.18.1's interp1d(kind='linear') evaluates
+ * (w_hi = (x-x_lo)/(x_hi-x_lo), w_lo = (x_hi-x)/(x_hi-x_lo), computed by the host).  Needs at least two levels.
+ * in: device [nlev][plane] of in_dtype; lo/w_hi/w_lo: device [nnew]; out: device f64 [nnew][plane]. */
+int lcs_time_lerp(const void* in, int in_dtype, const int32_t* lo, const double* w_hi, const double* w_lo,
+                  int nnew, int64_t plane, double* out, void* stream);
+
 /* ---------------------------------------------------------------- integrator
  * lcs_advect replaces parcel_propagation's loop, trajectory.py:80-126, together with the
  * xr_map_coordinates calls inside it (tools.py:11-41).
@@ -149,6 +156,12 @@ int lcs_ftle_epilogue(const double* x_dep, const double* y_dep, int nfields,
                       int out_row0, int nrow_out, const double* dx, double dy,
                       const uint8_t* mask, int log_scale,
                       double* sigma, double* jac, int32_t* status, void* stream);
+
+/* lcs_gaussian_filter2d: scipy.ndimage.gaussian_filter(x_departure, sigma) of LCS.py:187-190 (mode='reflect',
+ * truncate=4, axis 0 then axis 1, scipy's accumulation order: bit-identical results).  in/out/scratch: device f64
+ * [nfields][n0][n1], distinct; weights: device [2*radius+1] normalised kernel, radius = int(4*sigma + 0.5). */
+int lcs_gaussian_filter2d(const double* in, double* out, double* scratch, int nfields, int n0, int n1,
+                          const double* weights, int radius, void* stream);
 
 /* ---------------------------------------------------------------- array-level seams
  * The three third-party kernels the reference calls, as stand-alone device operations. */

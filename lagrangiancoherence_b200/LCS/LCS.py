@@ -55,8 +55,12 @@ class LCS:
         elif isinstance(ds, str):                                    # LCS.py:84-87
             raise NotImplementedError('opening NetCDF paths needs xarray/netCDF4, which this image lacks; '
                                       'pass u= and v= arrays')
-        if isinstance(resample, str):                                # LCS.py:88-91
-            raise NotImplementedError("resample= (linear time refinement) is not implemented yet")
+        resample_plan_ = None
+        if isinstance(resample, str):                                # LCS.py:88-91: linear refinement in time
+            from ..timeaxis import resample_plan
+            resample_plan_ = resample_plan(coord_values(u, timedim), resample)
+            new_t = resample_plan_[0]
+            timestep = np.sign(timestep) * (new_t[1] - new_t[0]).astype('timedelta64[s]').astype('float')   # LCS.py:91
         assert set(u.dims) == set(v.dims), "u and v dims are different"                      # LCS.py:95
         assert set(u.dims) == {'latitude', 'longitude', timedim}, \
             'array dims should be latitude and longitude only'                               # LCS.py:96
@@ -76,11 +80,13 @@ class LCS:
             print('using s = ' + str(s / 1e6) + '1e6')
         verboseprint("*---- Parcel propagation ----*")
         engine, out, Us, lat, lon, times = propagate(u, v, timestep, timedim, return_traj, self.SETTLS_order,
-                                                     traj_interp_order, cyclic_xboundary, xclamp, device, precision)
+                                                     traj_interp_order, cyclic_xboundary, xclamp, device, precision,
+                                                     resample=resample_plan_)
         x_dep, y_dep = out[0], out[1]
         verboseprint("*---- Computing deformation tensor ----*")
-        if isinstance(self.gauss_sigma, (float, int)):               # LCS.py:187-190
-            raise NotImplementedError('gauss_sigma smoothing of the departure points is not implemented yet')
+        xs, ys = x_dep, y_dep
+        if isinstance(self.gauss_sigma, (float, int)):               # LCS.py:187-190 (inside flowmap_gradient upstream)
+            xs, ys = engine.gaussian(x_dep, self.gauss_sigma), engine.gaussian(y_dep, self.gauss_sigma)
         latkeep = lonkeep = None
         out_rows = None
         if isinstance(self.subdomain, dict):                         # LCS.py:143-144 (crop after the derivatives)
@@ -90,7 +96,7 @@ class LCS:
             if rows.size:
                 out_rows = (int(rows[0]), int(rows[-1]) + 1)         # only these rows are computed
         verboseprint("*---- Computing eigenvalues ----*")
-        sigma = engine.epilogue(x_dep, y_dep, out_rows=out_rows)
+        sigma = engine.epilogue(xs, ys, out_rows=out_rows)
         engine.check_finite()                                        # ValueError on inf, as scipy.linalg.norm (LCS.py:154)
         sigma = sigma[0].cpu().numpy()
         verboseprint("*---- Done eigenvalues ----*")
@@ -99,7 +105,7 @@ class LCS:
             r0 = out_rows[0] if out_rows else 0
             sigma = sigma[latkeep[r0:r0 + sigma.shape[0]]][:, lonkeep] if out_rows else sigma[:0, :0]
             olat, olon = lat[latkeep], lon[lonkeep]
-        tvals = coord_values(Us, timedim)
+        tvals = coord_values(Us, timedim) if resample_plan_ is None else resample_plan_[0]
         timestamp = tvals[-1] if np.sign(timestep) == 1 else tvals[0]                         # LCS.py:158
         coords = {'latitude': olat, 'longitude': olon, 'time': np.asarray(timestamp)}        # LCS.py:159
         if timedim == 'time':
@@ -126,8 +132,6 @@ class LCS:
 
 def flowmap_gradient(x_departure, y_departure, sigma=None, *, device='cuda:0'):
     """The nine stacked 'derivatives' ``(derivatives, latitude, longitude)`` of LCS.py:171-225."""
-    if isinstance(sigma, (float, int)):
-        raise NotImplementedError('gauss_sigma smoothing of the departure points is not implemented yet')
     xd = x_departure.transpose('latitude', 'longitude')
     yd = y_departure.transpose('latitude', 'longitude')
     lat, lon = coord_values(xd, 'latitude'), coord_values(xd, 'longitude')
@@ -135,6 +139,8 @@ def flowmap_gradient(x_departure, y_departure, sigma=None, *, device='cuda:0'):
     dev = torch.device(device)
     tx = torch.from_numpy(np.ascontiguousarray(xd.values, dtype=np.float64)).to(dev)
     ty = torch.from_numpy(np.ascontiguousarray(yd.values, dtype=np.float64)).to(dev)
+    if isinstance(sigma, (float, int)):                              # LCS.py:187-190
+        tx, ty = engine.gaussian(tx, sigma), engine.gaussian(ty, sigma)
     _, jac = engine.epilogue(tx, ty, return_jac=True)
     jac = jac[0]
     full = torch.cat([jac, torch.zeros((3,) + tuple(jac.shape[1:]), dtype=jac.dtype, device=dev)])   # LCS.py:206-208

@@ -20,20 +20,25 @@ def _sorted_winds(U, V, propdim):
 
 
 def propagate(U, V, timestep, propdim, return_traj, SETTLS_order, interp_order, cyclic_xboundary,
-              xclamp=XCLAMP_DEFAULT, device='cuda:0', precision='f64', engine=None):
+              xclamp=XCLAMP_DEFAULT, device='cuda:0', precision='f64', engine=None, resample=None):
     """Shared by parcel_propagation and LCS.__call__: returns device tensors plus the metadata the
     callers need to label them."""
     U, V = _sorted_winds(U, V, propdim)
     lat = coord_values(U, 'latitude')
     lon = coord_values(U, 'longitude')
-    times = coord_values(U, propdim).tolist()                      # trajectory.py:58
+    tcoord = coord_values(U, propdim) if resample is None else resample[0]
+    times = tcoord.tolist()                                        # trajectory.py:58
     if timestep < 0:
         times.reverse()                                            # labels only (quirk Q2), :59-60
     xmode = 'cyclic' if cyclic_xboundary else xclamp
     if engine is None:
         engine = FtleEngine(lat, lon, timestep, SETTLS_order=SETTLS_order, interp_order=interp_order,
                             xmode=xmode, pair_dtype=precision, device=device)
-    staged = engine.stage(np.asarray(U.values), np.asarray(V.values))
+    uu, vv = np.asarray(U.values), np.asarray(V.values)
+    if resample is not None:                                       # LCS.py:88-90, evaluated on the device
+        _, lo, w_hi, w_lo = resample
+        uu, vv = engine.time_lerp(uu, lo, w_hi, w_lo), engine.time_lerp(vv, lo, w_hi, w_lo)
+    staged = engine.stage(uu, vv)
     out = engine.advect(staged, return_traj=return_traj)
     return engine, out, U, lat, lon, times
 

@@ -49,6 +49,8 @@ SIGNATURES = {
     'lcs_prefilter': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                               c_int, c_int, c_int, c_void_p]),
     'lcs_pack_pairs': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    'lcs_time_lerp': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
+    'lcs_gaussian_filter2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     'lcs_advect_workspace_bytes': (c_size_t, [C.POINTER(Particles), C.POINTER(AdvectOpts)]),
     'lcs_pack_es': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'lcs_advect': (c_int, [C.POINTER(Grid), C.POINTER(Particles), C.POINTER(AdvectOpts), C.POINTER(Winds),

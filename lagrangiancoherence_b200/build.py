@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'liblcs_b200.so')
-SOURCES = ['advect.cu', 'prefilter.cu', 'epilogue.cu', 'seams.cu']
+SOURCES = ['advect.cu', 'prefilter.cu', 'epilogue.cu', 'filters.cu', 'seams.cu']
 HEADERS = ['lcs_device.cuh', 'lcs_internal.h', os.path.join('..', '..', 'include', 'lcs_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-shared', '--expt-relaxed-constexpr']

@@ -232,6 +232,33 @@ class FtleEngine:
                                                   _stream(self.device)), 'lcs_ftle_epilogue')
         return (sigma, jac) if return_jac else sigma
 
+    def gaussian(self, fields, sigma):
+        """scipy.ndimage.gaussian_filter(field, sigma) (reflect, truncate=4) on ``[nfields, n0, n1]`` f64 (LCS.py:187-190)."""
+        squeeze = fields.dim() == 2
+        f = (fields[None] if squeeze else fields).contiguous()
+        radius = int(4.0 * float(sigma) + 0.5)
+        xs = np.arange(-radius, radius + 1)
+        w = np.exp(-0.5 / (float(sigma) * float(sigma)) * xs ** 2)          # scipy _gaussian_kernel1d
+        w = w / w.sum()
+        with torch.cuda.device(self.device):
+            dw = torch.from_numpy(w).to(self.device)
+            out, scratch = torch.empty_like(f), torch.empty_like(f)
+            _lib.check(self.lib.lcs_gaussian_filter2d(_ptr(f), _ptr(out), _ptr(scratch), f.shape[0], f.shape[1], f.shape[2],
+                                                      _ptr(dw), radius, _stream(self.device)), 'lcs_gaussian_filter2d')
+        return out[0] if squeeze else out
+
+    def time_lerp(self, series, lo, w_hi, w_lo):
+        """Linear time refinement of ``[nlev, nlat, nlon]`` (LCS.py:88-91); see timeaxis.resample_plan."""
+        t = self._to_device(series)
+        with torch.cuda.device(self.device):
+            d_lo = torch.from_numpy(np.ascontiguousarray(lo, dtype=np.int32)).to(self.device)
+            d_num = torch.from_numpy(np.ascontiguousarray(w_hi, dtype=np.float64)).to(self.device)
+            d_den = torch.from_numpy(np.ascontiguousarray(w_lo, dtype=np.float64)).to(self.device)
+            out = torch.empty((len(lo),) + tuple(t.shape[1:]), dtype=torch.float64, device=self.device)
+            _lib.check(self.lib.lcs_time_lerp(_ptr(t), _dtype_code(t), _ptr(d_lo), _ptr(d_num), _ptr(d_den), len(lo),
+                                              int(t[0].numel()), _ptr(out), _stream(self.device)), 'lcs_time_lerp')
+        return out
+
     def check_finite(self):
         """Raise like scipy.linalg.norm(check_finite=True) does at LCS.py:154 (synchronises)."""
         if int(self.d_status.item()) & 1:

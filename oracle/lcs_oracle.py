@@ -310,16 +310,43 @@ def subdomain_mask(lat, lon, subdomain):
 
 
 # --------------------------------------------------------------------------------------
+# resample= (LCS.py:88-91): u.resample({timedim: freq}).interpolate('linear')
+# --------------------------------------------------------------------------------------
+def resample_linear(U, times, freq):
+    """Linear refinement in time as xarray executes it: new index = pandas resample bin labels, values from
+    scipy.interpolate.interp1d(kind='linear') (scipy 1.18.1) over float64 ns offsets:
+    y = ((x_new - x_lo)/(x_hi - x_lo)) * y_hi + ((x_hi - x_new)/(x_hi - x_lo)) * y_lo, bracket from
+    searchsorted(x, x_new, 'left') clipped to [1, n-1].  Returns ``(U_new, new_times)``."""
+    import pandas as pd
+    t = np.asarray(times).astype('datetime64[ns]')
+    new = pd.Series(0.0, index=pd.DatetimeIndex(t)).resample(freq).asfreq().index.values.astype('datetime64[ns]')
+    x = (t - t.min()).astype('int64').astype(np.float64)
+    xn = (new - t.min()).astype('int64').astype(np.float64)
+    hi = np.clip(np.searchsorted(x, xn, side='left'), 1, x.size - 1)
+    lo = hi - 1
+    U = np.asarray(U)
+    shp = (-1,) + (1,) * (U.ndim - 1)
+    w_hi = ((xn - x[lo]) / (x[hi] - x[lo])).reshape(shp)
+    w_lo = ((x[hi] - xn) / (x[hi] - x[lo])).reshape(shp)
+    return w_hi * U[hi] + w_lo * U[lo], new
+
+
+# --------------------------------------------------------------------------------------
 # a2: LCS.__call__ (LCS.py:48-168), regional path and the cheap isglobal/truncation=None path
 # --------------------------------------------------------------------------------------
 def lcs_field(U, V, lat, lon, timestep, SETTLS_order=0, traj_interp_order=3,
               cyclic_xboundary=False, xclamp='outer', gauss_sigma=None, subdomain=None,
-              return_dpts=False, return_traj=False):
+              return_dpts=False, return_traj=False, resample=None):
     """sigma_max field ``(nlat, nlon)`` for one window of winds ``(nt, nlat, nlon)``.
 
     The caller-side FTLE scaling ``0.5*log(sigma)`` (examples/ideal_vortex.py:282,288) is NOT
     applied here, as in the reference.
     """
+    if resample is not None:                                                   # LCS.py:88-91: (times, freq)
+        times, freq = resample
+        U, new_t = resample_linear(U, times, freq)
+        V, _ = resample_linear(V, times, freq)
+        timestep = np.sign(timestep) * (new_t[1] - new_t[0]).astype('timedelta64[s]').astype('float')
     res = parcel_propagation(U, V, lat, lon, timestep, SETTLS_order=SETTLS_order,
                              interp_order=traj_interp_order, cyclic_xboundary=cyclic_xboundary,
                              xclamp=xclamp, return_traj=return_traj)          # LCS.py:129-134

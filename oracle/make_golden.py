@@ -150,6 +150,12 @@ def main():
     sub = {'latitude': slice(-20, 0), 'longitude': slice(-70, -40)}
     with contextlib.redirect_stdout(quiet):
         eig = ref_lcs.LCS(timestep=case['timestep'], SETTLS_order=case['S'], subdomain=sub)(u=du, v=dv, verbose=False)
+        # resample='3H' (LCS.py:88-91, as area_of_influence.py:181 uses it) and gauss_sigma (LCS.py:187-190)
+        rs = ref_lcs.LCS(timestep=case['timestep'], SETTLS_order=2, return_dpts=True)(u=du, v=dv, verbose=False, resample='3h')
+        gs = ref_lcs.LCS(timestep=case['timestep'], SETTLS_order=case['S'], gauss_sigma=1.5)(u=du, v=dv, verbose=False)
+    seams['resample_sigma'], seams['resample_x_dep'], seams['resample_y_dep'] = rs[0].values, rs[1].values, rs[2].values
+    seams['resample_time'] = np.asarray(rs[0].coords['time']).astype('datetime64[ns]').astype('int64')
+    seams['gauss_sigma_field'] = gs.values
     seams['subdomain_sigma'] = eig.values
     seams['subdomain_lat'], seams['subdomain_lon'] = eig.coords['latitude'], eig.coords['longitude']
     np.savez_compressed(os.path.join(GOLDEN, 'seams.npz'), **seams)

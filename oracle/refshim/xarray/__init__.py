@@ -204,6 +204,11 @@ class DataArray:
         coords = {m.get(k, k): v for k, v in self.coords.items()}
         return DataArray(self.values, coords, dims, self.name, self.attrs)
 
+    # ------------------------------------------------------------- resample(...).interpolate('linear')  (LCS.py:89-90)
+    def resample(self, indexer=None, **kw):
+        (dim, freq), = dict(indexer or {}, **kw).items()
+        return _Resampler(self, dim, freq)
+
     # ------------------------------------------------------------- reductions
     def _reduce(self, fn):
         return DataArray(fn(self.values), {k: v for k, v in self.coords.items() if v.ndim == 0}, (), self.name)
@@ -312,6 +317,28 @@ class DataArray:
         coords = {k: val for k, val in self.coords.items() if not k.startswith('_')}
         coords[a], coords[b] = ua, ub
         return DataArray(out, coords, lead + [a, b], self.name)
+
+
+class _Resampler:
+    """xarray: DataArrayResample.interpolate(kind) == obj.interp({dim: new pandas bin labels}, method=kind,
+    kwargs={'bounds_error': False}); for one dimension that is scipy.interpolate.interp1d over the time axis
+    converted to float64 nanosecond offsets from its minimum (xarray.core.missing._floatize_x)."""
+
+    def __init__(self, obj, dim, freq):
+        self.obj, self.dim, self.freq = obj, dim, freq
+
+    def interpolate(self, kind='linear'):
+        import pandas as pd
+        from scipy.interpolate import interp1d
+        t = np.asarray(self.obj.coords[self.dim]).astype('datetime64[ns]')
+        new = pd.Series(0.0, index=pd.DatetimeIndex(t)).resample(self.freq).asfreq().index.values.astype('datetime64[ns]')
+        x = (t - t.min()).astype('int64').astype(np.float64)
+        xn = (new - t.min()).astype('int64').astype(np.float64)
+        ax = self.obj.dims.index(self.dim)
+        f = interp1d(x, self.obj.values, kind=kind, axis=ax, bounds_error=False, fill_value=np.nan, assume_sorted=True, copy=False)
+        coords = dict(self.obj.coords)
+        coords[self.dim] = new
+        return DataArray(f(xn), coords, self.obj.dims, self.obj.name)
 
 
 class Dataset:

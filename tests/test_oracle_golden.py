@@ -75,3 +75,29 @@ def test_outer_clamp_is_what_the_reference_executes():
     u, v, lat, lon, _ = make_inputs(case)
     xp, _ = O.parcel_propagation(u, v, lat, lon, case['timestep'], SETTLS_order=case['S'], xclamp='pointwise')
     assert np.array_equal(xp, g['x_dep'])
+
+
+def test_resample_and_gauss_sigma_reproduce_reference_bitwise():
+    """resample='3h' (LCS.py:88-91: pandas bin labels + scipy interp1d in time, timestep re-derived at :91) and
+    gauss_sigma (LCS.py:187-190: scipy gaussian_filter of the departure points) through the unmodified reference."""
+    g = load('seams')
+    case = CASES['regional_outer_p3']
+    u, v, lat, lon, time = make_inputs(case)
+    sig, xd, yd = O.lcs_field(u, v, lat, lon, case['timestep'], SETTLS_order=2, resample=(time, '3h'), return_dpts=True)
+    assert np.array_equal(xd, g['resample_x_dep']) and np.array_equal(yd, g['resample_y_dep'])
+    assert np.array_equal(sig, g['resample_sigma'][0])
+    assert g['resample_time'][0] == time[0].astype('int64')
+    sig = O.lcs_field(u, v, lat, lon, case['timestep'], SETTLS_order=case['S'], gauss_sigma=1.5)
+    assert np.array_equal(sig, g['gauss_sigma_field'][0])
+
+
+def test_resample_plan_matches_oracle_weights():
+    from lagrangiancoherence_b200.timeaxis import resample_plan
+    _, _, _, _, time = make_inputs(CASES['regional_outer_p3'])
+    u = np.random.default_rng(0).normal(size=(time.size, 4, 5))
+    new, lo, w_hi, w_lo = resample_plan(time, '3h')
+    ref, new_ref = O.resample_linear(u, time, '3h')
+    assert np.array_equal(new, new_ref) and new.size == 2 * time.size - 1
+    got = w_hi[:, None, None] * u[lo + 1] + w_lo[:, None, None] * u[lo]
+    assert np.array_equal(got, ref)
+    assert np.array_equal(got[::2], u)              # levels that coincide with input levels come back exactly
