@@ -1,1 +1,1 @@
-timeout 1200 python -m pytest tests/test_gpu_configs.py tests/test_gpu_multi.py -m gpu -q -x 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_gpu_edges.py -m gpu -q 2>&1 | tail -5

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'liblcs_b200.so')
+LIB_PATH = os.environ.get('LCS_B200_LIB') or os.path.join(HERE, 'liblcs_b200.so')   # override: tuning experiments only
 
 LCS_F64, LCS_F32 = 0, 1
 LCS_X_CYCLIC, LCS_X_CLAMP_POINTWISE, LCS_X_CLAMP_OUTER = 0, 1, 2

@@ -140,8 +140,11 @@ __device__ __forceinline__ void bounds_local(const AdvectParams& P, double& x, d
 }
 
 // ---------------------------------------------------------------------------------------------
+#ifndef LCS_FUSED_MINBLOCKS
+#define LCS_FUSED_MINBLOCKS 4       // 64 registers, 1024 threads per SM (measured against 3 and 2 blocks: see DESIGN.md)
+#endif
 template <typename T, bool STRICT, int ORDER, int LAYOUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LCS_FUSED_MINBLOCKS)
 advect_fused_kernel(const AdvectParams P) {
     const int w = blockIdx.z;
     int row, col;
@@ -350,7 +353,10 @@ __device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, int w, in
 }
 
 template <typename T, bool STRICT, int ORDER, int LAYOUT, int CS>
-__global__ void __launch_bounds__(kClusterThreads, 2)
+#ifndef LCS_CLUSTER_MINBLOCKS
+#define LCS_CLUSTER_MINBLOCKS 2
+#endif
+__global__ void __launch_bounds__(kClusterThreads, LCS_CLUSTER_MINBLOCKS)
 advect_outer_cluster_kernel(const AdvectParams P) {
     extern __shared__ unsigned char s_flags[];            // [lt rows | lt cols | gt rows | gt cols]
     const int w = blockIdx.x / CS;
@@ -440,7 +446,7 @@ static cudaError_t launch_advect(const AdvectParams& P, int nwindows, cudaStream
     // Enough windows to fill the machine: one persistent cluster per window (cluster barriers).
     // Few windows: one launch pair per sub-step over all particles (kernel-boundary barriers).
     const int mode = lcs_env_int("LCS_OUTER_MODE", 0);          // 0 auto, 1 phased launches, 2 clusters
-    const int slots = lcs_sm_count() * 2;                        // two 512-thread CTAs per SM
+    const int slots = lcs_sm_count() * LCS_CLUSTER_MINBLOCKS;    // 512-thread CTAs per SM
     if (P.nsub > 0 && 2 * (size_t)(P.nrow + P.ncol) <= 64 * 1024 && mode != 1) {
         int cs = 8;
         while (cs > 1 && nwindows * cs > slots) cs >>= 1;
