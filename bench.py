@@ -172,6 +172,18 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- CUDA arm
+def ncu_traffic(args, B):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+    `ncu --set full` capture of this very command line (profiles/r01_traffic.json); null for any other config."""
+    try:
+        table = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+    except OSError:
+        return None
+    key = f'{args.workload}:{args.xclamp}:p{args.order}:{args.precision}:B{B}'
+    entry = table.get(key)
+    return entry['dram_bytes_per_launch'] if entry else None
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -350,7 +362,7 @@ def run_b200(args):
                        'note': 'ES layout: the SETTLS operand 2f_k - f_{k+1} is pre-combined per grid point, so a stage '
                                'gathers 2 values per tap instead of 4; peak = same microbenchmark with 2-value taps'},
             'advect_ms_per_step': advect_ms,
-            'traffic': None,
+            'traffic': ncu_traffic(args, B),
             'hbm': {'achieved': hbm_bytes / (advect_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
                     'frac': hbm_bytes / (advect_ms * 1e-3) / 1e9 / hbm_peak, 'peak_source': hbm_src,
                     'compulsory_bytes': hbm_bytes},

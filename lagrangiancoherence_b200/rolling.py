@@ -172,3 +172,26 @@ def band_ftle(engine, staged, world_size, rank, nsteps=None, nwindows=1, level0=
     x, y = engine.advect(staged, nsteps=nsteps, nwindows=nwindows, level0=level0, rows=(in0, in1))
     sigma = engine.epilogue(x, y, log_scale=log_scale, in_row0=in0, out_rows=(out0, out1))
     return sigma, (out0, out1)
+
+
+# ------------------------------------------------------------------ sharded drivers (one process per GPU)
+def rolling_ftle_sharded(u, v, lat, lon, window_levels, timestep, group=None, dst=None, **kw):
+    """Start-time sharding of a rolling series over the ranks of ``group``: every rank integrates its contiguous
+    block of windows (staging only the levels that block touches) and the finished fields are gathered with one
+    collective.  ``kw`` as for :func:`rolling_ftle`.  Returns ``[nstarts, nlat, nlon]`` on the device."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    nstarts = u.shape[0] - window_levels + 1
+    first, count = shard_starts(nstarts, world, rank)
+    kw.pop('return_device', None)
+    mine = rolling_ftle(u, v, lat, lon, window_levels, timestep, starts=(first, count), return_device=True, **kw)
+    return gather_fields(mine, [shard_starts(nstarts, world, r)[1] for r in range(world)], group=group, dst=dst)
+
+
+def ftle_row_bands(engine, u, v, group=None, log_scale=False):
+    """Row-band sharding of ONE field over the ranks of ``group`` (winds replicated, 2-row recomputed halo,
+    cyclic / pointwise x-boundary only).  Returns the full ``[nlat, nlon]`` field on every rank."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    band, _ = band_ftle(engine, engine.stage(u, v), world, rank, log_scale=log_scale)
+    return gather_bands(band, engine.nlat, group=group)[0]

@@ -20,7 +20,7 @@ def _worker(rank, world, port, q):
     import torch.distributed as dist
     from lagrangiancoherence_b200 import synthetic as S
     from lagrangiancoherence_b200.engine import FtleEngine
-    from lagrangiancoherence_b200.rolling import band_ftle, gather_bands, gather_fields, rolling_ftle, shard_starts
+    from lagrangiancoherence_b200.rolling import ftle_row_bands, rolling_ftle, rolling_ftle_sharded
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = torch.device('cuda', rank)
@@ -31,18 +31,15 @@ def _worker(rank, world, port, q):
     u, v = S.era5_like_winds(lat, lon, nt + nstarts - 1)
     # start-time sharding, outer clamp
     eng = FtleEngine(lat, lon, -21600, SETTLS_order=4, xmode='outer', device=dev)
-    first, count = shard_starts(nstarts, world, rank)
-    mine = rolling_ftle(u, v, lat, lon, nt, -21600, engine=eng, starts=(first, count), return_device=True)
-    allf = gather_fields(mine, [shard_starts(nstarts, world, r)[1] for r in range(world)])
+    allf = rolling_ftle_sharded(u, v, lat, lon, nt, -21600, engine=eng)
     # row bands, pointwise clamp
     engp = FtleEngine(lat, lon, -21600, SETTLS_order=4, xmode='pointwise', device=dev)
     st = engp.stage(u[:nt], v[:nt])
-    band, _ = band_ftle(engp, st, world, rank)
-    full = gather_bands(band, lat.size)
+    full = ftle_row_bands(engp, u[:nt], v[:nt])
     if rank == 0:
         ref_all = rolling_ftle(u, v, lat, lon, nt, -21600, engine=eng, return_device=True)
         x, y = engp.advect(st)
-        ref_full = engp.epilogue(x, y)
+        ref_full = engp.epilogue(x, y)[0]
         q.put((bool(torch.equal(allf, ref_all)), bool(torch.equal(full, ref_full))))
     dist.barrier()
     dist.destroy_process_group()
