@@ -282,7 +282,10 @@ advect_phase_final(const AdvectParams P) {
 // are resolved with hardware cluster barriers (barrier.cluster, ~0.2 us) instead of kernel
 // boundaries.  A cluster of 1 degenerates to __syncthreads().  The exit flags of the current
 // sub-step are mirrored into shared memory after each barrier so the per-particle tests are LDS.
-constexpr int kClusterThreads = 512;
+#ifndef LCS_CLUSTER_THREADS
+#define LCS_CLUSTER_THREADS 512
+#endif
+constexpr int kClusterThreads = LCS_CLUSTER_THREADS;   // multiple of 32: a warp owns whole 2x16 tiles
 
 // Slot enumeration of a window for the persistent kernel: warp-sized tiles of 2 rows x 16 columns
 // (6 L1 wavefronts per 16-B gather request instead of 8 for a 4x8 patch, better hit rate than a 1x32
@@ -352,10 +355,10 @@ __device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, int w, in
     }
 }
 
-template <typename T, bool STRICT, int ORDER, int LAYOUT, int CS>
 #ifndef LCS_CLUSTER_MINBLOCKS
 #define LCS_CLUSTER_MINBLOCKS 2
 #endif
+template <typename T, bool STRICT, int ORDER, int LAYOUT, int CS>
 __global__ void __launch_bounds__(kClusterThreads, LCS_CLUSTER_MINBLOCKS)
 advect_outer_cluster_kernel(const AdvectParams P) {
     extern __shared__ unsigned char s_flags[];            // [lt rows | lt cols | gt rows | gt cols]

@@ -114,6 +114,12 @@ __device__ __forceinline__ int mirror_idx(int i, int n) {
     return i;
 }
 
+// The same reflection for the indices a gather can actually produce: coordinates are folded into [0, n-1]
+// first, so taps lie in [-1, n+1]; for n >= 3 that needs no division: -1 -> 1, n -> n-2, n+1 -> n-3.
+__device__ __forceinline__ int mirror_near(int i, int n) {
+    return i < 0 ? -i : (i > n - 1 ? 2 * (n - 1) - i : i);
+}
+
 template <bool STRICT>
 __device__ __forceinline__ void cubic_weights(double y, double (&w)[4]) {
     const double z = __dsub_rn(1.0, y);
@@ -173,12 +179,15 @@ __device__ __forceinline__ void gather_cubic_wrap(const typename E::type* __rest
         }
         return;
     }
+    // edge path: every tap index reflected; fully unrolled so the weight arrays stay in registers
+    // (a rolled loop indexed them dynamically and put 4 local-memory stores into every stage: ncu showed
+    // local-memory wavefronts at 22-48 % of the global-load wavefronts on the L1 pipe that bounds the kernel)
     int col[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) col[j] = mirror_idx(sx + j, nlon);
-#pragma unroll 1
+    for (int j = 0; j < 4; ++j) col[j] = mirror_near(sx + j, nlon);
+#pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const typename E::type* rowp = f + (size_t)mirror_idx(sy + i, nlat) * nlon;
+        const typename E::type* rowp = f + (size_t)mirror_near(sy + i, nlat) * nlon;
         double c[4][NV];
 #pragma unroll
         for (int j = 0; j < 4; ++j) E::ld(rowp + col[j], c[j]);
@@ -204,12 +213,12 @@ __device__ __forceinline__ void bilinear_taps(const typename E::type* __restrict
     const double wy[2] = {wy0, __dsub_rn(1.0, wy0)};
     const double wx[2] = {wx0, __dsub_rn(1.0, wx0)};
     const int iy0 = (int)fy, ix0 = (int)fx;
-    const int col[2] = {mirror_idx(ix0, nlon), mirror_idx(ix0 + 1, nlon)};
+    const int col[2] = {mirror_near(ix0, nlon), mirror_near(ix0 + 1, nlon)};
 #pragma unroll
     for (int v = 0; v < NV; ++v) out[v] = 0.0;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const typename E::type* rowp = f + (size_t)mirror_idx(iy0 + i, nlat) * nlon;
+        const typename E::type* rowp = f + (size_t)mirror_near(iy0 + i, nlat) * nlon;
         double c[2][NV];
 #pragma unroll
         for (int j = 0; j < 2; ++j) E::ld(rowp + col[j], c[j]);
