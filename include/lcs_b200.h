@@ -183,10 +183,11 @@ int lcs_fourth_order_derivative(const float* arr, int n0, int n1, int dim, int i
 int lcs_spectral_norm_3x3(const double* vals, int64_t n, double* out, void* stream);
 
 /* ---------------------------------------------------------------- roofline microbenchmark
- * Same taps x taps vector-gather pattern as the integrator, no dependent arithmetic: the measured
- * upper bound for the L1/L2 gather roofline.  vec_width = values per tap (4: PAIR4 elements, 32 B
- * in f64 -- the reference formulation's bytes; 2: ES elements).  jitter: displacement amplitude in
- * grid cells applied to the start grid (smooth field). */
+ * Same taps x taps vector-gather pattern and thread tiling as the integrator with nothing else in the
+ * loop (integer positions, one add per loaded value, all rounds independent): the measured upper bound
+ * for the L1/L2 gather roofline.  vec_width = values per tap (4: PAIR4 elements, 32 B in f64 -- the
+ * reference formulation's bytes; 2: ES elements).  jitter: per-particle pseudo-random displacement of
+ * up to +-jitter cells on top of a coherent per-round shift (0 = neighbours stay neighbours). */
 int lcs_gather_peak(const void* pairs, int pair_dtype, int vec_width, int nlat, int nlon, int nrow, int ncol,
                     int nwindows, int taps, double jitter, int iters, double* sink, void* stream);
 

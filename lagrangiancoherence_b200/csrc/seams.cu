@@ -67,49 +67,47 @@ map_coordinates_kernel(const MapParams P) {
 }
 
 // ------------------------------------------------------------------ gather roofline microbenchmark
-// Same tap pattern as the integrator (TAPS x TAPS neighbourhood of packed pairs around a smoothly
-// displaced copy of the start grid), no index folding, no dependent position update: the loads of
-// all `iters` rounds are independent, so the measured rate is what L1/L2 can deliver for this
-// access pattern.  Bytes counted = particles * iters * TAPS^2 * sizeof(pair).
+// Same tap pattern as the integrator (TAPS x TAPS neighbourhood of packed elements around a displaced
+// copy of the start grid) with nothing else in the loop: integer position arithmetic only (no index
+// folding, no weights, no dependent position update), one add per loaded value.  The loads of all
+// `iters` rounds are independent, so the measured rate is what the LSU/L1/L2 path can deliver for this
+// access pattern.  Every round shifts the whole grid by a few cells (coherent across a warp, like the
+// early sub-steps); `jitter` adds a per-particle pseudo-random displacement of up to +-jitter cells
+// (decorrelated neighbours, like late sub-steps).  Bytes counted = particles * iters * TAPS^2 * sizeof(element).
 template <typename E, int TAPS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 gather_peak_kernel(const typename E::type* __restrict__ pairs, int nlat, int nlon,
-                   int nrow, int ncol, double jitter, int iters, int band, double* sink) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    const int np = nrow * ncol;
-    if (p >= np) return;
-    const int w = blockIdx.y;
-    // banded enumeration identical to the integrator's
-    const int per_band = band * ncol;
-    const int nbands = (nrow + band - 1) / band;
-    int b = p / per_band;
-    if (b > nbands - 1) b = nbands - 1;
-    const int q = p - b * per_band;
-    const int h = (b == nbands - 1) ? (nrow - b * band) : band;
-    const int col = q / h;
-    const int row = b * band + (q - col * h);
-    const double sy = (double)(nlat - 1) / (double)(nrow > 1 ? nrow - 1 : 1);
-    const double sx = (double)(nlon - 1) / (double)(ncol > 1 ? ncol - 1 : 1);
+                   int nrow, int ncol, int jitter, int iters, int band_log2, double* sink) {
+    const int r = threadIdx.x & ((1 << band_log2) - 1), c = threadIdx.x >> band_log2;
+    const int row = blockIdx.y * (1 << band_log2) + r;
+    const int col = blockIdx.x * (256 >> band_log2) + c;
+    if (row >= nrow || col >= ncol) return;
+    const int w = blockIdx.z;
+    const int by = (int)((long long)row * (nlat - 1) / (nrow > 1 ? nrow - 1 : 1));
+    const int bx = (int)((long long)col * (nlon - 1) / (ncol > 1 ? ncol - 1 : 1));
+    const unsigned seed = (unsigned)(row * ncol + col) * 2654435761u + (unsigned)w * 40503u;
     double acc[E::NV];
 #pragma unroll
     for (int v = 0; v < E::NV; ++v) acc[v] = 0.0;
     for (int it = 0; it < iters; ++it) {
-        const double ph = 0.37 * (it + 1) + 0.11 * w;
-        const double fy = row * sy + jitter * sin(0.05 * col + ph);
-        const double fx = col * sx + jitter * cos(0.05 * row - ph);
-        int iy = (int)floor(fy) - (TAPS / 2 - 1), ix = (int)floor(fx) - (TAPS / 2 - 1);
+        int iy = by + ((it * 3 + w) & 7) - (TAPS / 2 - 1), ix = bx + ((it * 5 + w) & 7) - (TAPS / 2 - 1);
+        if (jitter > 0) {
+            const unsigned h = seed ^ ((unsigned)it * 2246822519u);
+            iy += (int)((h >> 8) % (unsigned)(2 * jitter + 1)) - jitter;
+            ix += (int)((h >> 20) % (unsigned)(2 * jitter + 1)) - jitter;
+        }
         iy = max(0, min(iy, nlat - TAPS));
         ix = max(0, min(ix, nlon - TAPS));
         const typename E::type* base = pairs + (size_t)iy * nlon + ix;
 #pragma unroll
         for (int i = 0; i < TAPS; ++i) {
-            double c[TAPS][E::NV];
+            double cc[TAPS][E::NV];
 #pragma unroll
-            for (int j = 0; j < TAPS; ++j) E::ld(base + (size_t)i * nlon + j, c[j]);
+            for (int j = 0; j < TAPS; ++j) E::ld(base + (size_t)i * nlon + j, cc[j]);
 #pragma unroll
             for (int j = 0; j < TAPS; ++j) {
 #pragma unroll
-                for (int v = 0; v < E::NV; ++v) acc[v] += c[j][v];
+                for (int v = 0; v < E::NV; ++v) acc[v] += cc[j][v];
             }
         }
     }
@@ -148,17 +146,18 @@ extern "C" int lcs_map_coordinates(const lcs_grid* g, const double* field, const
 extern "C" int lcs_gather_peak(const void* pairs, int pair_dtype, int vec_width, int nlat, int nlon, int nrow, int ncol,
                                int nwindows, int taps, double jitter, int iters, double* sink, void* stream) {
     if (!pairs || !sink) return lcs_fail(LCS_E_INVALID, "lcs_gather_peak: null argument");
-    if (nlat < 4 || nlon < 4 || nrow < 1 || ncol < 1 || nwindows < 1 || iters < 1)
+    if (nlat < 4 || nlon < 4 || nrow < 1 || ncol < 1 || nwindows < 1 || nwindows > 65535 || iters < 1 || jitter < 0)
         return lcs_fail(LCS_E_INVALID, "lcs_gather_peak: bad sizes");
     if ((taps != 2 && taps != 4) || (vec_width != 2 && vec_width != 4) || (pair_dtype != LCS_F64 && pair_dtype != LCS_F32))
         return lcs_fail(LCS_E_INVALID, "lcs_gather_peak: taps and vec_width must be 2 or 4");
-    const long long np = (long long)nrow * ncol;
-    const dim3 grid((unsigned)((np + 255) / 256), (unsigned)nwindows);
-    int band = lcs_env_int("LCS_ADVECT_BAND", 4);
-    if (band < 1) band = 1;
-    if (band > 32) band = 32;
+    int bl = lcs_env_int("LCS_ADVECT_BAND_LOG2", 1);       // same thread->particle tiling as the integrator
+    if (bl < 0) bl = 0;
+    if (bl > 5) bl = 5;
+    const int tw = 256 >> bl, th = 1 << bl;
+    const dim3 grid((unsigned)((ncol + tw - 1) / tw), (unsigned)((nrow + th - 1) / th), (unsigned)nwindows);
+    const int jit = (int)jitter;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define LCS_GP(EL, TP) gather_peak_kernel<EL, TP><<<grid, 256, 0, st>>>((const EL::type*)pairs, nlat, nlon, nrow, ncol, jitter, iters, band, sink)
+#define LCS_GP(EL, TP) gather_peak_kernel<EL, TP><<<grid, 256, 0, st>>>((const EL::type*)pairs, nlat, nlon, nrow, ncol, jit, iters, bl, sink)
     if (pair_dtype == LCS_F64) {
         if (vec_width == 4) { if (taps == 4) LCS_GP(Pair4<double>, 4); else LCS_GP(Pair4<double>, 2); }
         else { if (taps == 4) LCS_GP(Vec2<double>, 4); else LCS_GP(Vec2<double>, 2); }

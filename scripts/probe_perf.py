@@ -52,7 +52,7 @@ if __name__ == '__main__':
     sink = torch.zeros(1, dtype=torch.float64, device='cuda')
     buf = torch.zeros(281 * 321 * 32 + 1024, dtype=torch.uint8, device='cuda')
     for vec in (4, 2):
-        for jit in (0.0, 8.0, 40.0):
+        for jit in (0.0, 2.0, 8.0, 40.0):
             fn = lambda: _lib.check(lib.lcs_gather_peak(_ptr(buf), 0, vec, 281, 321, 281, 321, 64, 4, jit, 40, _ptr(sink), _stream(eng.device)), 'gp')
             t = timeit(fn)
             print('gather_peak vec', vec, 'jitter', jit, 'ms', t, 'GB/s', 64 * 281 * 321 * 40 * 16 * vec * 8 / t[0] / 1e6, flush=True)
