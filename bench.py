@@ -48,6 +48,7 @@ def parse():
     ap.add_argument('--precision', default='f64', choices=['f64', 'f32'])
     ap.add_argument('--workload', default='C2', choices=['C2', 'C3'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--chunk', type=int, default=148, help='windows per launch in the pipelined end-to-end path')
     return ap.parse_args()
 
 
@@ -274,7 +275,7 @@ def run_b200(args):
         a, b = ev(), ev()
         a.record()
         rolling.rolling_ftle(h_u, h_v, lat, lon, nt, dt, SETTLS_order=S_ORDER, interp_order=args.order,
-                             xclamp=args.xclamp, precision=args.precision, device=dev, out=h_out,
+                             xclamp=args.xclamp, precision=args.precision, device=dev, out=h_out, chunk=args.chunk,
                              engine=eng)
         b.record()
         barrier()

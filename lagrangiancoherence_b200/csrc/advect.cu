@@ -299,9 +299,9 @@ __device__ __forceinline__ bool slot_rc(const AdvectParams& P, int e, int& row, 
     return row < P.nrow && col < P.ncol;
 }
 
-template <int CS>
+template <bool CLUSTERED>
 __device__ __forceinline__ void window_sync() {
-    if (CS > 1) cg::this_cluster().sync();     // release/acquire at cluster scope: global writes become visible
+    if (CLUSTERED) cg::this_cluster().sync();  // release/acquire at cluster scope: global writes become visible
     else __syncthreads();
 }
 
@@ -358,14 +358,14 @@ __device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, int w, in
 #ifndef LCS_CLUSTER_MINBLOCKS
 #define LCS_CLUSTER_MINBLOCKS 2
 #endif
-template <typename T, bool STRICT, int ORDER, int LAYOUT, int CS>
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool CLUSTERED>
 __global__ void __launch_bounds__(kClusterThreads, LCS_CLUSTER_MINBLOCKS)
-advect_outer_cluster_kernel(const AdvectParams P) {
+advect_outer_cluster_kernel(const AdvectParams P, const int cs /* CTAs per window = cluster size (1..8) */) {
     extern __shared__ unsigned char s_flags[];            // [lt rows | lt cols | gt rows | gt cols]
-    const int w = blockIdx.x / CS;
-    const int rank = blockIdx.x - w * CS;
+    const int w = blockIdx.x / cs;
+    const int rank = blockIdx.x - w * cs;
     const int tid_w = rank * kClusterThreads + threadIdx.x;
-    const int nthr_w = CS * kClusterThreads;
+    const int nthr_w = cs * kClusterThreads;
     const int nflag = P.nrow + P.ncol;
     unsigned char* s_lt = s_flags;
     unsigned char* s_gt = s_flags + nflag;
@@ -381,7 +381,7 @@ advect_outer_cluster_kernel(const AdvectParams P) {
         // ---- phase A: pending clamps of q-1 (mirrored in smem), stage, y clamp, raise "< x_min" flags
         if (k == 0) cluster_phase_a<T, STRICT, ORDER, LAYOUT, true>(P, w, q, t, tid_w, nthr_w, s_lt, s_gt, spos, swind, cand, g_lt, g_cnt);
         else cluster_phase_a<T, STRICT, ORDER, LAYOUT, false>(P, w, q, t, tid_w, nthr_w, s_lt, s_gt, spos, swind, cand, g_lt, g_cnt);
-        window_sync<CS>();
+        window_sync<CLUSTERED>();
         // ---- phase B: mirror the "< x_min" flags; candidates that survive that pass raise "> x_max" flags
         for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_lt[i] = __ldcg(g_lt + i);
         __syncthreads();
@@ -391,7 +391,7 @@ advect_outer_cluster_kernel(const AdvectParams P) {
             slot_rc(P, __ldcg(cand + i), row, col);
             if (!(s_lt[row] && s_lt[P.nrow + col])) { g_gt[row] = 1; g_gt[P.nrow + col] = 1; }
         }
-        window_sync<CS>();
+        window_sync<CLUSTERED>();
         for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_gt[i] = __ldcg(g_gt + i);
         __syncthreads();
     }
@@ -416,23 +416,63 @@ advect_outer_cluster_kernel(const AdvectParams P) {
     }
 }
 
-template <typename T, bool STRICT, int ORDER, int LAYOUT, int CS>
-static cudaError_t launch_outer_cluster(const AdvectParams& P, int nwindows, cudaStream_t st) {
-    auto kern = advect_outer_cluster_kernel<T, STRICT, ORDER, LAYOUT, CS>;
-    const size_t smem = 2 * (size_t)(P.nrow + P.ncol);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+// Cluster size for `nwindows` windows: the driver reports how many clusters of each size can be co-resident
+// (cluster placement strands SMs: GPCs hold 16/18/20 SMs, so size 4 or 8 does not tile the 148 SMs);
+// a window takes time ~1/cs and the launch runs ceil(nwindows / resident(cs)) waves, so pick the cs that
+// minimises waves/cs.  Returns 0 when even the best choice leaves most of the machine idle.
+template <typename T, bool STRICT, int ORDER, int LAYOUT>
+static int choose_cluster_size(const AdvectParams& P, int nwindows, size_t smem, double* busy_frac) {
+    static int resident[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};           // per instantiation; smem differences are tiny
+    int best = 1;
+    double best_cost = 1e30;
+    for (int cs = 1; cs <= 8; ++cs) {
+        if (!resident[cs]) {
+            int n = 0;
+            if (cs == 1) {
+                auto k1 = advect_outer_cluster_kernel<T, STRICT, ORDER, LAYOUT, false>;
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, kClusterThreads, smem) == cudaSuccess)
+                    n = per_sm * lcs_sm_count();
+            } else {
+                auto kc = advect_outer_cluster_kernel<T, STRICT, ORDER, LAYOUT, true>;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(cs * 64)); cfg.blockDim = dim3(kClusterThreads); cfg.dynamicSmemBytes = smem;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                if (cudaOccupancyMaxActiveClusters(&n, kc, &cfg) != cudaSuccess) n = 0;
+            }
+            (void)cudaGetLastError();
+            resident[cs] = n > 0 ? n : -1;
+        }
+        if (resident[cs] <= 0) continue;
+        const int waves = (nwindows + resident[cs] - 1) / resident[cs];
+        const double cost = (double)waves / cs;
+        if (cost < best_cost - 1e-12) { best_cost = cost; best = cs; }
+    }
+    const int forced = lcs_env_int("LCS_OUTER_CLUSTER", 0);
+    if (forced >= 1 && forced <= 8 && resident[forced] > 0) best = forced;
+    if (resident[best] <= 0) { *busy_frac = 0.0; return 0; }
+    const int waves = (nwindows + resident[best] - 1) / resident[best];
+    *busy_frac = (double)nwindows * best / ((double)waves * lcs_sm_count() * LCS_CLUSTER_MINBLOCKS);
+    return best;
+}
+
+template <typename T, bool STRICT, int ORDER, int LAYOUT>
+static cudaError_t launch_outer_cluster(const AdvectParams& P, int nwindows, int cs, size_t smem, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(nwindows * CS));
+    cfg.gridDim = dim3((unsigned)(nwindows * cs));
     cfg.blockDim = dim3(kClusterThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, P);
+    if (cs == 1) return cudaLaunchKernelEx(&cfg, advect_outer_cluster_kernel<T, STRICT, ORDER, LAYOUT, false>, P, cs);
+    return cudaLaunchKernelEx(&cfg, advect_outer_cluster_kernel<T, STRICT, ORDER, LAYOUT, true>, P, cs);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -449,20 +489,13 @@ static cudaError_t launch_advect(const AdvectParams& P, int nwindows, cudaStream
     // Enough windows to fill the machine: one persistent cluster per window (cluster barriers).
     // Few windows: one launch pair per sub-step over all particles (kernel-boundary barriers).
     const int mode = lcs_env_int("LCS_OUTER_MODE", 0);          // 0 auto, 1 phased launches, 2 clusters
-    const int slots = lcs_sm_count() * LCS_CLUSTER_MINBLOCKS;    // 512-thread CTAs per SM
-    if (P.nsub > 0 && 2 * (size_t)(P.nrow + P.ncol) <= 64 * 1024 && mode != 1) {
-        int cs = 8;
-        while (cs > 1 && nwindows * cs > slots) cs >>= 1;
-        const int forced = lcs_env_int("LCS_OUTER_CLUSTER", 0);
-        if (forced == 1 || forced == 2 || forced == 4 || forced == 8) cs = forced;
-        if (mode == 2 || nwindows * cs * 2 >= slots) {
+    const size_t smem = 2 * (size_t)(P.nrow + P.ncol);
+    if (P.nsub > 0 && smem <= 48 * 1024 && mode != 1) {
+        double busy = 0.0;
+        const int cs = choose_cluster_size<T, STRICT, ORDER, LAYOUT>(P, nwindows, smem, &busy);
+        if (cs > 0 && (mode == 2 || busy >= 0.45)) {
             lcs_count_launches(1);
-            switch (cs) {
-                case 8: return launch_outer_cluster<T, STRICT, ORDER, LAYOUT, 8>(P, nwindows, st);
-                case 4: return launch_outer_cluster<T, STRICT, ORDER, LAYOUT, 4>(P, nwindows, st);
-                case 2: return launch_outer_cluster<T, STRICT, ORDER, LAYOUT, 2>(P, nwindows, st);
-                default: return launch_outer_cluster<T, STRICT, ORDER, LAYOUT, 1>(P, nwindows, st);
-            }
+            return launch_outer_cluster<T, STRICT, ORDER, LAYOUT>(P, nwindows, cs, smem, st);
         }
     }
     const dim3 ggrid(4, (unsigned)nwindows);
