@@ -106,7 +106,13 @@ class DataArray:
         return DataArray(vals, dims, coords, self.name)
 
     def sortby(self, dim, ascending=True):
-        order = np.argsort(self.coords[dim], kind='stable')
+        c = self.coords[dim]
+        d = np.diff(c)
+        if ascending and (d > 0).all():                 # already sorted: no copy (13 MB per wind array at C2)
+            return self
+        if ascending and (d < 0).all():                 # ERA5-style descending latitude: a reversed view
+            return self.isel({dim: slice(None, None, -1)})
+        order = np.argsort(c, kind='stable')
         if not ascending:
             order = order[::-1]
         return self.isel({dim: order})

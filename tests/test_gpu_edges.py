@@ -115,3 +115,20 @@ def test_capi_rejects_bad_arguments_on_device(cuda_device, case):
     with pytest.raises(_lib.LcsError, match='halo'):
         x, y = eng.advect(st, rows=(10, 20))
         eng.epilogue(x, y, in_row0=10, out_rows=(10, 20))       # band without its 2-row halo
+
+
+def test_float32_inputs_agree_with_reference_at_its_own_f32_noise(cuda_device, case):
+    """With f32 winds AND f32 coordinates (how xarray decodes ERA5 NetCDF) numpy's dtype propagation makes the
+    reference integrate entirely in f32 (meshgrid of f32 coordinates, f32 samples, f32 updates: trajectory.py:68-70,
+    86-87).  The engine promotes to f64; the two agree to the reference's own f32 rounding noise, not to 1e-10.
+    Stated tolerance: departure points within 2e-5 relative (a few hundred f32 ulps accumulated over the sub-steps)."""
+    from lagrangiancoherence_b200.LCS.trajectory import parcel_propagation
+    u, v, lat, lon = case
+    u32, v32, lat32, lon32 = u.astype(np.float32), v.astype(np.float32), lat.astype(np.float32), lon.astype(np.float32)
+    rx, ry = O.parcel_propagation(u32, v32, lat32, lon32, -3600, SETTLS_order=4, xclamp='outer')
+    assert rx.dtype == np.float32 and ry.dtype == np.float32            # the reference's result is f32 here
+    du, dv, _ = arrays(u32, v32, lat32, lon32)
+    x, y = parcel_propagation(du, dv, timestep=-3600, SETTLS_order=4, verbose=False)
+    assert x.values.dtype == np.float64
+    assert np.abs(x.values - rx).max() <= 2e-5 * np.abs(lon).max()
+    assert np.abs(y.values - ry).max() <= 2e-5 * np.abs(lat).max()
