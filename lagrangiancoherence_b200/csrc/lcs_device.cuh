@@ -100,22 +100,10 @@ __device__ __forceinline__ double fold_wrap(double c, int n) {
     return c;
 }
 
-// scipy spline_mode mirror for out-of-range tap indices: d c b | a b c d | c b a
-__device__ __forceinline__ int mirror_idx(int i, int n) {
-    if (i < 0) {
-        const int sz2 = 2 * n - 2;
-        i = sz2 * (-i / sz2) + i;
-        i = (i <= 1 - n) ? i + sz2 : -i;
-    } else if (i > n - 1) {
-        const int sz2 = 2 * n - 2;
-        i -= sz2 * (i / sz2);
-        if (i >= n) i = sz2 - i;
-    }
-    return i;
-}
-
-// The same reflection for the indices a gather can actually produce: coordinates are folded into [0, n-1]
-// first, so taps lie in [-1, n+1]; for n >= 3 that needs no division: -1 -> 1, n -> n-2, n+1 -> n-3.
+// scipy's spline_mode mirror for out-of-range tap indices is d c b | a b c d | c b a.
+// The indices a gather can actually produce: coordinates are folded into [0, n-1] first (or rejected by
+// the 'constant' branch), so taps lie in [-1, n+1]; for n >= 3 the reflection needs no division:
+// -1 -> 1, n -> n-2, n+1 -> n-3 (scipy's general formula, oracle.mirror_index, reduces to this).
 __device__ __forceinline__ int mirror_near(int i, int n) {
     return i < 0 ? -i : (i > n - 1 ? 2 * (n - 1) - i : i);
 }
