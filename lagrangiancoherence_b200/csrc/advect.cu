@@ -314,18 +314,14 @@ __device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, int w, in
                                                 double2* __restrict__ spos, double2* __restrict__ swind,
                                                 int* cand, unsigned char* g_lt, int* g_cnt) {
     const int pair = P.level0 + w * P.level_stride + t;
-    double2 s_nxt = make_double2(0.0, 0.0), w_nxt = make_double2(0.0, 0.0);
-    if (tid_w < P.nslots) {
-        if (q != 0) s_nxt = __ldcs(spos + tid_w);
-        if (!EULER) w_nxt = __ldcs(swind + tid_w);
-    }
+    double2 s_nxt = make_double2(0.0, 0.0);
+    if (tid_w < P.nslots && q != 0) s_nxt = __ldcs(spos + tid_w);
     for (int e = tid_w; e < P.nslots; e += nthr_w) {
-        const double2 s = s_nxt, wv = w_nxt;
+        const double2 s = s_nxt;
+        double2 wv = make_double2(0.0, 0.0);
+        if (!EULER) wv = __ldcs(swind + e);
         const int en = e + nthr_w;
-        if (en < P.nslots) {                                   // prefetch: independent of this slot's work
-            if (q != 0) s_nxt = __ldcs(spos + en);
-            if (!EULER) w_nxt = __ldcs(swind + en);
-        }
+        if (en < P.nslots && q != 0) s_nxt = __ldcs(spos + en);  // prefetch: independent of this slot's work
         int row, col;
         if (!slot_rc(P, e, row, col)) continue;
         const int grow = P.row0 + row;
