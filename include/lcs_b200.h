@@ -182,6 +182,14 @@ int lcs_fourth_order_derivative(const float* arr, int n0, int n1, int dim, int i
  * feeds it: vals = nine stacked planes of N points (plane k = entry k of the row-major 3x3). */
 int lcs_spectral_norm_3x3(const double* vals, int64_t n, double* out, void* stream);
 
+/* lcs_ridge_classify: the per-point loop of find_ridges_spherical_hessian (tools.py:93-136): clean the Hessian
+ * (inf, NaN -> 0), eigen-decompose [[hxx, hxy], [hxy, hyy]] with LAPACK's dgeev/dlanv2 conventions (order of the
+ * eigenvalues, signs of the eigenvectors), dt = dot(ROW argmin(eigvals) of the eigenvector matrix, gradient) as
+ * executed upstream, eigmin = eigenvalue of largest magnitude, dt_prod = 1 where not(|dt| > tolerance) and
+ * eigmin < 0 else 0.  All arrays: device f64 [n]. */
+int lcs_ridge_classify(const double* hxx, const double* hxy, const double* hyy, const double* gx, const double* gy,
+                       int64_t n, double tolerance, double* dt_prod, double* eigmin, void* stream);
+
 /* ---------------------------------------------------------------- roofline microbenchmark
  * Same taps x taps vector-gather pattern and thread tiling as the integrator with nothing else in the
  * loop (integer positions, one add per loaded value, all rounds independent): the measured upper bound

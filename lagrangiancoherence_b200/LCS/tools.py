@@ -47,3 +47,57 @@ def derivative_spherical_coords(da, dim=0, isglobal=True, *, device='cuda:0'):
     else:
         deriv = deriv / torch.from_numpy(np.ascontiguousarray(dx, dtype=np.float64)).to(deriv.device)[:, None]  # :264
     return make_like(da, deriv.cpu().numpy(), ('latitude', 'longitude'), {'latitude': lat, 'longitude': lon})
+
+
+def _dsc_device(t, lat, lon, dim, isglobal, device):
+    """derivative_spherical_coords on a device tensor (lat, lon): f32 cast, stencil kernel, f64 division."""
+    import torch
+    lib = _engine._lib.load()
+    a = t.float().contiguous()                                                    # tools.py:258
+    out = torch.empty_like(a)
+    _engine._lib.check(lib.lcs_fourth_order_derivative(_engine._ptr(a), a.shape[0], a.shape[1], int(dim),
+                                                       int(bool(isglobal)), _engine._ptr(out),
+                                                       _engine._stream(a.device)), 'lcs_fourth_order_derivative')
+    y = lat * np.pi / 180
+    if dim == 0:
+        dy = (np.pi / 180) * (lat[1] - lat[0]) * EARTH_RADIUS
+        return out.double() / torch.tensor(float(dy), dtype=torch.float64, device=a.device)
+    dx = (np.pi / 180) * (lon[1] - lon[0]) * EARTH_RADIUS * np.cos(y)
+    return out.double() / torch.from_numpy(np.ascontiguousarray(dx, dtype=np.float64)).to(a.device)[:, None]
+
+
+def find_ridges_spherical_hessian(da, sigma=.5, scheme='first_order', tolerance_threshold=0.0005e-3,
+                                  return_eigvectors=False, isglobal=True, *, device='cuda:0'):
+    """Hessian ridge filter of an FTLE field in spherical coordinates (tools.py:52-155), as executed upstream:
+    Gaussian smoothing on the (longitude, latitude) transpose, five stencil passes that each re-cast to f32, the
+    Hessian's inf/NaN zeroed, and a per-point 2x2 eigen-decomposition whose eigenvector ROW (sic, tools.py:108) is
+    dotted with the gradient.  Returns ``(dt_prod, eigmin)`` in the input's dimension order; ``scheme`` is accepted
+    and ignored, as upstream.  ``return_eigvectors=True`` (four more diagnostic arrays) is not implemented."""
+    import torch
+    if return_eigvectors:
+        raise NotImplementedError('return_eigvectors=True is not implemented')
+    dims_in = tuple(da.dims)
+    d2 = da.sortby('latitude').sortby('longitude').transpose('latitude', 'longitude')
+    lat, lon = coord_values(d2, 'latitude'), coord_values(d2, 'longitude')
+    dev = torch.device(device)
+    eng = _engine.FtleEngine(lat, lon, 1, device=dev)
+    with torch.cuda.device(dev):
+        f = torch.from_numpy(np.ascontiguousarray(d2.values, dtype=np.float64)).to(dev)
+        if isinstance(sigma, (float, int)):                                           # tools.py:75-76, (lon, lat) layout
+            f = eng.gaussian(f.t().contiguous(), sigma).t().contiguous()
+        ddadx = _dsc_device(f, lat, lon, 1, isglobal, dev)                            # tools.py:78-82
+        ddady = _dsc_device(f, lat, lon, 0, isglobal, dev)
+        d2x2 = _dsc_device(ddadx, lat, lon, 1, isglobal, dev)
+        d2y2 = _dsc_device(ddady, lat, lon, 0, isglobal, dev)
+        d2xy = _dsc_device(ddadx, lat, lon, 0, isglobal, dev)
+        dt_prod, eigmin = torch.empty_like(f), torch.empty_like(f)
+        lib = _engine._lib.load()
+        _engine._lib.check(lib.lcs_ridge_classify(*[_engine._ptr(t.contiguous()) for t in (d2x2, d2xy, d2y2, ddadx, ddady)],
+                                                  f.numel(), float(tolerance_threshold), _engine._ptr(dt_prod),
+                                                  _engine._ptr(eigmin), _engine._stream(dev)), 'lcs_ridge_classify')
+    coords = {'latitude': lat, 'longitude': lon}
+    out = []
+    for t in (dt_prod, eigmin):
+        r = make_like(da, t.cpu().numpy(), ('latitude', 'longitude'), coords)
+        out.append(r.transpose(*dims_in))
+    return tuple(out)

@@ -90,3 +90,60 @@ extern "C" int lcs_gaussian_filter2d(const double* in, double* out, double* scra
     lcs_count_launches(2);
     return LCS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Ridge classification of find_ridges_spherical_hessian (tools.py:93-136), one thread per point.
+// The reference loops np.linalg.eig over 2x2 Hessians (tools.py:105-121); LAPACK's dgeev reduces a
+// symmetric [[a,b],[b,d]] with dlanv2, which fixes both the ORDER of the eigenvalues (rt1 is the one
+// on a's side: z = p + sign(sqrt(p^2+b^2), p), p = (a-d)/2) and the eigenvector matrix
+// [[cs,-sn],[sn,cs]], (cs,sn) = (z,b)/hypot(b,z).  Upstream then takes a ROW of that matrix
+// (eig[1][argmin(eig[0])], tools.py:108) -- reproduced as executed.  Eigenvalues equal LAPACK's bit
+// for bit; eigenvector entries to one ulp (dgeev renormalises), which only matters exactly at the
+// |dt| = tolerance threshold.
+namespace lcs {
+
+__device__ __forceinline__ double clean_hess(double h) { return (isinf(h) || isnan(h)) ? 0.0 : h; }   // tools.py:93-94
+
+__global__ void __launch_bounds__(256)
+ridge_classify_kernel(const double* __restrict__ hxx, const double* __restrict__ hxy, const double* __restrict__ hyy,
+                      const double* __restrict__ gx, const double* __restrict__ gy, long long n, double tol,
+                      double* __restrict__ dt_prod, double* __restrict__ eigmin) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double a = clean_hess(hxx[i]), b = clean_hess(hxy[i]), d = clean_hess(hyy[i]);
+    double rt1, rt2, cs, sn;
+    if (b == 0.0) { rt1 = a; rt2 = d; cs = 1.0; sn = 0.0; }
+    else {
+        const double p = __dmul_rn(0.5, __dsub_rn(a, d));
+        const double bc = fabs(b);
+        const double scale = fmax(fabs(p), bc);
+        double z = __dadd_rn(__dmul_rn(__ddiv_rn(p, scale), p), __dmul_rn(__ddiv_rn(bc, scale), bc));
+        z = __dadd_rn(p, copysign(__dmul_rn(sqrt(scale), sqrt(z)), p));
+        rt1 = __dadd_rn(d, z);
+        rt2 = __dsub_rn(d, __dmul_rn(__ddiv_rn(bc, z), bc));
+        const double tau = hypot(b, z);
+        cs = __ddiv_rn(z, tau); sn = __ddiv_rn(b, tau);
+    }
+    const bool first = !(rt2 < rt1);                       // np.argmin: first index on ties
+    const double r0 = first ? cs : sn, r1 = first ? -sn : cs;
+    const double dt = __dadd_rn(__dmul_rn(r0, gx[i]), __dmul_rn(r1, gy[i]));                 // tools.py:116
+    const double em = (fabs(rt1) >= fabs(rt2)) ? rt1 : rt2;                                  // tools.py:119
+    eigmin[i] = em;
+    dt_prod[i] = (!(fabs(dt) > tol) && em < 0.0) ? 1.0 : 0.0;                                 // tools.py:134-136
+}
+
+}  // namespace lcs
+
+extern "C" int lcs_ridge_classify(const double* hxx, const double* hxy, const double* hyy, const double* gx,
+                                  const double* gy, int64_t n, double tolerance, double* dt_prod, double* eigmin,
+                                  void* stream) {
+    if (!hxx || !hxy || !hyy || !gx || !gy || !dt_prod || !eigmin) return lcs_fail(LCS_E_INVALID, "lcs_ridge_classify: null argument");
+    if (n < 0) return lcs_fail(LCS_E_INVALID, "lcs_ridge_classify: negative n");
+    if (n == 0) return LCS_OK;
+    lcs::ridge_classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        hxx, hxy, hyy, gx, gy, n, tolerance, dt_prod, eigmin);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_ridge_classify");
+    lcs_count_launches(1);
+    return LCS_OK;
+}

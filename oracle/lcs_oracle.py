@@ -310,6 +310,59 @@ def subdomain_mask(lat, lon, subdomain):
 
 
 # --------------------------------------------------------------------------------------
+# find_ridges_spherical_hessian (tools.py:52-155)
+# --------------------------------------------------------------------------------------
+def find_ridges_spherical_hessian(field, lat, lon, sigma=.5, tolerance_threshold=0.0005e-3, isglobal=True):
+    """Hessian ridge filter of an FTLE field ``(nlat, nlon)``; returns ``(dt_prod, eigmin)``.
+
+    As executed: Gaussian smoothing on the (longitude, latitude) transpose (tools.py:70-76), five
+    derivative_spherical_coords passes, each re-casting its input to f32 (:78-82), inf/NaN of the Hessian set to 0
+    (:93-94), then per point ``np.linalg.eig`` of [[xx, xy], [xy, yy]] with the upstream quirk that a ROW of the
+    eigenvector matrix is taken (:108): ``dt = dot(eig[1][argmin(eig[0])], gradient)``;
+    ``eigmin = eig[0][argmax(|eig[0]|)]`` (:119); ``dt_prod = 1`` where not(|dt| > tol) and eigmin < 0, else 0 (:134-136)."""
+    f = np.asarray(field, dtype=np.float64)
+    if isinstance(sigma, (float, int)):
+        f = gaussian_filter(f.T, sigma=sigma).T                                         # :75-76
+    ddadx = derivative_spherical_coords(f, lat, lon, dim=1, isglobal=isglobal)          # :78
+    ddady = derivative_spherical_coords(f, lat, lon, dim=0, isglobal=isglobal)          # :79
+    d2dadx2 = derivative_spherical_coords(ddadx, lat, lon, dim=1, isglobal=isglobal)    # :80
+    d2dady2 = derivative_spherical_coords(ddady, lat, lon, dim=0, isglobal=isglobal)    # :81
+    d2dadxdy = derivative_spherical_coords(ddadx, lat, lon, dim=0, isglobal=isglobal)   # :82
+    hess = np.stack([d2dadx2, d2dadxdy, d2dadxdy, d2dady2]).reshape(4, -1)
+    hess = np.where(np.abs(hess) != np.inf, hess, 0)                                    # :93
+    hess = np.where(~np.isnan(hess), hess, 0)                                           # :94
+    grad = np.stack([ddadx, ddady]).reshape(2, -1)
+    H = hess.T.reshape(-1, 2, 2)
+    w, v = np.linalg.eig(H)                                                             # :107, one LAPACK call per point
+    n = np.arange(H.shape[0])
+    row = v[n, np.argmin(w, axis=1)]                                                    # :108 (a row, not a column)
+    dt = row[:, 0] * grad[0] + row[:, 1] * grad[1]                                      # :116 np.dot of two 2-vectors
+    eigmin = w[n, np.argmax(np.abs(w), axis=1)]                                         # :119
+    dt_prod = np.where(np.abs(dt) > tolerance_threshold, 0.0, 1.0)                      # :134-135 (NaN -> 1)
+    dt_prod = np.where(np.sign(eigmin) == -1, dt_prod, 0.0)                             # :136
+    return dt_prod.reshape(f.shape), eigmin.reshape(f.shape)
+
+
+def eig_sym2x2_lapack(a, b, d):
+    """What ``np.linalg.eig`` (LAPACK dgeev -> dlanv2) returns for [[a, b], [b, d]]: eigenvalues in the order
+    (rt1, rt2) and the rotation (cs, sn) with eigenvector matrix [[cs, -sn], [sn, cs]] (before dgeev's final
+    renormalisation, which moves entries by at most one ulp).  The spec of the CUDA ridge kernel."""
+    a, b, d = (np.asarray(t, dtype=np.float64) for t in (a, b, d))
+    with np.errstate(all='ignore'):
+        p = 0.5 * (a - d)
+        bc = np.abs(b)
+        scale = np.maximum(np.abs(p), bc)
+        z = p / scale * p + bc / scale * bc
+        z = p + np.copysign(np.sqrt(scale) * np.sqrt(z), p)
+        rt1 = d + z
+        rt2 = d - bc / z * bc
+        tau = np.hypot(b, z)
+        cs, sn = z / tau, b / tau
+    diag = b == 0
+    return (np.where(diag, a, rt1), np.where(diag, d, rt2), np.where(diag, 1.0, cs), np.where(diag, 0.0, sn))
+
+
+# --------------------------------------------------------------------------------------
 # resample= (LCS.py:88-91): u.resample({timedim: freq}).interpolate('linear')
 # --------------------------------------------------------------------------------------
 def resample_linear(U, times, freq):

@@ -156,6 +156,12 @@ def main():
     seams['resample_sigma'], seams['resample_x_dep'], seams['resample_y_dep'] = rs[0].values, rs[1].values, rs[2].values
     seams['resample_time'] = np.asarray(rs[0].coords['time']).astype('datetime64[ns]').astype('int64')
     seams['gauss_sigma_field'] = gs.values
+    # find_ridges_spherical_hessian (tools.py:52-155) on 0.5*log(sigma) of the gauss-smoothed field
+    ftle = 0.5 * np.log(np.where(gs.values[0] > 0, gs.values[0], np.nan))
+    ftle = np.where(np.isfinite(ftle), ftle, 0.0)
+    fda = xr.DataArray(ftle, {'latitude': lat, 'longitude': lon}, ('latitude', 'longitude'))
+    ridges, eigmin = ref_tools.find_ridges_spherical_hessian(fda, sigma=1.2, tolerance_threshold=0.002e-3)
+    seams['ridge_input'], seams['ridge_dt_prod'], seams['ridge_eigmin'] = ftle, ridges.values, eigmin.values
     seams['subdomain_sigma'] = eig.values
     seams['subdomain_lat'], seams['subdomain_lon'] = eig.coords['latitude'], eig.coords['longitude']
     np.savez_compressed(os.path.join(GOLDEN, 'seams.npz'), **seams)

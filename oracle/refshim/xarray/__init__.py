@@ -81,7 +81,26 @@ class DataArray:
         coords = self.__dict__.get('coords', {})
         if item in coords:
             return self[item]
+        stack = self.__dict__.get('_stack')
+        if stack is not None and item == stack[0]:        # hessian.points: the stacked index (tools.py:96)
+            return self
         raise AttributeError(item)
+
+    def sel(self, **kw):
+        (dim, index), = kw.items()
+        assert self._stack is not None and dim == self._stack[0], 'refshim: sel is only implemented on a stacked dim'
+        a, b = self._stack[1]
+        mine = list(zip(self.coords['_' + a].tolist(), self.coords['_' + b].tolist()))
+        want = list(zip(index.coords['_' + a].tolist(), index.coords['_' + b].tolist()))
+        if mine == want:
+            return self
+        pos = {k: i for i, k in enumerate(mine)}
+        idx = np.array([pos[k] for k in want])
+        ax = self.dims.index(dim)
+        coords = {k: (v[idx] if k.startswith('_') else v) for k, v in self.coords.items()}
+        out = DataArray(np.take(self.values, idx, axis=ax), coords, self.dims, self.name)
+        out._stack = self._stack
+        return out
 
     def _new(self, values, dims=None, coords=None):
         dims = self.dims if dims is None else tuple(dims)
@@ -240,8 +259,8 @@ class DataArray:
         else:
             dims, x, y, coords = list(self.dims), self.values, other, self.coords
         res = op(y, x) if reflected else op(x, y)
-        out = DataArray(res, {k: v for k, v in coords.items() if v.ndim == 0 or k in dims}, dims, self.name)
-        out._stack = self._stack
+        out = DataArray(res, {k: v for k, v in coords.items() if v.ndim == 0 or k in dims or k.startswith('_')}, dims, self.name)
+        out._stack = self._stack if self._stack is not None else (other._stack if _is_da(other) else None)
         return out
 
     def __array_ufunc__(self, ufunc, method, *inputs, **kwargs):
@@ -264,6 +283,9 @@ class DataArray:
     __rtruediv__ = lambda s, o: s._binary(o, np.true_divide, True)
     __mod__ = lambda s, o: s._binary(o, np.mod)
     __pow__ = lambda s, o: s._binary(o, np.power)
+    __eq__ = lambda s, o: s._binary(o, np.equal)
+    __ne__ = lambda s, o: s._binary(o, np.not_equal)
+    __hash__ = None
     __lt__ = lambda s, o: s._binary(o, np.less)
     __gt__ = lambda s, o: s._binary(o, np.greater)
     __le__ = lambda s, o: s._binary(o, np.less_equal)
@@ -306,6 +328,8 @@ class DataArray:
         return out
 
     def unstack(self, dim=None):
+        if self._stack is None or self._stack[0] not in self.dims:
+            return self                                   # nothing stacked (tools.py:147 unstacks twice)
         new, (a, b) = self._stack
         ca, cb = self.coords['_' + a], self.coords['_' + b]
         ua, ub = np.unique(ca), np.unique(cb)            # unused index levels are dropped, as xarray does
@@ -316,7 +340,7 @@ class DataArray:
         out[..., np.searchsorted(ua, ca), np.searchsorted(ub, cb)] = v
         coords = {k: val for k, val in self.coords.items() if not k.startswith('_')}
         coords[a], coords[b] = ua, ub
-        return DataArray(out, coords, lead + [a, b], self.name)
+        return DataArray(out, coords, lead + [a, b], self.name)      # _stack is None again
 
 
 class _Resampler:
@@ -395,7 +419,9 @@ def broadcast(*args):
         v = a.values.transpose([a.dims.index(d) for d in dims if d in a.dims])
         v = v.reshape([shape[d] if d in a.dims else 1 for d in dims])
         v = np.broadcast_to(v, [shape[d] for d in dims]).copy()
-        out.append(DataArray(v, {k: c for k, c in coords.items() if c.ndim == 0 or k in dims}, dims, a.name))
+        o = DataArray(v, {k: c for k, c in coords.items() if c.ndim == 0 or k in dims or k.startswith('_')}, dims, a.name)
+        o._stack = next((x._stack for x in args if x._stack is not None), None)
+        out.append(o)
     return tuple(out)
 
 

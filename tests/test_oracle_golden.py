@@ -101,3 +101,30 @@ def test_resample_plan_matches_oracle_weights():
     got = w_hi[:, None, None] * u[lo + 1] + w_lo[:, None, None] * u[lo]
     assert np.array_equal(got, ref)
     assert np.array_equal(got[::2], u)              # levels that coincide with input levels come back exactly
+
+
+def test_ridge_filter_reproduces_reference_bitwise():
+    """find_ridges_spherical_hessian (tools.py:52-155) through the unmodified reference, incl. the per-point
+    np.linalg.eig loop and its row-of-the-eigenvector-matrix quirk."""
+    g = load('seams')
+    _, _, lat, lon, _ = make_inputs(CASES['regional_outer_p3'])
+    dt_prod, eigmin = O.find_ridges_spherical_hessian(g['ridge_input'], lat, lon, sigma=1.2, tolerance_threshold=0.002e-3)
+    assert np.array_equal(dt_prod, g['ridge_dt_prod']) and np.array_equal(eigmin, g['ridge_eigmin'])
+    assert 0.02 < dt_prod.mean() < 0.98                           # a non-trivial mask
+
+
+def test_lapack_2x2_conventions_closed_form():
+    """The closed form the CUDA ridge kernel uses equals np.linalg.eig (dgeev/dlanv2) on symmetric 2x2 input:
+    eigenvalues bit for bit in LAPACK's order, eigenvectors to one ulp, incl. b = 0 and a = d."""
+    rng = np.random.default_rng(0)
+    n = 50000
+    a, d = rng.normal(size=n), rng.normal(size=n)
+    b = rng.normal(size=n) * rng.choice([0, 1, 1e-3, 1e3], size=n)
+    a[:10] = d[:10]
+    b[10:20] = 0
+    a[10:15] = d[10:15]
+    w, v = np.linalg.eig(np.stack([np.stack([a, b], -1), np.stack([b, d], -1)], -2))
+    rt1, rt2, cs, sn = O.eig_sym2x2_lapack(a, b, d)
+    assert np.array_equal(w[:, 0], rt1) and np.array_equal(w[:, 1], rt2)
+    for got, ref in ((v[:, 0, 0], cs), (v[:, 1, 0], sn), (v[:, 0, 1], -sn), (v[:, 1, 1], cs)):
+        assert np.abs(got - ref).max() <= 2.3e-16
