@@ -305,23 +305,33 @@ __device__ __forceinline__ void window_sync() {
     else __syncthreads();
 }
 
-// phase A of one sub-step for the slots owned by this thread.  The state of the NEXT slot is
-// requested before the current slot's gathers are issued (ncu: 28 % of all stall samples sat on the
-// first use of the state load, an L2/DRAM round trip at the head of every iteration).
+// phase A of one sub-step for the slots owned by this thread.  Everything that is uniform over the CTA
+// (window, sub-step, array bases) is re-derived from the constant bank where it is used instead of being
+// carried in registers across the gathers: at 64 registers the first version spilled its loop-invariant
+// pointers and its prefetched state (ncu: local-memory wavefronts = 25 % of the global-load wavefronts).
+#ifndef LCS_CLUSTER_PREFETCH
+#define LCS_CLUSTER_PREFETCH 2      // 0 none, 1 into L1, 2 into L2 (measured: see DESIGN.md)
+#endif
+__device__ __forceinline__ void prefetch_state(const void* p) {
+#if LCS_CLUSTER_PREFETCH == 1
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#elif LCS_CLUSTER_PREFETCH == 2
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#endif
+}
+
 template <typename T, bool STRICT, int ORDER, int LAYOUT, bool EULER>
-__device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, int w, int q, int t, int tid_w, int nthr_w,
-                                                const unsigned char* s_lt, const unsigned char* s_gt,
-                                                double2* __restrict__ spos, double2* __restrict__ swind,
-                                                int* cand, unsigned char* g_lt, int* g_cnt) {
-    const int pair = P.level0 + w * P.level_stride + t;
-    double2 s_nxt = make_double2(0.0, 0.0);
-    if (tid_w < P.nslots && q != 0) s_nxt = __ldcs(spos + tid_w);
+__device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, const int w, const int q, const int t,
+                                                const int tid_w, const int nthr_w,
+                                                const unsigned char* s_lt, const unsigned char* s_gt) {
+    const unsigned sbase = (unsigned)w * (unsigned)P.nslots;        // host guarantees nwindows*nslots < 2^32
     for (int e = tid_w; e < P.nslots; e += nthr_w) {
-        const double2 s = s_nxt;
-        double2 wv = make_double2(0.0, 0.0);
-        if (!EULER) wv = __ldcs(swind + e);
-        const int en = e + nthr_w;
-        if (en < P.nslots && q != 0) s_nxt = __ldcs(spos + en);  // prefetch: independent of this slot's work
+        double2* const ps = reinterpret_cast<double2*>(P.spos) + (sbase + (unsigned)e);
+        double2* const pw = reinterpret_cast<double2*>(P.swind) + (sbase + (unsigned)e);
+        if (e + nthr_w < P.nslots) {                                 // next slot's state: L2 by the time it is needed
+            if (q != 0) prefetch_state(ps + nthr_w);
+            if (!EULER) prefetch_state(pw + nthr_w);
+        }
         int row, col;
         if (!slot_rc(P, e, row, col)) continue;
         const int grow = P.row0 + row;
@@ -329,10 +339,12 @@ __device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, int w, in
         double x, y;
         if (q == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
         else {
+            const double2 s = __ldcs(ps);
             x = s.x; y = s.y;
             if (s_lt[row] && s_lt[P.nrow + col]) x = P.lon_min;      // trajectory.py:96
             if (s_gt[row] && s_gt[P.nrow + col]) x = P.lon_max;      // trajectory.py:97
         }
+        const int pair = P.level0 + w * P.level_stride + t;
         if (EULER) {
             if (P.x_traj) {                                    // level t is final once the pending passes ran
                 const size_t to = ((size_t)w * (P.nsteps + 1) + t) * P.np + (size_t)row * P.ncol + col;
@@ -340,14 +352,22 @@ __device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, int w, in
             }
             double ua, va;
             stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
-            __stcs(swind + e, make_double2(ua, va));
+            __stcs(pw, make_double2(ua, va));
         } else {
+            const double2 wv = __ldcs(pw);
             stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.hx + row), wv.x, wv.y, x, y);
         }
         y = clamp_y(y, P.lat_min, P.lat_max);
-        __stcs(spos + e, make_double2(x, y));
-        if (x < P.lon_min) { g_lt[row] = 1; g_lt[P.nrow + col] = 1; }
-        else if (x > P.lon_max) cand[atomicAdd(g_cnt, 1)] = e;
+        __stcs(ps, make_double2(x, y));
+        if (x < P.lon_min) {
+            unsigned char* g_lt = flag_slot(P, w, q, 0);
+            int r2, c2;
+            slot_rc(P, e, r2, c2);                                   // rare: re-derived rather than kept live
+            g_lt[r2] = 1; g_lt[P.nrow + c2] = 1;
+        } else if (x > P.lon_max) {
+            const int slot = atomicAdd(P.cand_count + (size_t)w * P.nsub + q, 1);
+            P.cand[(size_t)sbase + slot] = e;
+        }
     }
 }
 
@@ -365,33 +385,32 @@ advect_outer_cluster_kernel(const AdvectParams P, const int cs /* CTAs per windo
     const int nflag = P.nrow + P.ncol;
     unsigned char* s_lt = s_flags;
     unsigned char* s_gt = s_flags + nflag;
-    double2* spos = reinterpret_cast<double2*>(P.spos) + (size_t)w * P.nslots;
-    double2* swind = reinterpret_cast<double2*>(P.swind) + (size_t)w * P.nslots;
-    int* cand = P.cand + (size_t)w * P.nslots;
-    const int per = 1 + P.S;
-    for (int q = 0; q < P.nsub; ++q) {
-        const int t = q / per, k = q - t * per;
-        unsigned char* g_lt = flag_slot(P, w, q, 0);
-        unsigned char* g_gt = flag_slot(P, w, q, 1);
-        int* g_cnt = P.cand_count + (size_t)w * P.nsub + q;
-        // ---- phase A: pending clamps of q-1 (mirrored in smem), stage, y clamp, raise "< x_min" flags
-        if (k == 0) cluster_phase_a<T, STRICT, ORDER, LAYOUT, true>(P, w, q, t, tid_w, nthr_w, s_lt, s_gt, spos, swind, cand, g_lt, g_cnt);
-        else cluster_phase_a<T, STRICT, ORDER, LAYOUT, false>(P, w, q, t, tid_w, nthr_w, s_lt, s_gt, spos, swind, cand, g_lt, g_cnt);
-        window_sync<CLUSTERED>();
-        // ---- phase B: mirror the "< x_min" flags; candidates that survive that pass raise "> x_max" flags
-        for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_lt[i] = __ldcg(g_lt + i);
-        __syncthreads();
-        const int ncand = __ldcg(g_cnt);
-        for (int i = tid_w; i < ncand; i += nthr_w) {
-            int row, col;
-            slot_rc(P, __ldcg(cand + i), row, col);
-            if (!(s_lt[row] && s_lt[P.nrow + col])) { g_gt[row] = 1; g_gt[P.nrow + col] = 1; }
+    int q = 0;
+    for (int t = 0; t < P.nsteps; ++t) {
+        for (int k = 0; k <= P.S; ++k, ++q) {
+            // ---- phase A: pending clamps of q-1 (mirrored in smem), stage, y clamp, raise "< x_min" flags
+            if (k == 0) cluster_phase_a<T, STRICT, ORDER, LAYOUT, true>(P, w, q, t, tid_w, nthr_w, s_lt, s_gt);
+            else cluster_phase_a<T, STRICT, ORDER, LAYOUT, false>(P, w, q, t, tid_w, nthr_w, s_lt, s_gt);
+            window_sync<CLUSTERED>();
+            // ---- phase B: mirror the "< x_min" flags; candidates that survive that pass raise "> x_max" flags
+            const unsigned char* g_lt = flag_slot(P, w, q, 0);
+            unsigned char* g_gt = flag_slot(P, w, q, 1);
+            for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_lt[i] = __ldcg(g_lt + i);
+            __syncthreads();
+            const int ncand = __ldcg(P.cand_count + (size_t)w * P.nsub + q);
+            const int* cand = P.cand + (size_t)w * P.nslots;
+            for (int i = tid_w; i < ncand; i += nthr_w) {
+                int row, col;
+                slot_rc(P, __ldcg(cand + i), row, col);
+                if (!(s_lt[row] && s_lt[P.nrow + col])) { g_gt[row] = 1; g_gt[P.nrow + col] = 1; }
+            }
+            window_sync<CLUSTERED>();
+            for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_gt[i] = __ldcg(g_gt + i);
+            __syncthreads();
         }
-        window_sync<CLUSTERED>();
-        for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_gt[i] = __ldcg(g_gt + i);
-        __syncthreads();
     }
     // ---- final: pending clamps of the last sub-step, outputs
+    const double2* spos = reinterpret_cast<const double2*>(P.spos) + (size_t)w * P.nslots;
     for (int e = tid_w; e < P.nslots; e += nthr_w) {
         int row, col;
         if (!slot_rc(P, e, row, col)) continue;
@@ -593,6 +612,8 @@ extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_a
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
     if (o->xmode == LCS_X_CLAMP_OUTER) {
+        if ((unsigned long long)o->nwindows * (unsigned long long)P.nslots >= (1ULL << 32))
+            return lcs_fail(LCS_E_INVALID, "lcs_advect: outer clamp: nwindows * slots per window must stay below 2^32 (split the call)");
         const WsLayout L = ws_layout(p, o);
         char* wsb = static_cast<char*>(workspace);
         P.spos = reinterpret_cast<d2*>(wsb + L.pos);
