@@ -45,7 +45,9 @@ def parse():
     ap.add_argument('--xclamp', default='outer', choices=['outer', 'pointwise'],
                     help="x-boundary: 'outer' = what the reference executes (quirk Q6)")
     ap.add_argument('--order', type=int, default=3, choices=[1, 3])
-    ap.add_argument('--precision', default='f64', choices=['f64', 'f32'])
+    ap.add_argument('--precision', default='f64', choices=['f64', 'f32', 'f32fast'],
+                    help="'f64' parity path (default, the headline); 'f32' f32 packed winds with f64 tap arithmetic; "
+                         "'f32fast' f32 winds and f32 tap arithmetic (tolerance-tested fast path)")
     ap.add_argument('--workload', default='C2', choices=['C2', 'C3', 'C4'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--chunk', type=int, default=148, help='windows per launch in the pipelined end-to-end path')
@@ -192,7 +194,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     from lagrangiancoherence_b200 import synthetic as S, _lib, rolling
-    from lagrangiancoherence_b200.engine import FtleEngine, _ptr, _stream
+    from lagrangiancoherence_b200.engine import FtleEngine, _ptr, _stream, precision_args
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -208,13 +210,13 @@ def run_b200(args):
     npts = lat.size * lon.size
     # rank r owns start times [r*B, (r+1)*B) of one long synthetic series (start-time sharding)
     u, v = S.era5_like_winds(lat, lon, nlev, t0=rank * B)
-    if args.precision == 'f32':
+    if args.precision != 'f64':
         u, v = u.astype(np.float32), v.astype(np.float32)
     h_u = torch.from_numpy(u).pin_memory()
     h_v = torch.from_numpy(v).pin_memory()
     d_u, d_v = h_u.to(dev), h_v.to(dev)
     eng = FtleEngine(lat, lon, dt, SETTLS_order=S_ORDER, interp_order=args.order, xmode=args.xclamp,
-                     pair_dtype=args.precision, device=dev)
+                     device=dev, **precision_args(args.precision))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     gathered = [torch.empty((B, lat.size, lon.size), dtype=torch.float64, device=dev) for _ in range(world)] \
         if world > 1 else None
@@ -364,7 +366,8 @@ def run_b200(args):
     line = {
         'metric': METRIC, 'value': value, 'unit': 'particle-steps/s', 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f64' if args.precision == 'f64' else 'f32 winds / f64 positions',
+        'vs_baseline': None, 'dtype': {'f64': 'f64', 'f32': 'f32 winds / f64 tap arithmetic and positions',
+                                       'f32fast': 'f32 winds and tap arithmetic / f64 index map and positions'}[args.precision],
         'data': 'synthetic', 'config': config_dict(args, desc, B, world),
         'fields_per_s': world * B * args.steps / (total_ms * 1e-3),
         'interpolations_per_s': value * (2 + 4 * S_ORDER),

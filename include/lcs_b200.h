@@ -26,12 +26,17 @@
 extern "C" {
 #endif
 
-#define LCS_ABI_VERSION 1
+#define LCS_ABI_VERSION 2
 
 enum { LCS_OK = 0, LCS_E_INVALID = -1, LCS_E_CUDA = -2, LCS_E_WORKSPACE = -3, LCS_E_UNSUPPORTED = -4 };
 enum { LCS_F64 = 0, LCS_F32 = 1 };
 /* device layouts of a staged wind series, see lcs_pack_pairs / lcs_pack_es */
 enum { LCS_LAYOUT_PAIR4 = 0, LCS_LAYOUT_ES = 1 };
+/* arithmetic of the cubic taps in the integrator */
+enum { LCS_ARITH_F64 = 0,         /* weights, products and sums in f64 whatever the storage type (parity path)      */
+       LCS_ARITH_F32 = 1 };       /* fast path: f32 weights and packed f32 FMAs on f32 winds; index map, positions
+                                     and the SETTLS update stay f64.  FTLE agrees with the f64 path to ~1e-5 relative
+                                     away from ridge-singular points (tolerance-tested, not bit parity)               */
 /* x-boundary of the integrator: trajectory.py:92-97 / 118-123 */
 enum { LCS_X_CYCLIC = 0,          /* cyclic_xboundary=True: the two `where` with Python-sign % 180 */
        LCS_X_CLAMP_POINTWISE = 1, /* per-particle clamp to [lon_min, lon_max] */
@@ -67,6 +72,7 @@ typedef struct lcs_advect_opts {
                                true divisions); needs LCS_LAYOUT_PAIR4                            */
     int32_t nwindows;       /* independent start times integrated by this call (rolling series)  */
     int32_t level0, level_stride; /* window b starts at packed pair index level0 + b*level_stride  */
+    int32_t arith;          /* LCS_ARITH_*; LCS_ARITH_F32 needs dtype LCS_F32, LCS_LAYOUT_ES, order 3   */
 } lcs_advect_opts;
 
 /* Staged winds handed to the integrator.

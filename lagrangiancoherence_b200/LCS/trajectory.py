@@ -6,7 +6,7 @@ from __future__ import annotations
 import numpy as np
 import pandas as pd
 
-from ..engine import FtleEngine
+from ..engine import FtleEngine, precision_args
 from ..labelled import coord_values, make_like
 
 XCLAMP_DEFAULT = 'outer'     # what the reference executes for cyclic_xboundary=False (quirk Q6)
@@ -33,7 +33,7 @@ def propagate(U, V, timestep, propdim, return_traj, SETTLS_order, interp_order, 
     xmode = 'cyclic' if cyclic_xboundary else xclamp
     if engine is None:
         engine = FtleEngine(lat, lon, timestep, SETTLS_order=SETTLS_order, interp_order=interp_order,
-                            xmode=xmode, pair_dtype=precision, device=device)
+                            xmode=xmode, device=device, **precision_args(precision))
     uu, vv = np.asarray(U.values), np.asarray(V.values)
     if resample is not None:                                       # LCS.py:88-90, evaluated on the device
         _, lo, w_hi, w_lo = resample

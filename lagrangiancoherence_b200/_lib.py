@@ -13,7 +13,8 @@ LIB_PATH = os.environ.get('LCS_B200_LIB') or os.path.join(HERE, 'liblcs_b200.so'
 LCS_F64, LCS_F32 = 0, 1
 LCS_X_CYCLIC, LCS_X_CLAMP_POINTWISE, LCS_X_CLAMP_OUTER = 0, 1, 2
 LCS_LAYOUT_PAIR4, LCS_LAYOUT_ES = 0, 1
-ABI_VERSION = 1
+LCS_ARITH_F64, LCS_ARITH_F32 = 0, 1
+ABI_VERSION = 2
 
 c_void_p, c_int, c_double, c_size_t, c_int64 = C.c_void_p, C.c_int, C.c_double, C.c_size_t, C.c_int64
 
@@ -32,7 +33,7 @@ class Particles(C.Structure):
 class AdvectOpts(C.Structure):
     _fields_ = [('nsteps', C.c_int32), ('settls_order', C.c_int32), ('interp_order', C.c_int32),
                 ('xmode', C.c_int32), ('strict', C.c_int32),
-                ('nwindows', C.c_int32), ('level0', C.c_int32), ('level_stride', C.c_int32)]
+                ('nwindows', C.c_int32), ('level0', C.c_int32), ('level_stride', C.c_int32), ('arith', C.c_int32)]
 
 
 class Winds(C.Structure):

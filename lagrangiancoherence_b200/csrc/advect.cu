@@ -19,6 +19,7 @@
 // hit rate 91 %, L2 throughput 5 % in ncu: staging tiles through shared memory/TMA would move the
 // same bytes through the same 128 B/clk port and was not pursued).
 #include <cooperative_groups.h>
+#include <stdio.h>
 #include "lcs_internal.h"
 #include "lcs_device.cuh"
 
@@ -62,6 +63,9 @@ struct AdvectParams {
 };
 
 constexpr int kPair4 = LCS_LAYOUT_PAIR4, kES = LCS_LAYOUT_ES;
+constexpr int kES32 = 2;     // internal: ES layout of f32 elements with the cubic taps evaluated in f32 (LCS_ARITH_F32)
+template <typename T, int LAYOUT> struct EsPolicy { using type = Vec2<T>; };
+template <> struct EsPolicy<float, kES32> { using type = Vec2F32Arith; };
 
 // Thread -> particle: a block is a (band x 256/band) tile of the particle grid, a warp a
 // (band x 32/band) patch (smaller unique tap footprint than a 1x32 strip: better L1 hit rate);
@@ -92,8 +96,10 @@ __device__ __forceinline__ void sample(const AdvectParams& P, const void* raw, c
         gather_linear_constant<E, STRICT>(reinterpret_cast<const ET*>(raw) + (size_t)level * P.plane,
                                           P.nlat, P.nlon, iy, ix, out);
     } else if (ORDER == 3) {
-        gather_cubic_wrap<E, STRICT>(reinterpret_cast<const ET*>(coef) + (size_t)level * P.plane,
-                                     P.nlat, P.nlon, iy, ix, out);
+        if constexpr (E::A32) gather_cubic_wrap_f32(reinterpret_cast<const ET*>(coef) + (size_t)level * P.plane,
+                                                    P.nlat, P.nlon, iy, ix, out);
+        else gather_cubic_wrap<E, STRICT>(reinterpret_cast<const ET*>(coef) + (size_t)level * P.plane,
+                                          P.nlat, P.nlon, iy, ix, out);
     } else {
         gather_linear_wrap<E, STRICT>(reinterpret_cast<const ET*>(raw) + (size_t)level * P.plane,
                                       P.nlat, P.nlon, iy, ix, out);
@@ -106,7 +112,7 @@ __device__ __forceinline__ void stage_euler(const AdvectParams& P, int k, bool p
                                             double& x, double& y, double& ua, double& va) {
     double s[2];
     if (LAYOUT == kPair4) sample<Pair4Lo<T>, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, s);
-    else sample<Vec2<T>, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, s);
+    else sample<typename EsPolicy<T, LAYOUT>::type, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, s);
     ua = s[0]; va = s[1];
     y = __dadd_rn(y, __dmul_rn(P.ky, va));
     x = __dadd_rn(x, __dmul_rn(kx, ua));
@@ -127,7 +133,7 @@ __device__ __forceinline__ void stage_settls(const AdvectParams& P, int k, bool 
         x = __dadd_rn(x, __dmul_rn(hx, __dsub_rn(__dadd_rn(ua, __dmul_rn(2.0, s[0])), s[2])));
     } else {
         double s[2];
-        sample<Vec2<T>, STRICT, ORDER>(P, P.raw_b, P.coef_b, k, pole, x, y, s);
+        sample<typename EsPolicy<T, LAYOUT>::type, STRICT, ORDER>(P, P.raw_b, P.coef_b, k, pole, x, y, s);
         y = __dadd_rn(y, __dmul_rn(P.hy, __dadd_rn(va, s[1])));
         x = __dadd_rn(x, __dmul_rn(hx, __dadd_rn(ua, s[0])));
     }
@@ -320,6 +326,21 @@ __device__ __forceinline__ void prefetch_state(const void* p) {
 #endif
 }
 
+// state access policy of the persistent kernel (LCS_CLUSTER_STATE_LD: 0 = ld.cs/st.cs evict-first,
+// 1 = loads that do not allocate in L1, so the L1 keeps the wind taps)
+#ifndef LCS_CLUSTER_STATE_LD
+#define LCS_CLUSTER_STATE_LD 0
+#endif
+__device__ __forceinline__ double2 ld_state(const double2* p) {
+#if LCS_CLUSTER_STATE_LD == 1
+    double2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+#else
+    return __ldcs(p);
+#endif
+}
+
 template <typename T, bool STRICT, int ORDER, int LAYOUT, bool EULER>
 __device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, const int w, const int q, const int t,
                                                 const int tid_w, const int nthr_w,
@@ -339,7 +360,7 @@ __device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, const int
         double x, y;
         if (q == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
         else {
-            const double2 s = __ldcs(ps);
+            const double2 s = ld_state(ps);
             x = s.x; y = s.y;
             if (s_lt[row] && s_lt[P.nrow + col]) x = P.lon_min;      // trajectory.py:96
             if (s_gt[row] && s_gt[P.nrow + col]) x = P.lon_max;      // trajectory.py:97
@@ -354,7 +375,7 @@ __device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, const int
             stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
             __stcs(pw, make_double2(ua, va));
         } else {
-            const double2 wv = __ldcs(pw);
+            const double2 wv = ld_state(pw);
             stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.hx + row), wv.x, wv.y, x, y);
         }
         y = clamp_y(y, P.lat_min, P.lat_max);
@@ -466,6 +487,11 @@ static int choose_cluster_size(const AdvectParams& P, int nwindows, size_t smem,
         const double cost = (double)waves / cs;
         if (cost < best_cost - 1e-12) { best_cost = cost; best = cs; }
     }
+    if (lcs_env_int("LCS_DEBUG_CLUSTER", 0)) {
+        fprintf(stderr, "[lcs] co-resident clusters by size 1..8:");
+        for (int cs = 1; cs <= 8; ++cs) fprintf(stderr, " %d", resident[cs]);
+        fprintf(stderr, "; %d windows -> cluster size %d\n", nwindows, best);
+    }
     const int forced = lcs_env_int("LCS_OUTER_CLUSTER", 0);
     if (forced >= 1 && forced <= 8 && resident[forced] > 0) best = forced;
     if (resident[best] <= 0) { *busy_frac = 0.0; return 0; }
@@ -569,6 +595,9 @@ extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_a
         if (o->interp_order == 3 && (!w->coef_a || (w->layout == LCS_LAYOUT_ES && !w->coef_b)))
             return lcs_fail(LCS_E_INVALID, "lcs_advect: spline coefficients required for order 3");
     }
+    if (o->arith != LCS_ARITH_F64 && o->arith != LCS_ARITH_F32) return lcs_fail(LCS_E_INVALID, "lcs_advect: bad arith");
+    if (o->arith == LCS_ARITH_F32 && (w->dtype != LCS_F32 || w->layout != LCS_LAYOUT_ES || o->interp_order != 3 || o->strict))
+        return lcs_fail(LCS_E_INVALID, "lcs_advect: f32 arithmetic needs f32 winds in the ES layout, interp_order 3, strict 0");
     if (g->nlat < 4 || g->nlon < 4) return lcs_fail(LCS_E_INVALID, "lcs_advect: grid must be at least 4x4");
     if (p->nrow < 1 || p->ncol < 1 || o->nwindows < 1 || o->nsteps < 0 || o->settls_order < 0)
         return lcs_fail(LCS_E_INVALID, "lcs_advect: bad sizes");
@@ -641,7 +670,8 @@ extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_a
                        : launch_advect<TT, false, 1, kPair4>(P, o->nwindows, st);             \
         }                                                                                     \
     } while (0)
-    if (w->dtype == LCS_F64) LCS_DISPATCH(double);
+    if (o->arith == LCS_ARITH_F32) e = launch_advect<float, false, 3, kES32>(P, o->nwindows, st);   // validated above
+    else if (w->dtype == LCS_F64) LCS_DISPATCH(double);
     else if (w->dtype == LCS_F32) LCS_DISPATCH(float);
     else return lcs_fail(LCS_E_INVALID, "lcs_advect: bad wind dtype");
 #undef LCS_DISPATCH

@@ -31,13 +31,13 @@ template <> struct Vec2Of<float> { using type = float2; };
 // all four SETTLS operands of a tap with one load (256-bit LDG.E.256.CONSTANT for f64)
 template <typename T> struct Pair4;
 template <> struct Pair4<double> {
-    using type = d4; static constexpr int NV = 4;
+    using type = d4; static constexpr int NV = 4; static constexpr bool A32 = false;
     static __device__ __forceinline__ void ld(const type* p, double (&o)[4]) {
         asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
     }
 };
 template <> struct Pair4<float> {
-    using type = float4; static constexpr int NV = 4;
+    using type = float4; static constexpr int NV = 4; static constexpr bool A32 = false;
     static __device__ __forceinline__ void ld(const type* p, double (&o)[4]) {
         const float4 t = __ldg(p);
         o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
@@ -46,13 +46,13 @@ template <> struct Pair4<float> {
 // first half (u_k, v_k) of a 4-wide element: the Euler stage samples one level (trajectory.py:82-84)
 template <typename T> struct Pair4Lo;
 template <> struct Pair4Lo<double> {
-    using type = d4; static constexpr int NV = 2;
+    using type = d4; static constexpr int NV = 2; static constexpr bool A32 = false;
     static __device__ __forceinline__ void ld(const type* p, double (&o)[2]) {
         asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "l"(p));
     }
 };
 template <> struct Pair4Lo<float> {
-    using type = float4; static constexpr int NV = 2;
+    using type = float4; static constexpr int NV = 2; static constexpr bool A32 = false;
     static __device__ __forceinline__ void ld(const type* p, double (&o)[2]) {
         const float2 t = __ldg(reinterpret_cast<const float2*>(p));
         o[0] = t.x; o[1] = t.y;
@@ -61,13 +61,22 @@ template <> struct Pair4Lo<float> {
 // dense 2-wide element (the E / S arrays of the fast layout): 16 B (f64) or 8 B (f32) per tap
 template <typename T> struct Vec2;
 template <> struct Vec2<double> {
-    using type = d2; static constexpr int NV = 2;
+    using type = d2; static constexpr int NV = 2; static constexpr bool A32 = false;
     static __device__ __forceinline__ void ld(const type* p, double (&o)[2]) {
         asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "l"(p));
     }
 };
 template <> struct Vec2<float> {
-    using type = float2; static constexpr int NV = 2;
+    using type = float2; static constexpr int NV = 2; static constexpr bool A32 = false;
+    static __device__ __forceinline__ void ld(const type* p, double (&o)[2]) {
+        const float2 t = __ldg(p);
+        o[0] = t.x; o[1] = t.y;
+    }
+};
+// f32 elements whose cubic taps are also weighted and accumulated in f32 (LCS_ARITH_F32, the fast path):
+// same storage and loads as Vec2<float>; the cubic gather is gather_cubic_wrap_f32 below
+struct Vec2F32Arith {
+    using type = float2; static constexpr int NV = 2; static constexpr bool A32 = true;
     static __device__ __forceinline__ void ld(const type* p, double (&o)[2]) {
         const float2 t = __ldg(p);
         o[0] = t.x; o[1] = t.y;
@@ -75,7 +84,7 @@ template <> struct Vec2<float> {
 };
 // planar f64 field, one value per tap (the map_coordinates seam)
 struct Scalar64 {
-    using type = double; static constexpr int NV = 1;
+    using type = double; static constexpr int NV = 1; static constexpr bool A32 = false;
     static __device__ __forceinline__ void ld(const double* p, double (&o)[1]) { o[0] = __ldg(p); }
 };
 
@@ -186,6 +195,63 @@ __device__ __forceinline__ void gather_cubic_wrap(const typename E::type* __rest
             for (int v = 0; v < NV; ++v) out[v] = tap_acc<STRICT>(out[v], c[j][v], wy[i], wx[j], wyx);
         }
     }
+}
+
+// Fast-path cubic gather (LCS_ARITH_F32): index map, fold and the fractional offsets stay in f64 (an f32 index
+// of magnitude ~10^3 would carry 1e-4 cells of error into the weights); the four weights per axis, the 16
+// products and the accumulation are f32, two values (u, v) per packed FFMA2.  Row sums first, then the
+// latitude weights: 20 FFMA2 per sample and no per-tap weight products.  Results differ from the f64
+// evaluation of the same f32 coefficients by a few f32 ulp of the wind magnitude (tolerance-tested).
+__device__ __forceinline__ void cubic_weights_f32(float y, float2 (&w)[4]) {
+    const float z = 1.0f - y;
+    const float s = 1.0f / 6.0f;
+    const float w1 = (y * y * (y - 2.0f) * 3.0f + 4.0f) * s;
+    const float w2 = (z * z * (z - 2.0f) * 3.0f + 4.0f) * s;
+    const float w0 = z * z * z * s;
+    const float w3 = 1.0f - w0 - w1 - w2;
+    w[0] = make_float2(w0, w0); w[1] = make_float2(w1, w1); w[2] = make_float2(w2, w2); w[3] = make_float2(w3, w3);
+}
+
+__device__ __forceinline__ void gather_cubic_wrap_f32(const float2* __restrict__ f, int nlat, int nlon,
+                                                      double iy, double ix, double (&out)[2]) {
+    const double cy = fold_wrap(iy, nlat);
+    const double cx = fold_wrap(ix, nlon);
+    const double fy = floor(cy), fx = floor(cx);
+    float2 wy[4], wx[4];
+    cubic_weights_f32((float)(cy - fy), wy);
+    cubic_weights_f32((float)(cx - fx), wx);
+    const int sy = (int)fy - 1, sx = (int)fx - 1;
+    float2 acc = make_float2(0.0f, 0.0f);
+    if (sy >= 0 && sy + 3 < nlat && sx >= 0 && sx + 3 < nlon) {
+        const float2* base = f + (size_t)sy * nlon + sx;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float2 c[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = __ldg(base + j);
+            float2 r = __fmul2_rn(c[0], wx[0]);
+#pragma unroll
+            for (int j = 1; j < 4; ++j) r = __ffma2_rn(c[j], wx[j], r);
+            acc = __ffma2_rn(r, wy[i], acc);
+            base += nlon;
+        }
+    } else {
+        int col[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) col[j] = mirror_near(sx + j, nlon);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2* rowp = f + (size_t)mirror_near(sy + i, nlat) * nlon;
+            float2 c[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) c[j] = __ldg(rowp + col[j]);
+            float2 r = __fmul2_rn(c[0], wx[0]);
+#pragma unroll
+            for (int j = 1; j < 4; ++j) r = __ffma2_rn(c[j], wx[j], r);
+            acc = __ffma2_rn(r, wy[i], acc);
+        }
+    }
+    out[0] = (double)acc.x; out[1] = (double)acc.y;
 }
 
 // Shared 2x2 tap sum of the order-1 branches (weights (1-y, 1-(1-y)), mirror taps).

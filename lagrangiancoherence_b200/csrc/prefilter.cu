@@ -73,6 +73,77 @@ fir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__
         if (r0 + j < n0) o[j] = acc[j];
 }
 
+// Same filter, same interface, ~10x fewer FMAs: inside a thread's run of KQ consecutive outputs the two one-sided
+// sums obey the one-pole recursions that scipy runs along the whole line,
+//      a[i] = s[i] + z a[i-1]   (causal),      m[i] = s[i] + z m[i+1]   (anticausal),      c[i] = sqrt(3) (a[i] + z m[i+1]),
+// and only their values at the ends of the run need the truncated (|k| <= KH, remainder < 1e-18) mirror sums.  Per run:
+// 2*(KH+1) Horner steps for the two ends + 2*KQ recursion steps, instead of KQ*65 FMAs -- the filter becomes a
+// streaming kernel (ncu: the FIR form ran the FP64 pipe at ~45 %).  Agreement with scipy stays ~1e-15 of the field.
+constexpr int KQ = 32;    // outputs per thread in the recursive form
+
+struct MirrorWalk {        // index into the mirror extension d c b | a b c d | c b a, stepped by +-1
+    int i, dir, n;
+    __device__ __forceinline__ MirrorWalk(int start, int n_, int step) : n(n_) {
+        const int period = 2 * n - 2;
+        int ii = start % period;
+        if (ii < 0) ii += period;
+        dir = step;
+        if (ii >= n) { ii = period - ii; dir = -step; }
+        i = ii;
+        fix();
+    }
+    __device__ __forceinline__ void fix() { if (i == n - 1 && dir > 0) dir = -1; else if (i == 0 && dir < 0) dir = 1; }
+    __device__ __forceinline__ void next() { i += dir; fix(); }
+};
+
+template <typename Tin>
+__global__ void __launch_bounds__(128)
+iir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b, int interleaved_planes,
+                           double* __restrict__ out_a, double* __restrict__ out_b, int split_out,
+                           int n0, int n1, double z, double h0) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n1) return;
+    const int r0 = blockIdx.y * KQ;
+    const int p = blockIdx.z;
+    const size_t plane = (size_t)n0 * n1;
+    const Tin* src = interleaved_planes ? ((p & 1) ? in_b : in_a) + (size_t)(p >> 1) * plane + c
+                                        : in_a + (size_t)p * plane + c;
+    double* dst = split_out ? ((p & 1) ? out_b : out_a) + (size_t)(p >> 1) * plane
+                            : out_a + (size_t)p * plane;
+    auto ld = [&](int i) { return (double)__ldg(src + (size_t)i * n1); };
+    // causal sum just before the run: a[r0-1] = sum_{k>=0} z^k s[r0-1-k], Horner from the far end
+    double a;
+    {
+        MirrorWalk w(r0 - 1 - KH, n0, +1);
+        a = ld(w.i);
+        for (int k = 0; k < KH; ++k) { w.next(); a = fma(z, a, ld(w.i)); }
+    }
+    double av[KQ];
+    {
+        MirrorWalk w(r0, n0, +1);
+#pragma unroll
+        for (int j = 0; j < KQ; ++j) { a = fma(z, a, ld(w.i)); av[j] = a; w.next(); }
+    }
+    // anticausal sum just after the run: m[r0+KQ] = sum_{k>=0} z^k s[r0+KQ+k]
+    double m;
+    {
+        MirrorWalk w(r0 + KQ + KH, n0, -1);
+        m = ld(w.i);
+        for (int k = 0; k < KH; ++k) { w.next(); m = fma(z, m, ld(w.i)); }
+    }
+    double* o = dst + (size_t)c * n0 + r0;
+    {
+        MirrorWalk w(r0 + KQ - 1, n0, -1);
+#pragma unroll
+        for (int j = KQ - 1; j >= 0; --j) {
+            const double out = h0 * fma(z, m, av[j]);
+            m = fma(z, m, ld(w.i));
+            w.next();
+            if (r0 + j < n0) o[j] = out;
+        }
+    }
+}
+
 template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(256)
 pack_pairs_kernel(const Tin* __restrict__ u, const Tin* __restrict__ v,
@@ -133,8 +204,28 @@ extern "C" int lcs_prefilter(const void* u, const void* v, int in_dtype, double*
         return lcs_fail(LCS_E_WORKSPACE, "lcs_prefilter: scratch too small");
     if (2 * nlev > 65535) return lcs_fail(LCS_E_INVALID, "lcs_prefilter: at most 32767 levels per call");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const FirTaps taps = make_taps();
     double* tmp = static_cast<double*>(scratch);
+    if (lcs_env_int("LCS_PREFILTER_FIR", 0) == 0) {
+        const double z = sqrt(3.0) - 2.0;
+        const double h0 = (1.0 - z) * (1.0 - 1.0 / z) * (-z) / (1.0 - z * z);   // = sqrt(3)
+        const dim3 q1((nlon + 127) / 128, (nlat + KQ - 1) / KQ, 2 * nlev);
+        if (in_dtype == LCS_F64)
+            iir_axis0_transpose_kernel<double><<<q1, 128, 0, st>>>((const double*)u, (const double*)v, 1, tmp, nullptr, 0,
+                                                                   nlat, nlon, z, h0);
+        else if (in_dtype == LCS_F32)
+            iir_axis0_transpose_kernel<float><<<q1, 128, 0, st>>>((const float*)u, (const float*)v, 1, tmp, nullptr, 0,
+                                                                  nlat, nlon, z, h0);
+        else return lcs_fail(LCS_E_INVALID, "lcs_prefilter: bad in_dtype");
+        cudaError_t e1 = cudaGetLastError();
+        if (e1 != cudaSuccess) return lcs_fail_cuda(e1, "lcs_prefilter(lat pass)");
+        const dim3 q2((nlat + 127) / 128, (nlon + KQ - 1) / KQ, 2 * nlev);
+        iir_axis0_transpose_kernel<double><<<q2, 128, 0, st>>>(tmp, nullptr, 0, coef_u, coef_v, 1, nlon, nlat, z, h0);
+        e1 = cudaGetLastError();
+        if (e1 != cudaSuccess) return lcs_fail_cuda(e1, "lcs_prefilter(lon pass)");
+        lcs_count_launches(2);
+        return LCS_OK;
+    }
+    const FirTaps taps = make_taps();
     // pass 1: along latitude; [plane][lat][lon] -> scratch [plane][lon][lat]
     const dim3 g1((nlon + 127) / 128, (nlat + KR - 1) / KR, 2 * nlev);
     if (in_dtype == LCS_F64)

@@ -23,6 +23,16 @@ XMODES = {'cyclic': _lib.LCS_X_CYCLIC, 'pointwise': _lib.LCS_X_CLAMP_POINTWISE, 
 DTYPES = {'f64': _lib.LCS_F64, 'f32': _lib.LCS_F32}
 
 
+def precision_args(precision):
+    """``precision=`` of the public API -> FtleEngine keywords: 'f64' (parity path), 'f32' (f32 packed winds, f64
+    tap arithmetic), 'f32fast' (f32 winds and f32 tap arithmetic, cubic interpolation only)."""
+    try:
+        return {'f64': dict(pair_dtype='f64', arith='f64'), 'f32': dict(pair_dtype='f32', arith='f64'),
+                'f32fast': dict(pair_dtype='f32', arith='f32')}[precision]
+    except KeyError:
+        raise ValueError("precision must be 'f64', 'f32' or 'f32fast'") from None
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -71,7 +81,8 @@ class FtleEngine:
     """
 
     def __init__(self, lat, lon, timestep, SETTLS_order=0, interp_order=3, xmode='outer',
-                 pair_dtype='f64', strict=False, device='cuda:0', part_lat=None, part_lon=None, layout='es'):
+                 pair_dtype='f64', strict=False, device='cuda:0', part_lat=None, part_lon=None, layout='es',
+                 arith='f64'):
         if not torch.cuda.is_available():
             raise _lib.LcsError('lagrangiancoherence_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
         self.lib = _lib.load()
@@ -91,6 +102,11 @@ class FtleEngine:
         self.pair_dtype = DTYPES[pair_dtype]
         self.strict = int(bool(strict))
         self.layout = _lib.LCS_LAYOUT_PAIR4 if self.strict or layout == 'pair4' else _lib.LCS_LAYOUT_ES
+        if arith not in ('f64', 'f32'):
+            raise ValueError("arith must be 'f64' or 'f32'")
+        if arith == 'f32' and (self.pair_dtype != _lib.LCS_F32 or self.layout != _lib.LCS_LAYOUT_ES or self.order != 3):
+            raise ValueError("arith='f32' needs pair_dtype='f32', the ES layout and interp_order=3")
+        self.arith = _lib.LCS_ARITH_F32 if arith == 'f32' else _lib.LCS_ARITH_F64
         self.grid = _lib.Grid(self.nlat, self.nlon, self.lat.min(), self.lat.max(), self.lon.min(), self.lon.max())
         self.part_lat = self.lat if part_lat is None else np.ascontiguousarray(part_lat, dtype=np.float64)
         self.part_lon = self.lon if part_lon is None else np.ascontiguousarray(part_lon, dtype=np.float64)
@@ -196,7 +212,7 @@ class FtleEngine:
                                   self.d_plat[r0:].data_ptr(), self.d_plon.data_ptr(),
                                   self.d_kx[r0:].data_ptr(), self.d_hx[r0:].data_ptr(), self.ky, self.hy)
             opts = _lib.AdvectOpts(nsteps, self.S, self.order, self.xmode, self.strict,
-                                   nwindows, level0, level_stride)
+                                   nwindows, level0, level_stride, self.arith)
             need = self.lib.lcs_advect_workspace_bytes(C.byref(part), C.byref(opts))
             ws = None
             if need:

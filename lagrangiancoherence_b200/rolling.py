@@ -18,7 +18,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from .engine import FtleEngine
+from .engine import FtleEngine, precision_args
 
 
 # ------------------------------------------------------------------ pure planning helpers (CPU-testable)
@@ -83,7 +83,7 @@ def rolling_ftle(u, v, lat, lon, window_levels, timestep, SETTLS_order=4, interp
         raise ValueError('start-time range runs past the wind series')
     if engine is None:
         engine = FtleEngine(lat, lon, timestep, SETTLS_order=SETTLS_order, interp_order=interp_order,
-                            xmode='cyclic' if cyclic_xboundary else xclamp, pair_dtype=precision, device=device)
+                            xmode='cyclic' if cyclic_xboundary else xclamp, device=device, **precision_args(precision))
     dev = engine.device
     on_device = isinstance(u, torch.Tensor) and u.is_cuda
     if not on_device:

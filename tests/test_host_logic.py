@@ -35,7 +35,7 @@ def test_ctypes_structs_match_the_header_layout(lib_path):
     from lagrangiancoherence_b200 import _lib
     assert ctypes.sizeof(_lib.Grid) == 8 + 4 * 8
     assert ctypes.sizeof(_lib.Particles) == 16 + 4 * 8 + 2 * 8
-    assert ctypes.sizeof(_lib.AdvectOpts) == 8 * 4
+    assert ctypes.sizeof(_lib.AdvectOpts) == 9 * 4
     assert ctypes.sizeof(_lib.Winds) == 8 + 4 * 8
 
 
@@ -49,7 +49,7 @@ def test_argument_validation_without_a_gpu(lib_path):
     assert lib.lcs_ftle_epilogue(None, None, 1, 8, 8, 0, 8, 0, 8, None, 1.0, None, 0, None, None, None, None) == -1
     assert lib.lcs_prefilter_scratch_bytes(3, 10, 20) == 2 * 3 * 10 * 20 * 8
     part = _lib.Particles(10, 20, 0, 10, None, None, None, None, 1.0, 0.5)
-    opts = _lib.AdvectOpts(8, 4, 3, _lib.LCS_X_CLAMP_POINTWISE, 0, 1, 0, 1)
+    opts = _lib.AdvectOpts(8, 4, 3, _lib.LCS_X_CLAMP_POINTWISE, 0, 1, 0, 1, 0)
     assert lib.lcs_advect_workspace_bytes(ctypes.byref(part), ctypes.byref(opts)) == 0
     opts.xmode = _lib.LCS_X_CLAMP_OUTER
     assert lib.lcs_advect_workspace_bytes(ctypes.byref(part), ctypes.byref(opts)) > 10 * 20 * 32
