@@ -4,7 +4,7 @@ configuration (BASELINE.json configs[1], "C2": 281x321, 6-hourly u,v, 48 h backw
 SETTLS_order=4, cubic interpolation, f64).
 
 A *step* is one batch of B independent start times (a rolling series of B+8 six-hourly levels;
-every window is exactly configs[1]) pushed through the whole hot path:
+every window is exactly configs[1]; B defaults to 1184 = 8 windows per SM) pushed through the whole hot path:
 prefilter + pack (new levels only once) -> departure-point integration -> fused FTLE epilogue.
 
   python bench.py --gpus N --steps K --warmup W            # this repository (CUDA, sm_100a)
@@ -41,7 +41,9 @@ def parse():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=296, help='start times per step and per GPU (296 = two windows per SM)')
+    ap.add_argument('--batch', type=int, default=1184,
+                    help='start times per step and per GPU: 1184 = 8 windows per SM = one GPU\'s share (1095) of a year of '
+                         'hourly start times sharded 8-way (BASELINE configs[3]) rounded up to whole waves of 296')
     ap.add_argument('--xclamp', default='outer', choices=['outer', 'pointwise'],
                     help="x-boundary: 'outer' = what the reference executes (quirk Q6)")
     ap.add_argument('--order', type=int, default=3, choices=[1, 3])
@@ -378,7 +380,9 @@ def run_b200(args):
         'gpu_launches_per_step': launches_timed / args.steps,
         'clocks': clocks,
         'roofline': {
-            'bound': 'gather (L1/L2 -> SM); not hbm, not tensor: nothing on this path is a dense contraction',
+            'bound': 'l1-gather',
+            'bound_note': 'L1/L2 -> SM gather throughput (SURVEY 8(d)); not hbm (see roofline.hbm: <2 % of the measured copy '
+                          'bandwidth), not tensor: nothing on this path is a dense contraction',
             'kernel': kernel_name,
             'achieved': achieved, 'peak': gather_peak_es, 'unit': 'GB/s', 'frac': achieved / gather_peak_es,
             'bytes_per_particle_step': issued_bytes_pstep,

@@ -66,7 +66,7 @@ typedef struct lcs_particles {
 typedef struct lcs_advect_opts {
     int32_t nsteps;         /* wind intervals to cross = nt-1 (trajectory.py:80)                 */
     int32_t settls_order;   /* accumulating sub-iterations per interval (trajectory.py:100)      */
-    int32_t interp_order;   /* 1 or 3 (tools.py:11 `order`)                                       */
+    int32_t interp_order;   /* 1..5 (tools.py:11 `order`); 2, 4, 5: f64 ES layout only            */
     int32_t xmode;          /* LCS_X_*                                                            */
     int32_t strict;         /* 1: accumulate taps as scipy does ((c*wy)*wx, no fused multiply-add,
                                true divisions); needs LCS_LAYOUT_PAIR4                            */
@@ -97,14 +97,14 @@ const char* lcs_last_error(void);
 unsigned long long lcs_kernel_launches(void);
 
 /* ---------------------------------------------------------------- wind staging
- * lcs_prefilter: cubic B-spline coefficients of every level, mirror boundary, latitude axis then
- * longitude axis, f64 -- what scipy.ndimage.map_coordinates(order=3, mode='wrap') recomputes inside
- * every call at tools.py:26-30; here it runs once per level.  u, v: device [nlev][nlat][nlon] of
+ * lcs_prefilter: B-spline coefficients (order 2..5; 3 = the reference default) of every level, mirror
+ * boundary, latitude axis then longitude axis, f64 -- what scipy.ndimage.map_coordinates(order, mode='wrap')
+ * recomputes inside every call at tools.py:26-30; here it runs once per level.  u, v: device [nlev][nlat][nlon] of
  * `in_dtype`; coef_u, coef_v: device f64 planes of the same shape (may not alias the inputs);
  * scratch: device buffer of lcs_prefilter_scratch_bytes() bytes. */
 size_t lcs_prefilter_scratch_bytes(int nlev, int nlat, int nlon);
 int lcs_prefilter(const void* u, const void* v, int in_dtype, double* coef_u, double* coef_v,
-                  void* scratch, size_t scratch_bytes, int nlev, int nlat, int nlon, void* stream);
+                  void* scratch, size_t scratch_bytes, int nlev, int nlat, int nlon, int order, void* stream);
 
 /* lcs_pack_pairs: interleave two planar series into the gather layout
  * pairs[k][lat][lon] = (u_k, v_k, u_{k+1}, v_{k+1}), k = 0..nlev-2, one 32-byte (f64) or 16-byte
@@ -174,8 +174,8 @@ int lcs_gaussian_filter2d(const double* in, double* out, double* scratch, int nf
 
 /* xr_map_coordinates body (tools.py:19-41) for one field: positions in degrees,
  * [nrow][ncol]; rows < order or >= nrow_global-order (global row index) take the
- * order-1/'constant' branch.  field: device f64 [nlat][nlon] raw values; coef: its cubic
- * coefficients (order 3) or NULL; out: device f64 [nrow][ncol]. */
+ * order-1/'constant' branch.  field: device f64 [nlat][nlon] raw values; coef: its B-spline
+ * coefficients of that order (order >= 2) or NULL; out: device f64 [nrow][ncol]. */
 int lcs_map_coordinates(const lcs_grid* g, const double* field, const double* coef, int order,
                         const double* pos_x, const double* pos_y, int nrow, int ncol,
                         int row0, int nrow_global, double* out, void* stream);

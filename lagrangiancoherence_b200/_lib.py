@@ -48,7 +48,7 @@ SIGNATURES = {
     'lcs_kernel_launches': (C.c_ulonglong, []),
     'lcs_prefilter_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
     'lcs_prefilter': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
-                              c_int, c_int, c_int, c_void_p]),
+                              c_int, c_int, c_int, c_int, c_void_p]),
     'lcs_pack_pairs': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'lcs_time_lerp': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     'lcs_gaussian_filter2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),

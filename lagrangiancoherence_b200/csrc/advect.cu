@@ -100,9 +100,13 @@ __device__ __forceinline__ void sample(const AdvectParams& P, const void* raw, c
                                                     P.nlat, P.nlon, iy, ix, out);
         else gather_cubic_wrap<E, STRICT>(reinterpret_cast<const ET*>(coef) + (size_t)level * P.plane,
                                           P.nlat, P.nlon, iy, ix, out);
-    } else {
+    } else if (ORDER == 1) {
         gather_linear_wrap<E, STRICT>(reinterpret_cast<const ET*>(raw) + (size_t)level * P.plane,
                                       P.nlat, P.nlon, iy, ix, out);
+    } else {
+        if constexpr (ORDER == 2 || ORDER == 4 || ORDER == 5)
+            gather_spline_wrap<E, STRICT, ORDER>(reinterpret_cast<const ET*>(coef) + (size_t)level * P.plane,
+                                                 P.nlat, P.nlon, iy, ix, out);
     }
 }
 
@@ -585,15 +589,18 @@ extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_a
                           double* x_out, double* y_out, double* x_traj, double* y_traj,
                           void* workspace, size_t workspace_bytes, void* stream) {
     if (!g || !p || !o || !w || !x_out || !y_out) return lcs_fail(LCS_E_INVALID, "lcs_advect: null argument");
-    if (o->interp_order != 1 && o->interp_order != 3)
-        return lcs_fail(LCS_E_UNSUPPORTED, "lcs_advect: interp_order must be 1 or 3");
+    if (o->interp_order < 1 || o->interp_order > 5)
+        return lcs_fail(LCS_E_UNSUPPORTED, "lcs_advect: interp_order must be 1..5 (0 is broken upstream: empty row slices)");
+    const bool other_order = o->interp_order == 2 || o->interp_order == 4 || o->interp_order == 5;
+    if (other_order && (w->dtype != LCS_F64 || w->layout != LCS_LAYOUT_ES || o->strict))
+        return lcs_fail(LCS_E_UNSUPPORTED, "lcs_advect: interp_order 2, 4, 5 need f64 winds in the ES layout, strict 0");
     if (w->layout != LCS_LAYOUT_PAIR4 && w->layout != LCS_LAYOUT_ES) return lcs_fail(LCS_E_INVALID, "lcs_advect: bad wind layout");
     if (o->strict && w->layout != LCS_LAYOUT_PAIR4)
         return lcs_fail(LCS_E_INVALID, "lcs_advect: strict evaluation needs the PAIR4 layout");
     if (o->nsteps > 0) {
         if (!w->raw_a || (w->layout == LCS_LAYOUT_ES && !w->raw_b)) return lcs_fail(LCS_E_INVALID, "lcs_advect: raw winds missing");
-        if (o->interp_order == 3 && (!w->coef_a || (w->layout == LCS_LAYOUT_ES && !w->coef_b)))
-            return lcs_fail(LCS_E_INVALID, "lcs_advect: spline coefficients required for order 3");
+        if (o->interp_order >= 2 && (!w->coef_a || (w->layout == LCS_LAYOUT_ES && !w->coef_b)))
+            return lcs_fail(LCS_E_INVALID, "lcs_advect: spline coefficients required for orders >= 2");
     }
     if (o->arith != LCS_ARITH_F64 && o->arith != LCS_ARITH_F32) return lcs_fail(LCS_E_INVALID, "lcs_advect: bad arith");
     if (o->arith == LCS_ARITH_F32 && (w->dtype != LCS_F32 || w->layout != LCS_LAYOUT_ES || o->interp_order != 3 || o->strict))
@@ -671,6 +678,9 @@ extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_a
         }                                                                                     \
     } while (0)
     if (o->arith == LCS_ARITH_F32) e = launch_advect<float, false, 3, kES32>(P, o->nwindows, st);   // validated above
+    else if (ord == 2) e = launch_advect<double, false, 2, kES>(P, o->nwindows, st);
+    else if (ord == 4) e = launch_advect<double, false, 4, kES>(P, o->nwindows, st);
+    else if (ord == 5) e = launch_advect<double, false, 5, kES>(P, o->nwindows, st);
     else if (w->dtype == LCS_F64) LCS_DISPATCH(double);
     else if (w->dtype == LCS_F32) LCS_DISPATCH(float);
     else return lcs_fail(LCS_E_INVALID, "lcs_advect: bad wind dtype");

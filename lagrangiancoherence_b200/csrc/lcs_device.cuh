@@ -111,8 +111,9 @@ __device__ __forceinline__ double fold_wrap(double c, int n) {
 
 // scipy's spline_mode mirror for out-of-range tap indices is d c b | a b c d | c b a.
 // The indices a gather can actually produce: coordinates are folded into [0, n-1] first (or rejected by
-// the 'constant' branch), so taps lie in [-1, n+1]; for n >= 3 the reflection needs no division:
-// -1 -> 1, n -> n-2, n+1 -> n-3 (scipy's general formula, oracle.mirror_index, reduces to this).
+// the 'constant' branch), so taps lie in [-1, n+1] (orders 1, 3) or [-2, n+2] (orders 2, 4, 5); for n >= 4 a
+// single reflection needs no division: -1 -> 1, n -> n-2, n+2 -> n-4 (scipy's general formula,
+// oracle.mirror_index, reduces to this).
 __device__ __forceinline__ int mirror_near(int i, int n) {
     return i < 0 ? -i : (i > n - 1 ? 2 * (n - 1) - i : i);
 }
@@ -190,6 +191,102 @@ __device__ __forceinline__ void gather_cubic_wrap(const typename E::type* __rest
         for (int j = 0; j < 4; ++j) E::ld(rowp + col[j], c[j]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+            const double wyx = wy[i] * wx[j];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) out[v] = tap_acc<STRICT>(out[v], c[j][v], wy[i], wx[j], wyx);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ spline orders 2, 4, 5
+// `traj_interp_order` is free upstream (whatever scipy accepts); 3 is the default and 1 the other value any
+// caller uses, so those two have hand-tuned gathers above.  Orders 2, 4 and 5 share this generic form:
+// scipy's weights (ni_splines.c:get_spline_interpolation_weights) in scipy's order of operations, first tap
+// floor(c) - order/2 (odd) or floor(c + 0.5) - order/2 (even), (order+1)^2 mirrored taps.
+template <bool ST> __device__ __forceinline__ double op_mul(double a, double b) { return ST ? __dmul_rn(a, b) : a * b; }
+template <bool ST> __device__ __forceinline__ double op_add(double a, double b) { return ST ? __dadd_rn(a, b) : a + b; }
+template <bool ST> __device__ __forceinline__ double op_sub(double a, double b) { return ST ? __dsub_rn(a, b) : a - b; }
+template <bool ST> __device__ __forceinline__ double op_div(double a, double b) { return ST ? __ddiv_rn(a, b) : a * (1.0 / b); }
+
+template <int ORDER, bool ST>
+__device__ __forceinline__ int spline_weights(double c, double (&w)[ORDER + 1]) {
+    static_assert(ORDER == 2 || ORDER == 4 || ORDER == 5, "orders 1 and 3 have their own gathers");
+    const double f = (ORDER & 1) ? floor(c) : floor(__dadd_rn(c, 0.5));
+    const double x = __dsub_rn(c, f);
+    double y = x, z = __dsub_rn(1.0, x), t;
+    if (ORDER == 2) {
+        w[1] = op_sub<ST>(0.75, op_mul<ST>(x, x));
+        y = op_sub<ST>(0.5, x);
+        w[0] = op_mul<ST>(op_mul<ST>(0.5, y), y);
+    } else if (ORDER == 4) {
+        t = op_mul<ST>(x, x);
+        w[2] = op_add<ST>(op_mul<ST>(t, op_sub<ST>(op_mul<ST>(t, 0.25), 0.625)), 115.0 / 192.0);
+        y = op_add<ST>(1.0, x);
+        w[1] = op_add<ST>(op_mul<ST>(y, op_add<ST>(op_mul<ST>(y, op_sub<ST>(op_div<ST>(op_mul<ST>(y, op_sub<ST>(5.0, y)), 6.0), 1.25)), 5.0 / 24.0)), 55.0 / 96.0);
+        w[3] = op_add<ST>(op_mul<ST>(z, op_add<ST>(op_mul<ST>(z, op_sub<ST>(op_div<ST>(op_mul<ST>(z, op_sub<ST>(5.0, z)), 6.0), 1.25)), 5.0 / 24.0)), 55.0 / 96.0);
+        y = op_sub<ST>(0.5, x);
+        t = op_mul<ST>(y, y);
+        w[0] = op_div<ST>(op_mul<ST>(t, t), 24.0);
+    } else {
+        t = op_mul<ST>(y, y);
+        w[2] = op_add<ST>(op_mul<ST>(t, op_sub<ST>(op_mul<ST>(t, op_sub<ST>(0.25, op_div<ST>(y, 12.0))), 0.5)), 0.55);
+        t = op_mul<ST>(z, z);
+        w[3] = op_add<ST>(op_mul<ST>(t, op_sub<ST>(op_mul<ST>(t, op_sub<ST>(0.25, op_div<ST>(z, 12.0))), 0.5)), 0.55);
+        y = op_add<ST>(y, 1.0);
+        w[1] = op_add<ST>(op_mul<ST>(y, op_add<ST>(op_mul<ST>(y, op_sub<ST>(op_mul<ST>(y, op_add<ST>(op_mul<ST>(y, op_sub<ST>(op_div<ST>(y, 24.0), 0.375)), 1.25)), 1.75)), 0.625)), 0.425);
+        z = op_add<ST>(z, 1.0);
+        w[4] = op_add<ST>(op_mul<ST>(z, op_add<ST>(op_mul<ST>(z, op_sub<ST>(op_mul<ST>(z, op_add<ST>(op_mul<ST>(z, op_sub<ST>(op_div<ST>(z, 24.0), 0.375)), 1.25)), 1.75)), 0.625)), 0.425);
+        y = op_sub<ST>(1.0, x);
+        t = op_mul<ST>(y, y);
+        w[0] = op_div<ST>(op_mul<ST>(op_mul<ST>(y, t), t), 120.0);
+    }
+    double last = 1.0;
+#pragma unroll
+    for (int i = 0; i < ORDER; ++i) last = __dsub_rn(last, w[i]);
+    w[ORDER] = last;
+    return (int)f - ORDER / 2;
+}
+
+template <typename E, bool STRICT, int ORDER>
+__device__ __forceinline__ void gather_spline_wrap(const typename E::type* __restrict__ f,
+                                                   int nlat, int nlon, double iy, double ix,
+                                                   double (&out)[E::NV]) {
+    constexpr int NV = E::NV, NT = ORDER + 1;
+    const double cy = fold_wrap(iy, nlat);
+    const double cx = fold_wrap(ix, nlon);
+    double wy[NT], wx[NT];
+    const int sy = spline_weights<ORDER, STRICT>(cy, wy);
+    const int sx = spline_weights<ORDER, STRICT>(cx, wx);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) out[v] = 0.0;
+    if (sy >= 0 && sy + ORDER < nlat && sx >= 0 && sx + ORDER < nlon) {
+        const typename E::type* base = f + (size_t)sy * nlon + sx;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+            double c[NT][NV];
+#pragma unroll
+            for (int j = 0; j < NT; ++j) E::ld(base + j, c[j]);
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const double wyx = wy[i] * wx[j];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) out[v] = tap_acc<STRICT>(out[v], c[j][v], wy[i], wx[j], wyx);
+            }
+            base += nlon;
+        }
+        return;
+    }
+    int col[NT];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) col[j] = mirror_near(sx + j, nlon);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        const typename E::type* rowp = f + (size_t)mirror_near(sy + i, nlat) * nlon;
+        double c[NT][NV];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) E::ld(rowp + col[j], c[j]);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
             const double wyx = wy[i] * wx[j];
 #pragma unroll
             for (int v = 0; v < NV; ++v) out[v] = tap_acc<STRICT>(out[v], c[j][v], wy[i], wx[j], wyx);

@@ -100,7 +100,7 @@ template <typename Tin>
 __global__ void __launch_bounds__(128)
 iir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b, int interleaved_planes,
                            double* __restrict__ out_a, double* __restrict__ out_b, int split_out,
-                           int n0, int n1, double z, double h0) {
+                           int n0, int n1, double z, double h0, int kh) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n1) return;
     const int r0 = blockIdx.y * KQ;
@@ -114,9 +114,9 @@ iir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__
     // causal sum just before the run: a[r0-1] = sum_{k>=0} z^k s[r0-1-k], Horner from the far end
     double a;
     {
-        MirrorWalk w(r0 - 1 - KH, n0, +1);
+        MirrorWalk w(r0 - 1 - kh, n0, +1);
         a = ld(w.i);
-        for (int k = 0; k < KH; ++k) { w.next(); a = fma(z, a, ld(w.i)); }
+        for (int k = 0; k < kh; ++k) { w.next(); a = fma(z, a, ld(w.i)); }
     }
     double av[KQ];
     {
@@ -127,9 +127,9 @@ iir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__
     // anticausal sum just after the run: m[r0+KQ] = sum_{k>=0} z^k s[r0+KQ+k]
     double m;
     {
-        MirrorWalk w(r0 + KQ + KH, n0, -1);
+        MirrorWalk w(r0 + KQ + kh, n0, -1);
         m = ld(w.i);
-        for (int k = 0; k < KH; ++k) { w.next(); m = fma(z, m, ld(w.i)); }
+        for (int k = 0; k < kh; ++k) { w.next(); m = fma(z, m, ld(w.i)); }
     }
     double* o = dst + (size_t)c * n0 + r0;
     {
@@ -195,54 +195,69 @@ extern "C" size_t lcs_prefilter_scratch_bytes(int nlev, int nlat, int nlon) {
     return (size_t)2 * nlev * nlat * nlon * sizeof(double);
 }
 
+// Poles of the B-spline prefilter (scipy ni_splines.c:get_filter_poles)
+static int spline_poles(int order, double* z) {
+    switch (order) {
+        case 2: z[0] = sqrt(8.0) - 3.0; return 1;
+        case 3: z[0] = sqrt(3.0) - 2.0; return 1;
+        case 4: z[0] = sqrt(664.0 - sqrt(438976.0)) + sqrt(304.0) - 19.0;
+                z[1] = sqrt(664.0 + sqrt(438976.0)) - sqrt(304.0) - 19.0; return 2;
+        case 5: z[0] = sqrt(67.5 - sqrt(4436.25)) + sqrt(26.25) - 6.5;
+                z[1] = sqrt(67.5 + sqrt(4436.25)) - sqrt(26.25) - 6.5; return 2;
+        default: return 0;
+    }
+}
+
 extern "C" int lcs_prefilter(const void* u, const void* v, int in_dtype, double* coef_u, double* coef_v,
-                             void* scratch, size_t scratch_bytes, int nlev, int nlat, int nlon, void* stream) {
+                             void* scratch, size_t scratch_bytes, int nlev, int nlat, int nlon, int order, void* stream) {
     if (!u || !v || !coef_u || !coef_v || !scratch) return lcs_fail(LCS_E_INVALID, "lcs_prefilter: null argument");
     if (nlev < 1 || nlat < 2 || nlon < 2) return lcs_fail(LCS_E_INVALID, "lcs_prefilter: bad sizes");
     if (u == coef_u || v == coef_v) return lcs_fail(LCS_E_INVALID, "lcs_prefilter: outputs may not alias inputs");
     if (scratch_bytes < lcs_prefilter_scratch_bytes(nlev, nlat, nlon))
         return lcs_fail(LCS_E_WORKSPACE, "lcs_prefilter: scratch too small");
     if (2 * nlev > 65535) return lcs_fail(LCS_E_INVALID, "lcs_prefilter: at most 32767 levels per call");
+    if (in_dtype != LCS_F64 && in_dtype != LCS_F32) return lcs_fail(LCS_E_INVALID, "lcs_prefilter: bad in_dtype");
+    double poles[2];
+    const int npoles = spline_poles(order, poles);
+    if (npoles == 0) return lcs_fail(LCS_E_UNSUPPORTED, "lcs_prefilter: order must be 2..5 (order 1 needs no prefilter)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double* tmp = static_cast<double*>(scratch);
-    if (lcs_env_int("LCS_PREFILTER_FIR", 0) == 0) {
-        const double z = sqrt(3.0) - 2.0;
-        const double h0 = (1.0 - z) * (1.0 - 1.0 / z) * (-z) / (1.0 - z * z);   // = sqrt(3)
-        const dim3 q1((nlon + 127) / 128, (nlat + KQ - 1) / KQ, 2 * nlev);
-        if (in_dtype == LCS_F64)
-            iir_axis0_transpose_kernel<double><<<q1, 128, 0, st>>>((const double*)u, (const double*)v, 1, tmp, nullptr, 0,
-                                                                   nlat, nlon, z, h0);
-        else if (in_dtype == LCS_F32)
-            iir_axis0_transpose_kernel<float><<<q1, 128, 0, st>>>((const float*)u, (const float*)v, 1, tmp, nullptr, 0,
-                                                                  nlat, nlon, z, h0);
-        else return lcs_fail(LCS_E_INVALID, "lcs_prefilter: bad in_dtype");
-        cudaError_t e1 = cudaGetLastError();
-        if (e1 != cudaSuccess) return lcs_fail_cuda(e1, "lcs_prefilter(lat pass)");
-        const dim3 q2((nlat + 127) / 128, (nlon + KQ - 1) / KQ, 2 * nlev);
-        iir_axis0_transpose_kernel<double><<<q2, 128, 0, st>>>(tmp, nullptr, 0, coef_u, coef_v, 1, nlon, nlat, z, h0);
-        e1 = cudaGetLastError();
-        if (e1 != cudaSuccess) return lcs_fail_cuda(e1, "lcs_prefilter(lon pass)");
-        lcs_count_launches(2);
-        return LCS_OK;
-    }
+    const bool fir = order == 3 && lcs_env_int("LCS_PREFILTER_FIR", 0) != 0;    // the first (65-tap FIR) form, kept for A/B runs
     const FirTaps taps = make_taps();
-    // pass 1: along latitude; [plane][lat][lon] -> scratch [plane][lon][lat]
-    const dim3 g1((nlon + 127) / 128, (nlat + KR - 1) / KR, 2 * nlev);
-    if (in_dtype == LCS_F64)
-        fir_axis0_transpose_kernel<double><<<g1, 128, 0, st>>>((const double*)u, (const double*)v, 1, tmp, nullptr, 0,
-                                                               nlat, nlon, taps);
-    else if (in_dtype == LCS_F32)
-        fir_axis0_transpose_kernel<float><<<g1, 128, 0, st>>>((const float*)u, (const float*)v, 1, tmp, nullptr, 0,
-                                                              nlat, nlon, taps);
-    else return lcs_fail(LCS_E_INVALID, "lcs_prefilter: bad in_dtype");
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_prefilter(lat pass)");
-    // pass 2: along longitude; scratch [plane][lon][lat] -> coef [lat][lon] of u / v
-    const dim3 g2((nlat + 127) / 128, (nlon + KR - 1) / KR, 2 * nlev);
-    fir_axis0_transpose_kernel<double><<<g2, 128, 0, st>>>(tmp, nullptr, 0, coef_u, coef_v, 1, nlon, nlat, taps);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_prefilter(lon pass)");
-    lcs_count_launches(2);
+    const dim3 q1((nlon + 127) / 128, (nlat + KQ - 1) / KQ, 2 * nlev), q2((nlat + 127) / 128, (nlon + KQ - 1) / KQ, 2 * nlev);
+    const dim3 g1((nlon + 127) / 128, (nlat + KR - 1) / KR, 2 * nlev), g2((nlat + 127) / 128, (nlon + KR - 1) / KR, 2 * nlev);
+    // One pole = one symmetric two-sided exponential h0 z^|k| with unit DC gain.  Per pole: a pass along latitude
+    // ([plane][lat][lon] -> scratch [plane][lon][lat]) and a pass along longitude (scratch -> coef [lat][lon]); the
+    // second pole of orders 4 and 5 re-reads the coefficient planes.  scipy runs all poles along an axis before the
+    // next axis; the passes are linear and separable, so the order only moves the last bits.
+    for (int ip = 0; ip < npoles; ++ip) {
+        const double z = poles[ip];
+        const double h0 = (1.0 - z) * (1.0 - 1.0 / z) * (-z) / (1.0 - z * z);
+        int kh = (int)ceil(log(1e-18) / log(fabs(z)));                  // |z|^kh < 1e-18: below one f64 ulp of the sum
+        if (kh < 4) kh = 4;
+        const void* src_u = ip == 0 ? u : (const void*)coef_u;
+        const void* src_v = ip == 0 ? v : (const void*)coef_v;
+        const int src_dtype = ip == 0 ? in_dtype : LCS_F64;
+        if (fir) {
+            if (src_dtype == LCS_F64)
+                fir_axis0_transpose_kernel<double><<<g1, 128, 0, st>>>((const double*)src_u, (const double*)src_v, 1, tmp, nullptr, 0, nlat, nlon, taps);
+            else
+                fir_axis0_transpose_kernel<float><<<g1, 128, 0, st>>>((const float*)src_u, (const float*)src_v, 1, tmp, nullptr, 0, nlat, nlon, taps);
+        } else if (src_dtype == LCS_F64) {
+            iir_axis0_transpose_kernel<double><<<q1, 128, 0, st>>>((const double*)src_u, (const double*)src_v, 1, tmp, nullptr, 0,
+                                                                   nlat, nlon, z, h0, kh);
+        } else {
+            iir_axis0_transpose_kernel<float><<<q1, 128, 0, st>>>((const float*)src_u, (const float*)src_v, 1, tmp, nullptr, 0,
+                                                                  nlat, nlon, z, h0, kh);
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_prefilter(lat pass)");
+        if (fir) fir_axis0_transpose_kernel<double><<<g2, 128, 0, st>>>(tmp, nullptr, 0, coef_u, coef_v, 1, nlon, nlat, taps);
+        else iir_axis0_transpose_kernel<double><<<q2, 128, 0, st>>>(tmp, nullptr, 0, coef_u, coef_v, 1, nlon, nlat, z, h0, kh);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_prefilter(lon pass)");
+        lcs_count_launches(2);
+    }
     return LCS_OK;
 }
 

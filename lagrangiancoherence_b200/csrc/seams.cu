@@ -62,7 +62,10 @@ map_coordinates_kernel(const MapParams P) {
     double o[1];
     if (pole) gather_linear_constant<Scalar64, true>(P.field, P.nlat, P.nlon, iy, ix, o);
     else if (P.order == 3) gather_cubic_wrap<Scalar64, true>(P.coef, P.nlat, P.nlon, iy, ix, o);
-    else gather_linear_wrap<Scalar64, true>(P.field, P.nlat, P.nlon, iy, ix, o);
+    else if (P.order == 1) gather_linear_wrap<Scalar64, true>(P.field, P.nlat, P.nlon, iy, ix, o);
+    else if (P.order == 2) gather_spline_wrap<Scalar64, true, 2>(P.coef, P.nlat, P.nlon, iy, ix, o);
+    else if (P.order == 4) gather_spline_wrap<Scalar64, true, 4>(P.coef, P.nlat, P.nlon, iy, ix, o);
+    else gather_spline_wrap<Scalar64, true, 5>(P.coef, P.nlat, P.nlon, iy, ix, o);
     P.out[idx] = o[0];
 }
 
@@ -125,8 +128,8 @@ extern "C" int lcs_map_coordinates(const lcs_grid* g, const double* field, const
                                    const double* pos_x, const double* pos_y, int nrow, int ncol,
                                    int row0, int nrow_global, double* out, void* stream) {
     if (!g || !field || !pos_x || !pos_y || !out) return lcs_fail(LCS_E_INVALID, "lcs_map_coordinates: null argument");
-    if (order != 1 && order != 3) return lcs_fail(LCS_E_UNSUPPORTED, "lcs_map_coordinates: order must be 1 or 3");
-    if (order == 3 && !coef) return lcs_fail(LCS_E_INVALID, "lcs_map_coordinates: coef required for order 3");
+    if (order < 1 || order > 5) return lcs_fail(LCS_E_UNSUPPORTED, "lcs_map_coordinates: order must be 1..5");
+    if (order >= 2 && !coef) return lcs_fail(LCS_E_INVALID, "lcs_map_coordinates: coef required for orders >= 2");
     if (g->nlat < 4 || g->nlon < 4 || nrow < 1 || ncol < 1) return lcs_fail(LCS_E_INVALID, "lcs_map_coordinates: bad sizes");
     MapParams P{};
     P.field = field; P.coef = coef; P.nlat = g->nlat; P.nlon = g->nlon;

@@ -95,13 +95,17 @@ class FtleEngine:
         self.timestep = timestep
         self.S = int(SETTLS_order)
         self.order = int(interp_order)
-        if self.order not in (1, 3):
-            raise NotImplementedError('interp_order must be 1 or 3 (the reference default is 3; 0 is broken upstream, '
-                                      '2/4/5 are not implemented in the CUDA gather)')
+        if self.order not in (1, 2, 3, 4, 5):
+            # scipy raises RuntimeError('spline order not supported') outside 0..5; order 0 yields empty row slices
+            # upstream (tools.py:25,31-33) and is refused here
+            raise RuntimeError('spline order not supported' if self.order != 0 else
+                               'interp_order=0 is broken upstream (empty slices in xr_map_coordinates); use 1..5')
         self.xmode = XMODES[xmode]
         self.pair_dtype = DTYPES[pair_dtype]
         self.strict = int(bool(strict))
         self.layout = _lib.LCS_LAYOUT_PAIR4 if self.strict or layout == 'pair4' else _lib.LCS_LAYOUT_ES
+        if self.order in (2, 4, 5) and (self.pair_dtype != _lib.LCS_F64 or self.layout != _lib.LCS_LAYOUT_ES):
+            raise ValueError('interp_order 2, 4 and 5 run on the f64 ES layout only (no strict / pair4 / f32 variants)')
         if arith not in ('f64', 'f32'):
             raise ValueError("arith must be 'f64' or 'f32'")
         if arith == 'f32' and (self.pair_dtype != _lib.LCS_F32 or self.layout != _lib.LCS_LAYOUT_ES or self.order != 3):
@@ -143,13 +147,13 @@ class FtleEngine:
         with torch.cuda.device(self.device):
             st = _stream(self.device)
             cu = cv = None
-            if self.order == 3:
+            if self.order >= 2:
                 cu = torch.empty((nlev,) + shape2, dtype=torch.float64, device=self.device)
                 cv = torch.empty_like(cu)
                 scratch = torch.empty((2,) + tuple(cu.shape), dtype=torch.float64, device=self.device)
                 _lib.check(self.lib.lcs_prefilter(_ptr(u), _ptr(v), _dtype_code(u), _ptr(cu), _ptr(cv),
                                                   _ptr(scratch), scratch.numel() * 8,
-                                                  nlev, self.nlat, self.nlon, st), 'lcs_prefilter')
+                                                  nlev, self.nlat, self.nlon, self.order, st), 'lcs_prefilter')
             if self.layout == _lib.LCS_LAYOUT_PAIR4:
                 def pack(a, b, code):
                     out = torch.empty((nlev - 1,) + shape2 + (4,), dtype=tdt, device=self.device)
@@ -302,20 +306,20 @@ def map_coordinates_device(field, pos_x, pos_y, lat, lon, order=1, device='cuda:
         py = torch.as_tensor(np.ascontiguousarray(pos_y, dtype=np.float64)).to(device)
         nrow, ncol = px.shape
         coef = None
-        if order == 3:
+        if order >= 2:
             coef = torch.empty_like(f)
             dummy = torch.empty_like(f)
             scratch = torch.empty((2,) + tuple(f.shape), dtype=torch.float64, device=device)
             _lib.check(lib.lcs_prefilter(_ptr(f), _ptr(f), _lib.LCS_F64, _ptr(coef), _ptr(dummy), _ptr(scratch),
-                                         scratch.numel() * 8, 1, lat.size, lon.size, _stream(device)), 'lcs_prefilter')
+                                         scratch.numel() * 8, 1, lat.size, lon.size, int(order), _stream(device)), 'lcs_prefilter')
         out = torch.empty_like(px)
         _lib.check(lib.lcs_map_coordinates(C.byref(grid), _ptr(f), _ptr(coef), order, _ptr(px), _ptr(py),
                                            nrow, ncol, 0, nrow, _ptr(out), _stream(device)), 'lcs_map_coordinates')
     return out
 
 
-def prefilter_device(u, v, device='cuda:0'):
-    """Cubic B-spline coefficients of ``[nlev, nlat, nlon]`` series (f64 tensors on the device)."""
+def prefilter_device(u, v, device='cuda:0', order=3):
+    """B-spline coefficients (order 2..5) of ``[nlev, nlat, nlon]`` series (f64 tensors on the device)."""
     lib = _lib.load()
     device = torch.device(device)
     with torch.cuda.device(device):
@@ -326,7 +330,7 @@ def prefilter_device(u, v, device='cuda:0'):
         cv = torch.empty_like(cu)
         scratch = torch.empty((2,) + tuple(cu.shape), dtype=torch.float64, device=device)
         _lib.check(lib.lcs_prefilter(_ptr(tu), _ptr(tv), _dtype_code(tu), _ptr(cu), _ptr(cv), _ptr(scratch),
-                                     scratch.numel() * 8, nlev, nlat, nlon, _stream(device)), 'lcs_prefilter')
+                                     scratch.numel() * 8, nlev, nlat, nlon, int(order), _stream(device)), 'lcs_prefilter')
     return cu, cv
 
 

@@ -428,35 +428,56 @@ def lcs_field(U, V, lat, lon, timestep, SETTLS_order=0, traj_interp_order=3,
 SPLINE_POLE = np.sqrt(3.0) - 2.0
 
 
-def prefilter_line_mirror(c, z=SPLINE_POLE):
-    """Cubic B-spline prefilter of one line, mirror boundary, exact causal initialisation."""
+def spline_poles(order):
+    """Poles of the B-spline prefilter, scipy ni_splines.c:get_filter_poles (orders 2..5)."""
+    if order == 2:
+        return [np.sqrt(8.0) - 3.0]
+    if order == 3:
+        return [np.sqrt(3.0) - 2.0]
+    if order == 4:
+        return [np.sqrt(664.0 - np.sqrt(438976.0)) + np.sqrt(304.0) - 19.0,
+                np.sqrt(664.0 + np.sqrt(438976.0)) - np.sqrt(304.0) - 19.0]
+    if order == 5:
+        return [np.sqrt(67.5 - np.sqrt(4436.25)) + np.sqrt(26.25) - 6.5,
+                np.sqrt(67.5 + np.sqrt(4436.25)) - np.sqrt(26.25) - 6.5]
+    raise RuntimeError('spline order not supported')          # scipy's message for order outside 0..5
+
+
+def prefilter_line_mirror(c, z=None, order=3):
+    """B-spline prefilter of one line, mirror boundary, exact causal initialisation: the gain of all poles
+    first, then per pole a causal and an anticausal recursion (scipy ni_splines.c:apply_filter)."""
     c = np.array(c, dtype=np.float64)
     n = c.shape[0]
     if n < 2:
         return c
-    c *= (1.0 - z) * (1.0 - 1.0 / z)
-    z_n_1 = z ** (n - 1)
-    z_i = z
-    c0 = c[0] + z_n_1 * c[n - 1]
-    for i in range(1, n - 1):
-        c0 += z_i * (c[i] + z_n_1 * c[n - 1 - i])
-        z_i *= z
-    c[0] = c0 / (1 - z_n_1 * z_n_1)
-    for i in range(1, n):
-        c[i] += z * c[i - 1]
-    c[n - 1] = (z * c[n - 2] + c[n - 1]) * z / (z * z - 1)
-    for i in range(n - 2, -1, -1):
-        c[i] = z * (c[i + 1] - c[i])
+    poles = [z] if z is not None else spline_poles(order)
+    gain = 1.0
+    for z in poles:
+        gain *= (1.0 - z) * (1.0 - 1.0 / z)
+    c *= gain
+    for z in poles:
+        z_n_1 = z ** (n - 1)
+        z_i = z
+        c0 = c[0] + z_n_1 * c[n - 1]
+        for i in range(1, n - 1):
+            c0 += z_i * (c[i] + z_n_1 * c[n - 1 - i])
+            z_i *= z
+        c[0] = c0 / (1 - z_n_1 * z_n_1)
+        for i in range(1, n):
+            c[i] += z * c[i - 1]
+        c[n - 1] = (z * c[n - 2] + c[n - 1]) * z / (z * z - 1)
+        for i in range(n - 2, -1, -1):
+            c[i] = z * (c[i + 1] - c[i])
     return c
 
 
-def prefilter_2d(field):
+def prefilter_2d(field, order=3):
     """Axis 0 then axis 1, f64 (what map_coordinates does on every call)."""
     c = np.array(field, dtype=np.float64)
     for j in range(c.shape[1]):
-        c[:, j] = prefilter_line_mirror(c[:, j])
+        c[:, j] = prefilter_line_mirror(c[:, j], order=order)
     for i in range(c.shape[0]):
-        c[i, :] = prefilter_line_mirror(c[i, :])
+        c[i, :] = prefilter_line_mirror(c[i, :], order=order)
     return c
 
 
@@ -483,31 +504,83 @@ def mirror_index(i, n):
     return i
 
 
+def spline_weights(c, order):
+    """First tap index and the order+1 interpolation weights at coordinate ``c``
+    (scipy ni_splines.c:get_spline_interpolation_weights and the `start` rule of NI_GeometricTransform),
+    in scipy's order of operations: the restatement is bit-exact against scipy (tests/test_oracle_scipy_spec.py)."""
+    if order & 1:
+        start = int(np.floor(c)) - order // 2
+        x = c - np.floor(c)
+    else:
+        start = int(np.floor(c + 0.5)) - order // 2
+        x = c - np.floor(c + 0.5)
+    y = x
+    z = 1.0 - x
+    w = [0.0] * (order + 1)
+    if order == 1:
+        w[0] = 1.0 - x
+    elif order == 2:
+        w[1] = 0.75 - x * x
+        y = 0.5 - x
+        w[0] = 0.5 * y * y
+    elif order == 3:
+        w[1] = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0
+        w[2] = (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0
+        w[0] = z * z * z / 6.0
+    elif order == 4:
+        t = x * x
+        w[2] = t * (t * 0.25 - 0.625) + 115.0 / 192.0
+        y = 1.0 + x
+        w[1] = y * (y * (y * (5.0 - y) / 6.0 - 1.25) + 5.0 / 24.0) + 55.0 / 96.0
+        w[3] = z * (z * (z * (5.0 - z) / 6.0 - 1.25) + 5.0 / 24.0) + 55.0 / 96.0
+        y = 0.5 - x
+        t = y * y
+        w[0] = t * t / 24.0
+    elif order == 5:
+        t = y * y
+        w[2] = t * (t * (0.25 - y / 12.0) - 0.5) + 0.55
+        t = z * z
+        w[3] = t * (t * (0.25 - z / 12.0) - 0.5) + 0.55
+        y = y + 1.0
+        w[1] = y * (y * (y * (y * (y / 24.0 - 0.375) + 1.25) - 1.75) + 0.625) + 0.425
+        z = z + 1.0
+        w[4] = z * (z * (z * (z * (z / 24.0 - 0.375) + 1.25) - 1.75) + 0.625) + 0.425
+        y = 1.0 - x
+        t = y * y
+        w[0] = y * t * t / 120.0
+    else:
+        raise RuntimeError('spline order not supported')
+    last = 1.0
+    for i in range(order):
+        last -= w[i]
+    w[order] = last
+    return start, tuple(w)
+
+
 def cubic_weights(x):
-    f = np.floor(x)
-    y = x - f
-    z = 1.0 - y
-    w1 = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0
-    w2 = (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0
-    w0 = z * z * z / 6.0
-    w3 = 1.0 - w0 - w1 - w2
-    return int(f) - 1, (w0, w1, w2, w3)
+    return spline_weights(x, 3)
 
 
-def gather_cubic_wrap(coef, cy, cx):
+def gather_spline_wrap(coef, cy, cx, order=3):
+    """map_coordinates(order, mode='wrap', prefilter=False) at one point: fold (period n-1), (order+1)^2 taps with
+    mirrored indices, accumulated in scipy's order ((c*wy)*wx, axis-0 index outer)."""
     ny, nx = coef.shape
     cy = fold_wrap(cy, ny)
     cx = fold_wrap(cx, nx)
-    sy, wy = cubic_weights(cy)
-    sx, wx = cubic_weights(cx)
+    sy, wy = spline_weights(cy, order)
+    sx, wx = spline_weights(cx, order)
     t = 0.0
-    for i in range(4):
-        for j in range(4):
+    for i in range(order + 1):
+        for j in range(order + 1):
             v = coef[mirror_index(sy + i, ny), mirror_index(sx + j, nx)]
             v = v * wy[i]
             v = v * wx[j]
             t += v
     return t
+
+
+def gather_cubic_wrap(coef, cy, cx):
+    return gather_spline_wrap(coef, cy, cx, 3)
 
 
 def gather_linear_constant(field, cy, cx):

@@ -43,7 +43,7 @@ def test_argument_validation_without_a_gpu(lib_path):
     """Entry points reject bad arguments before touching the device (safe to call on a CPU-only box)."""
     from lagrangiancoherence_b200 import _lib
     lib = _lib.load()
-    assert lib.lcs_prefilter(None, None, 0, None, None, None, 0, 1, 8, 8, None) == -1
+    assert lib.lcs_prefilter(None, None, 0, None, None, None, 0, 1, 8, 8, 3, None) == -1
     assert b'null' in lib.lcs_last_error()
     assert lib.lcs_pack_pairs(None, None, 0, None, 0, 2, 8, 8, None) == -1
     assert lib.lcs_ftle_epilogue(None, None, 1, 8, 8, 0, 8, 0, 8, None, 1.0, None, 0, None, None, None, None) == -1

@@ -32,6 +32,31 @@ def test_cubic_wrap_gather_is_bit_exact(field):
     assert np.array_equal(ref, mine)
 
 
+@pytest.mark.parametrize('order', [2, 4, 5])
+def test_other_spline_orders_gather_is_bit_exact(field, order):
+    """traj_interp_order is free upstream (any order scipy accepts); orders 2, 4, 5: weights, first-tap rule
+    (floor(x + 0.5) for even orders) and mirrored taps, bit for bit against scipy."""
+    C = ndi.spline_filter(field, order=order, output=np.float64, mode='mirror')
+    cy, cx = coords(6000, *field.shape, seed=10 + order)
+    ref = ndi.map_coordinates(C, np.array([cy, cx]), order=order, mode='wrap', prefilter=False)
+    mine = np.array([O.gather_spline_wrap(C, a, b, order) for a, b in zip(cy, cx)])
+    assert np.array_equal(ref, mine)
+
+
+@pytest.mark.parametrize('order', [2, 4, 5])
+def test_other_spline_orders_prefilter_and_composition(field, order):
+    """Poles and gain of orders 2, 4, 5 (two poles for 4 and 5: conditioning costs a digit or two, stated 1e-13)."""
+    ref = ndi.spline_filter(field, order=order, output=np.float64, mode='mirror')
+    C = O.prefilter_2d(field, order=order)
+    assert np.abs(C - ref).max() <= 1e-13 * np.abs(ref).max()
+    cy, cx = coords(2000, *field.shape, seed=20 + order)
+    full = ndi.map_coordinates(field, np.array([cy, cx]), order=order, mode='wrap')
+    mine = np.array([O.gather_spline_wrap(C, a, b, order) for a, b in zip(cy, cx)])
+    assert np.abs(full - mine).max() <= 1e-12 * np.abs(field).max()
+    with pytest.raises(RuntimeError):
+        O.spline_poles(6)
+
+
 def test_linear_wrap_and_constant_gathers_are_bit_exact(field):
     cy, cx = coords(20000, *field.shape, seed=2)
     ref = ndi.map_coordinates(field, np.array([cy, cx]), order=1, mode='wrap')
