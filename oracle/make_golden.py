@@ -15,7 +15,8 @@ How the reference is made importable here (nothing under /root/reference is modi
 Inputs are regenerated from seeds by lagrangiancoherence_b200.synthetic, so a fixture stores only the
 case description and the reference's outputs.
 
-    python oracle/make_golden.py          # rewrites tests/golden/
+    python oracle/make_golden.py                      # rewrites tests/golden/
+    python oracle/make_golden.py --only a,b,seams     # only these fixtures (the others keep their bytes)
 """
 from __future__ import annotations
 
@@ -61,6 +62,13 @@ CASES = {
                         timestep=-3600, S=0, order=3, cyclic=False),
     'cyclic_vortex_backward': dict(kind='vortex', timestep=-21600, S=4, order=3, cyclic=True),
     'cyclic_vortex_forward': dict(kind='vortex', timestep=21600, S=2, order=3, cyclic=True),
+    # traj_interp_order other than the default 3 and 1 (any order scipy accepts works upstream)
+    'regional_outer_p2': dict(kind='era5', nlat=33, nlon=45, lat=(-20.0, 12.0), lon=(-70.0, -26.0), nt=4, seed=6,
+                              timestep=-21600, S=3, order=2, cyclic=False),
+    'regional_outer_p4': dict(kind='era5', nlat=33, nlon=45, lat=(-20.0, 12.0), lon=(-70.0, -26.0), nt=4, seed=7,
+                              timestep=-21600, S=2, order=4, cyclic=False),
+    'regional_outer_p5': dict(kind='era5', nlat=33, nlon=45, lat=(-20.0, 12.0), lon=(-70.0, -26.0), nt=4, seed=8,
+                              timestep=10800, S=3, order=5, cyclic=False),
     'descending_lat_dims_shuffled': dict(kind='era5', nlat=29, nlon=37, lat=(-28.0, 0.0), lon=(-72.0, -36.0), nt=4, seed=5,
                                          timestep=-21600, S=3, order=3, cyclic=False, flip_lat=True,
                                          dims=['latitude', 'time', 'longitude']),
@@ -97,7 +105,13 @@ def main():
     os.makedirs(GOLDEN, exist_ok=True)
     quiet = io.StringIO()
     manifest = {}
+    only = None
+    if '--only' in sys.argv:
+        only = set(sys.argv[sys.argv.index('--only') + 1].split(','))
+        manifest = json.load(open(os.path.join(GOLDEN, 'manifest.json')))
     for name, case in CASES.items():
+        if only is not None and name not in only:
+            continue
         u, v, lat, lon, time = make_inputs(case)
         du, dv = to_xr(xr, case, u, v, lat, lon, time)
         out = {}
@@ -129,6 +143,10 @@ def main():
         manifest[name] = case
         print(f'{name}: ' + ', '.join(f'{k}{tuple(np.shape(v))}' for k, v in out.items()))
 
+    if only is not None and 'seams' not in only:
+        with open(os.path.join(GOLDEN, 'manifest.json'), 'w') as f:
+            json.dump(manifest, f, indent=1, sort_keys=True)
+        return
     # seams: xr_map_coordinates, derivative_spherical_coords, fourth_order_derivative, subdomain crop
     case = CASES['regional_outer_p3']
     u, v, lat, lon, time = make_inputs(case)
@@ -137,7 +155,7 @@ def main():
     X, Y = np.meshgrid(lon, lat)
     px, py = X + rng.normal(0, 3.0, X.shape), Y + rng.normal(0, 3.0, Y.shape)
     seams = {'px': px, 'py': py}
-    for order in (1, 3):
+    for order in (1, 2, 3, 4, 5):
         seams[f'map_coordinates_p{order}'] = ref_tools.xr_map_coordinates(du.isel(time=0), px, py, order=order).values
     c2 = {'latitude': lat, 'longitude': lon}
     Xs = xr.DataArray(6371000 * np.sin((py - 90) * np.pi / 180) * np.cos(px * np.pi / 180), c2, ('latitude', 'longitude'))

@@ -53,8 +53,10 @@ def test_unsupported_interp_order_is_loud(cuda_device, case):
     from lagrangiancoherence_b200.LCS.trajectory import parcel_propagation
     u, v, lat, lon = case
     du, dv, _ = arrays(u, v, lat, lon)
-    with pytest.raises(NotImplementedError):
-        parcel_propagation(du, dv, timestep=3600, interp_order=2, verbose=False)
+    with pytest.raises(RuntimeError, match='spline order not supported'):      # scipy's error and message upstream
+        parcel_propagation(du, dv, timestep=3600, interp_order=6, verbose=False)
+    with pytest.raises(RuntimeError):                                           # order 0: empty slices upstream
+        parcel_propagation(du, dv, timestep=3600, interp_order=0, verbose=False)
 
 
 def test_float32_winds_are_accepted(cuda_device, case):

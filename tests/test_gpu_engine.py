@@ -25,8 +25,9 @@ def rel_err(a, b, scale):
 @pytest.mark.parametrize('shape', [(41, 57), (5, 7), (281, 321), (64, 33)])
 @pytest.mark.parametrize('dtype', [np.float64, np.float32])
 def test_prefilter_matches_scipy(cuda_device, shape, dtype):
-    """65-tap truncated two-sided FIR == scipy's recursive spline_filter to ~1e-15 of the field magnitude
-    (f64 tolerance stated: 2e-14 * max|c|), including lines shorter than the filter half-width."""
+    """Run-recursive form of the truncated two-sided exponential filter == scipy's recursive spline_filter to
+    ~1e-15 of the field magnitude (f64 tolerance stated: 2e-14 * max|c|), including lines shorter than the
+    truncation half-width and than a thread's run of outputs."""
     from scipy import ndimage as ndi
     from lagrangiancoherence_b200 import engine as E
     rng = np.random.default_rng(1)
@@ -40,7 +41,50 @@ def test_prefilter_matches_scipy(cuda_device, shape, dtype):
             assert np.abs(got - ref).max() <= 2e-14 * np.abs(ref).max()
 
 
-@pytest.mark.parametrize('order', [1, 3])
+@pytest.mark.parametrize('order', [2, 4, 5])
+@pytest.mark.parametrize('shape', [(5, 7), (41, 57), (64, 33)])
+def test_prefilter_other_orders_match_scipy(cuda_device, shape, order):
+    """Orders 2 (one pole), 4 and 5 (two poles, applied as two lat/lon pass pairs).  Stated tolerance 5e-13 * max|c|:
+    the second pole's gain (1-z)(1-1/z) ~ 75 (order 4) amplifies rounding; scipy's own recursion differs from the
+    exact coefficients by as much (tests/test_oracle_scipy_spec.py)."""
+    from scipy import ndimage as ndi
+    from lagrangiancoherence_b200 import engine as E
+    rng = np.random.default_rng(order)
+    u = rng.normal(size=(2,) + shape) * 10
+    v = rng.normal(size=(2,) + shape) * 10
+    cu, cv = E.prefilter_device(u, v, cuda_device, order=order)
+    for k in range(2):
+        for got, src in ((cu[k].cpu().numpy(), u[k]), (cv[k].cpu().numpy(), v[k])):
+            ref = ndi.spline_filter(src, order=order, output=np.float64, mode='mirror')
+            assert np.abs(got - ref).max() <= 5e-13 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize('xmode,cyclic,xclamp', [('cyclic', True, 'outer'), ('pointwise', False, 'pointwise'),
+                                                 ('outer', False, 'outer')])
+@pytest.mark.parametrize('order', [2, 4, 5])
+def test_advect_other_spline_orders_match_oracle(cuda_device, xmode, cyclic, xclamp, order):
+    """traj_interp_order 2, 4, 5 (generic gather, f64 ES layout) against the oracle = scipy's own map_coordinates of that
+    order; the first/last `order` arrival rows take the order-1 'constant' branch (tools.py:31-39)."""
+    from lagrangiancoherence_b200.engine import FtleEngine
+    u, v, lat, lon = small_case()
+    dt = -21600
+    rx, ry = O.parcel_propagation(u, v, lat, lon, dt, SETTLS_order=3, interp_order=order,
+                                  cyclic_xboundary=cyclic, xclamp=xclamp, return_traj=True)
+    eng = FtleEngine(lat, lon, dt, SETTLS_order=3, interp_order=order, xmode=xmode, device=cuda_device)
+    x, y, xt, yt = eng.advect(eng.stage(u, v), return_traj=True)
+    ex = rel_err(xt[0].cpu().numpy(), rx, np.abs(lon).max())
+    ey = rel_err(yt[0].cpu().numpy(), ry, np.abs(lat).max())
+    frac_bad = max((ex > REL_POS).mean(), (ey > REL_POS).mean())
+    assert frac_bad <= 1e-3, (ex.max(), ey.max(), frac_bad)
+    assert np.median(ex) <= 1e-12 and np.median(ey) <= 1e-12
+    for bad in (dict(pair_dtype='f32'), dict(layout='pair4'), dict(strict=True)):
+        with pytest.raises(ValueError):
+            FtleEngine(lat, lon, dt, interp_order=order, device=cuda_device, **bad)
+    with pytest.raises(RuntimeError):
+        FtleEngine(lat, lon, dt, interp_order=6, device=cuda_device)
+
+
+@pytest.mark.parametrize('order', [1, 2, 3, 4, 5])
 def test_map_coordinates_seam(cuda_device, order):
     from lagrangiancoherence_b200 import engine as E
     u, v, lat, lon = small_case()
@@ -49,7 +93,7 @@ def test_map_coordinates_seam(cuda_device, order):
     py = np.meshgrid(lon, lat)[1] + rng.normal(0, 3.0, (lat.size, lon.size))
     ref = O.xr_map_coordinates(u[0], px, py, lat, lon, order=order)
     got = E.map_coordinates_device(u[0], px, py, lat, lon, order=order, device=cuda_device).cpu().numpy()
-    assert np.abs(got - ref).max() <= 1e-12 * np.abs(u[0]).max()
+    assert np.abs(got - ref).max() <= (1e-12 if order <= 3 else 1e-11) * np.abs(u[0]).max()
     if order == 1:
         assert np.array_equal(got, ref)          # no prefilter involved: bit-exact gather
 
