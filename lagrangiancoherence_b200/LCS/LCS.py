@@ -105,6 +105,7 @@ class LCS:
             r0 = out_rows[0] if out_rows else 0
             sigma = sigma[latkeep[r0:r0 + sigma.shape[0]]][:, lonkeep] if out_rows else sigma[:0, :0]
             olat, olon = lat[latkeep], lon[lonkeep]
+        sigma, olat, olon = drop_unused_levels(sigma, olat, olon)    # LCS.py:146,157: dropna('points') ... unstack('points')
         tvals = coord_values(Us, timedim) if resample_plan_ is None else resample_plan_[0]
         timestamp = tvals[-1] if np.sign(timestep) == 1 else tvals[0]                         # LCS.py:158
         coords = {'latitude': olat, 'longitude': olon, 'time': np.asarray(timestamp)}        # LCS.py:159
@@ -128,6 +129,19 @@ class LCS:
         elif return_traj:
             return eigenvalues, x_trajs, y_trajs
         return eigenvalues
+
+
+def drop_unused_levels(sigma, lat, lon):
+    """``def_tensor.dropna('points')`` followed by ``unstack('points')`` (LCS.py:146,157): points with a NaN
+    derivative come back as NaN, but a latitude (longitude) none of whose points survived is no longer a level of
+    the stacked index and disappears from the result altogether (xarray removes unused levels when unstacking)."""
+    nan = np.isnan(sigma)
+    if not nan.any():
+        return sigma, lat, lon
+    keep_r, keep_c = ~nan.all(axis=1), ~nan.all(axis=0)
+    if keep_r.all() and keep_c.all():
+        return sigma, lat, lon
+    return sigma[keep_r][:, keep_c], np.asarray(lat)[keep_r], np.asarray(lon)[keep_c]
 
 
 def flowmap_gradient(x_departure, y_departure, sigma=None, *, device='cuda:0'):

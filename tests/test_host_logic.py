@@ -110,3 +110,21 @@ def test_shard_planners_cover_everything_exactly_once():
             for o0, o1, i0, i1 in rows:
                 assert i0 == max(0, o0 - 2) and i1 == min(n, o1 + 2)        # 2-row halo: y-stencil spans +-2 rows
     assert chunk_starts(5, 10, 4) == [(5, 4), (9, 4), (13, 2)]
+
+
+def test_dropna_unstack_removes_fully_dropped_rows_and_columns():
+    """LCS.py:146,157: a point with a NaN derivative is dropped from the stacked index and comes back as NaN after
+    unstack; a latitude/longitude with no surviving point is not a level any more and vanishes from the result."""
+    from lagrangiancoherence_b200.LCS.LCS import drop_unused_levels
+    lat, lon = np.arange(5.0), np.arange(6.0)
+    s = np.arange(30.0).reshape(5, 6)
+    out, la, lo = drop_unused_levels(s, lat, lon)
+    assert out is s and la is lat and lo is lon
+    s[1, 2] = np.nan                       # isolated NaN: shape kept
+    out, la, lo = drop_unused_levels(s, lat, lon)
+    assert out.shape == (5, 6) and np.isnan(out[1, 2])
+    s[3, :] = np.nan                       # whole row dropped
+    s[:, 0] = np.nan                       # whole column dropped
+    out, la, lo = drop_unused_levels(s, lat, lon)
+    assert out.shape == (4, 5) and np.array_equal(la, [0, 1, 2, 4]) and np.array_equal(lo, [1, 2, 3, 4, 5])
+    assert np.isnan(out[1, 1]) and np.isnan(out).sum() == 1
