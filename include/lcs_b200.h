@@ -88,6 +88,10 @@ typedef struct lcs_winds {
     const void* raw_b;
     const void* coef_a;
     const void* coef_b;
+    int32_t raw_planar;     /* 1 (LCS_LAYOUT_ES, interp_order >= 2 only): raw_a / raw_b are the planar series u / v
+                               [nlev][nlat][nlon] of raw_dtype instead of packed E / S.  Only the 2*order pole rows
+                               sample the raw winds at those orders, so no second packed copy is staged for them */
+    int32_t raw_dtype;      /* LCS_F64 / LCS_F32 storage of the planar raw series                                  */
 } lcs_winds;
 
 /* ---------------------------------------------------------------- housekeeping */

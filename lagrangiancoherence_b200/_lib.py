@@ -38,7 +38,8 @@ class AdvectOpts(C.Structure):
 
 class Winds(C.Structure):
     _fields_ = [('layout', C.c_int32), ('dtype', C.c_int32),
-                ('raw_a', c_void_p), ('raw_b', c_void_p), ('coef_a', c_void_p), ('coef_b', c_void_p)]
+                ('raw_a', c_void_p), ('raw_b', c_void_p), ('coef_a', c_void_p), ('coef_b', c_void_p),
+                ('raw_planar', C.c_int32), ('raw_dtype', C.c_int32)]
 
 
 # name -> (restype, argtypes): every symbol include/lcs_b200.h declares

@@ -83,6 +83,10 @@ struct Vec2F32Arith {
     }
 };
 // planar f64 field, one value per tap (the map_coordinates seam)
+struct Scalar32 {
+    using type = float; static constexpr int NV = 1; static constexpr bool A32 = false;
+    static __device__ __forceinline__ void ld(const float* p, double (&o)[1]) { o[0] = (double)__ldg(p); }
+};
 struct Scalar64 {
     using type = double; static constexpr int NV = 1; static constexpr bool A32 = false;
     static __device__ __forceinline__ void ld(const double* p, double (&o)[1]) { o[0] = __ldg(p); }

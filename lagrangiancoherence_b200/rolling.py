@@ -114,9 +114,9 @@ def rolling_ftle(u, v, lat, lon, window_levels, timestep, SETTLS_order=4, interp
                     dv.copy_(v[lo:hi], non_blocking=True)
                 main.wait_event(up.record_event())
             staged = engine.stage(du, dv)
-            if not on_device:
-                pipe['in_free'][i % 2] = main.record_event()     # staging has consumed the raw levels
             x, y = engine.advect(staged, nsteps=nsteps, nwindows=n, level0=0, level_stride=1)
+            if not on_device:
+                pipe['in_free'][i % 2] = main.record_event()     # the integrator's pole rows read the raw levels too
             sig = engine.epilogue(x, y, log_scale=log_scale)
             if to_host:
                 down.wait_event(main.record_event())

@@ -227,3 +227,34 @@ def test_f32_arithmetic_argument_validation(cuda_device):
     eng.arith = _lib.LCS_ARITH_F32
     with pytest.raises(_lib.LcsError):
         eng.advect(st)
+
+
+@pytest.mark.parametrize('xmode', ['pointwise', 'outer'])
+@pytest.mark.parametrize('dtype', [np.float64, np.float32])
+def test_planar_and_packed_raw_winds_agree(cuda_device, xmode, dtype):
+    """The pole rows (first/last `order` arrival rows: order 1, mode 'constant' on the raw winds, tools.py:31-39) either
+    read a packed E/S copy of the series or the planar u, v input itself (engine.stage raw=...).  Same particles, same
+    taps; the SETTLS operand is combined before (packed) or after (planar, the reference's order) the interpolation, so
+    the two agree to rounding, and both agree with the oracle."""
+    from lagrangiancoherence_b200.engine import FtleEngine
+    u, v, lat, lon = small_case()
+    u, v = u.astype(dtype), v.astype(dtype)
+    eng = FtleEngine(lat, lon, -21600, SETTLS_order=4, xmode=xmode, device=cuda_device)
+    res = {}
+    for raw in ('packed', 'planar'):
+        st = eng.stage(u, v, raw=raw)
+        assert st.raw_planar == (raw == 'planar')
+        x, y = eng.advect(st)
+        res[raw] = (x[0].cpu().numpy(), y[0].cpu().numpy())
+    assert eng.stage(u, v).raw_planar
+    rx, ry = O.parcel_propagation(u.astype(np.float64), v.astype(np.float64), lat, lon, -21600, SETTLS_order=4, xclamp=xmode)
+    for raw in res:
+        assert (rel_err(res[raw][0], rx, np.abs(lon).max()) > REL_POS).mean() <= 1e-3
+        assert (rel_err(res[raw][1], ry, np.abs(lat).max()) > REL_POS).mean() <= 1e-3
+    pole = np.r_[0:3, lat.size - 3:lat.size]
+    assert np.abs(res['packed'][0][pole] - res['planar'][0][pole]).max() <= 1e-11 * np.abs(lon).max()
+    interior = np.arange(3, lat.size - 3)
+    if xmode == 'pointwise':                  # interior rows never touch the raw winds: identical bits
+        assert np.array_equal(res['packed'][0][interior], res['planar'][0][interior])
+    with pytest.raises(ValueError):
+        eng.stage(u, v, raw='texture')
