@@ -72,7 +72,8 @@ def config_dict(args, desc, B, world):
     return {'workload': f'{desc}, SETTLS_order={S_ORDER}, interp_order={args.order}, {args.precision} winds, '
                         f'xclamp={args.xclamp}; step = {B} rolling start times per GPU',
             'grid': desc.split(',')[0], 'windows_per_step_per_gpu': B, 'xclamp': args.xclamp,
-            'interp_order': args.order, 'settls_order': S_ORDER, 'sharding': f'start-times x{world}',
+            'interp_order': args.order, 'settls_order': S_ORDER, 'sharding': f'start-times x{world}' + ('' if world == 1 else ', finished fields gathered on every rank inside the timed '
+                                                                  'region (' + os.environ.get('LCS_BENCH_GATHER', 'p2p') + ')'),
             'l2': 'flushed between timed steps (256 MiB write)'}
 
 
@@ -201,6 +202,8 @@ def run_b200(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    from lagrangiancoherence_b200.affinity import bind_host_to_gpu
+    numa = bind_host_to_gpu(local) if world > 1 and not os.environ.get('LCS_NO_NUMA_BIND') else None
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
@@ -220,8 +223,13 @@ def run_b200(args):
     eng = FtleEngine(lat, lon, dt, SETTLS_order=S_ORDER, interp_order=args.order, xmode=args.xclamp,
                      device=dev, **precision_args(args.precision))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gathered = [torch.empty((B, lat.size, lon.size), dtype=torch.float64, device=dev) for _ in range(world)] \
-        if world > 1 else None
+    gather_mode = os.environ.get('LCS_BENCH_GATHER', 'p2p')          # 'p2p' (NVLink peer copies) | 'nccl' (all_gather)
+    gathered = peer = None
+    if world > 1 and gather_mode == 'p2p':
+        from lagrangiancoherence_b200.peer import PeerFields
+        peer = PeerFields([B] * world, lat.size, lon.size, device=dev)
+    elif world > 1:
+        gathered = [torch.empty((B, lat.size, lon.size), dtype=torch.float64, device=dev) for _ in range(world)]
     x = torch.empty((B, lat.size, lon.size), dtype=torch.float64, device=dev)
     y = torch.empty_like(x)
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -238,20 +246,27 @@ def run_b200(args):
             if timed:
                 adv_ms.append([(a, b)])
             return sigma
-        # N > 1: two half-batches, so that the NCCL gather of the first half's finished fields (the only
-        # collective on this path) runs while the second half is still being integrated
-        half = B // 2
+        # N > 1: the batch goes in parts (whole waves of 296 windows where B allows, else halves), so that the gather
+        # of a finished part's fields (the only exchange on this path: NVLink peer copies, or NCCL all_gather with
+        # LCS_BENCH_GATHER=nccl) runs while the next part is integrated
+        nparts = B // 296 if (B % 296 == 0 and B >= 592) else 2
+        bounds = [B * i // nparts for i in range(nparts + 1)]
         works, evs, sig = [], [], []
-        for lo, n in ((0, half), (half, B - half)):
+        for lo, n in ((bounds[i], bounds[i + 1] - bounds[i]) for i in range(nparts)):
             a, b = ev(), ev()
             a.record()
             eng.advect(st, nsteps=nt - 1, nwindows=n, level0=lo, out=(x[lo:lo + n], y[lo:lo + n]))
             b.record()
             evs.append((a, b))
             sig.append(eng.epilogue(x[lo:lo + n], y[lo:lo + n]))
-            works.append(dist.all_gather([g[lo:lo + n] for g in gathered], sig[-1], async_op=True))
+            if peer is not None:
+                peer.push(lo, sig[-1])
+            else:
+                works.append(dist.all_gather([g[lo:lo + n] for g in gathered], sig[-1], async_op=True))
         for w in works:
             w.wait()
+        if peer is not None:
+            torch.cuda.current_stream(dev).wait_stream(peer.side)       # the group barrier is the timed region's own
         if timed:
             adv_ms.append(evs)
         return sig
@@ -379,6 +394,7 @@ def run_b200(args):
         'gpu_launches': launches_timed,
         'gpu_launches_per_step': launches_timed / args.steps,
         'clocks': clocks,
+        'host_binding': numa,
         'roofline': {
             'bound': 'l1-gather',
             'bound_note': 'L1/L2 -> SM gather throughput (SURVEY 8(d)); not hbm (see roofline.hbm: <2 % of the measured copy '

@@ -62,13 +62,17 @@ def _pipeline(engine, in_shape, in_dtype, need_in):
 
 def rolling_ftle(u, v, lat, lon, window_levels, timestep, SETTLS_order=4, interp_order=3, xclamp='outer',
                  cyclic_xboundary=False, precision='f64', device='cuda:0', starts=None, chunk=148,
-                 log_scale=False, out=None, engine=None, return_device=False):
+                 log_scale=False, out=None, engine=None, return_device=False, on_chunk=None):
     """sigma_max fields for every start time of a wind series.
 
     ``u, v``: ``[nlev, nlat, nlon]`` (numpy, pinned or not, or device tensors).  Window ``s`` uses
     levels ``s .. s+window_levels-1`` exactly as ``LCS(...)(u.isel(time=slice(s, s+window_levels)))``
     would.  Returns ``[nstarts, nlat, nlon]`` (numpy unless ``return_device``; ``out`` = a pinned
     host tensor to fill).
+
+    ``on_chunk(first, fields)``: called with every finished chunk (device tensor ``[n, nlat, nlon]``, ``first`` = index
+    of its first window within this call) as soon as its kernels are queued -- the hook the multi-GPU driver uses to
+    push chunks to its peers while the next chunk runs.
 
     Start times are processed in chunks of ``chunk`` windows (148 = one cluster pair per SM for the
     outer-clamp kernel).  With host-resident winds the chunks are pipelined over three streams:
@@ -118,6 +122,8 @@ def rolling_ftle(u, v, lat, lon, window_levels, timestep, SETTLS_order=4, interp
             if not on_device:
                 pipe['in_free'][i % 2] = main.record_event()     # the integrator's pole rows read the raw levels too
             sig = engine.epilogue(x, y, log_scale=log_scale)
+            if on_chunk is not None:
+                on_chunk(s, sig)
             if to_host:
                 down.wait_event(main.record_event())
                 with torch.cuda.stream(down):
@@ -175,17 +181,32 @@ def band_ftle(engine, staged, world_size, rank, nsteps=None, nwindows=1, level0=
 
 
 # ------------------------------------------------------------------ sharded drivers (one process per GPU)
-def rolling_ftle_sharded(u, v, lat, lon, window_levels, timestep, group=None, dst=None, **kw):
+def rolling_ftle_sharded(u, v, lat, lon, window_levels, timestep, group=None, dst=None, gather='nccl', **kw):
     """Start-time sharding of a rolling series over the ranks of ``group``: every rank integrates its contiguous
-    block of windows (staging only the levels that block touches) and the finished fields are gathered with one
-    collective.  ``kw`` as for :func:`rolling_ftle`.  Returns ``[nstarts, nlat, nlon]`` on the device."""
+    block of windows (staging only the levels that block touches) and the finished fields are gathered on every rank:
+    ``gather='nccl'`` one all_gather at the end; ``gather='p2p'`` each finished chunk is pushed into every rank's
+    symmetric-memory buffer over NVLink while the next chunk is integrated (``peer.PeerFields``: copy engines, no SM
+    taken from the integrator; CUDA + NCCL groups only).  ``kw`` as for :func:`rolling_ftle`.
+    Returns ``[nstarts, nlat, nlon]`` on the device."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     nstarts = u.shape[0] - window_levels + 1
     first, count = shard_starts(nstarts, world, rank)
+    counts = [shard_starts(nstarts, world, r)[1] for r in range(world)]
     kw.pop('return_device', None)
+    if gather == 'p2p':
+        from .peer import PeerFields
+        engine = kw.get('engine')
+        device = engine.device if engine is not None else kw.get('device', 'cuda:0')
+        peer = PeerFields(counts, len(lat), len(lon), group=group, device=device)
+        rolling_ftle(u, v, lat, lon, window_levels, timestep, starts=(first, count), return_device=True,
+                     on_chunk=peer.push, **kw)
+        peer.finish()
+        return peer.result()
+    if gather != 'nccl':
+        raise ValueError("gather must be 'nccl' or 'p2p'")
     mine = rolling_ftle(u, v, lat, lon, window_levels, timestep, starts=(first, count), return_device=True, **kw)
-    return gather_fields(mine, [shard_starts(nstarts, world, r)[1] for r in range(world)], group=group, dst=dst)
+    return gather_fields(mine, counts, group=group, dst=dst)
 
 
 def ftle_row_bands(engine, u, v, group=None, log_scale=False):

@@ -14,7 +14,7 @@ from lagrangiancoherence_b200.engine import FtleEngine
 from lagrangiancoherence_b200.rolling import band_ftle, gather_bands
 
 ap = argparse.ArgumentParser()
-ap.add_argument('--nt', type=int, default=25)       # 24 hourly intervals (72 h = 73 levels in the config; shortened by default)
+ap.add_argument("--nt", type=int, default=73)       # BASELINE configs[2]: 72 h of hourly winds = 73 levels
 ap.add_argument('--steps', type=int, default=10)
 ap.add_argument('--warmup', type=int, default=3)
 a = ap.parse_args()

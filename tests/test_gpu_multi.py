@@ -1,5 +1,6 @@
 """Two-rank NCCL run of the sharded paths on real GPUs (skipped on a single-GPU box): start-time sharding of a
-rolling series and row-band sharding of one field, gathered with NCCL, against the single-GPU result."""
+rolling series (gathered with NCCL and with NVLink peer copies) and row-band sharding of one field, against the
+single-GPU result."""
 import os
 import socket
 
@@ -32,6 +33,8 @@ def _worker(rank, world, port, q):
     # start-time sharding, outer clamp
     eng = FtleEngine(lat, lon, -21600, SETTLS_order=4, xmode='outer', device=dev)
     allf = rolling_ftle_sharded(u, v, lat, lon, nt, -21600, engine=eng)
+    # same shards, finished chunks pushed into every rank's symmetric-memory buffer over NVLink (ragged: 4 + 3 windows)
+    allp = rolling_ftle_sharded(u, v, lat, lon, nt, -21600, engine=eng, gather='p2p', chunk=2).clone()
     # row bands, pointwise clamp
     engp = FtleEngine(lat, lon, -21600, SETTLS_order=4, xmode='pointwise', device=dev)
     st = engp.stage(u[:nt], v[:nt])
@@ -40,7 +43,9 @@ def _worker(rank, world, port, q):
         ref_all = rolling_ftle(u, v, lat, lon, nt, -21600, engine=eng, return_device=True)
         x, y = engp.advect(st)
         ref_full = engp.epilogue(x, y)[0]
-        q.put((bool(torch.equal(allf, ref_all)), bool(torch.equal(full, ref_full))))
+        q.put((bool(torch.equal(allf, ref_all)) and bool(torch.equal(allp, ref_all)), bool(torch.equal(full, ref_full))))
+    else:
+        assert torch.equal(allp, allf)                       # every rank holds the whole series either way
     dist.barrier()
     dist.destroy_process_group()
 

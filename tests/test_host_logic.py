@@ -128,3 +128,16 @@ def test_dropna_unstack_removes_fully_dropped_rows_and_columns():
     out, la, lo = drop_unused_levels(s, lat, lon)
     assert out.shape == (4, 5) and np.array_equal(la, [0, 1, 2, 4]) and np.array_equal(lo, [1, 2, 3, 4, 5])
     assert np.isnan(out[1, 1]) and np.isnan(out).sum() == 1
+
+
+def test_numa_binding_helper_is_best_effort():
+    """affinity.bind_host_to_gpu: parses sysfs cpulists, and is a silent no-op where NVML / sysfs give no answer
+    (this container has no GPU)."""
+    from lagrangiancoherence_b200 import affinity
+    assert affinity._parse_cpulist('0-3,8,10-11\n') == {0, 1, 2, 3, 8, 10, 11}
+    assert affinity._parse_cpulist('') == set()
+    before = os.sched_getaffinity(0)
+    res = affinity.bind_host_to_gpu(0)
+    assert res is None or set(res) == {'node', 'cpus'}
+    if res is None:
+        assert os.sched_getaffinity(0) == before
