@@ -42,6 +42,26 @@ def chunk_starts(first, count, chunk):
     return [(s, min(chunk, first + count - s)) for s in range(first, first + count, chunk)]
 
 
+def chunk_schedule(count, chunk):
+    """Launch sizes of the pipelined host path: ``chunk`` windows first and last -- the first upload and the last
+    download cannot overlap anything, so they should be short -- and ``2*chunk`` in between, where the copies hide
+    behind the kernels and bigger launches are cheaper per window (with ``chunk`` = 148 = one two-CTA cluster per SM
+    pair, the middle launches are whole waves of single-CTA windows: 61 instead of 64 us per C2 window).
+    Returns ``[(first, n), ...]`` covering ``0 .. count``."""
+    if count <= 3 * chunk:
+        return chunk_starts(0, count, chunk)
+    sizes, rem = [chunk], count - chunk
+    while rem > 3 * chunk:
+        sizes.append(2 * chunk)
+        rem -= 2 * chunk
+    sizes += [rem - chunk, chunk] if rem > chunk else [rem]
+    out, s = [], 0
+    for n in sizes:
+        out.append((s, n))
+        s += n
+    return out
+
+
 # ------------------------------------------------------------------ single-GPU rolling series
 def _pipeline(engine, in_shape, in_dtype, need_in):
     """Copy streams and double-buffered device staging for host-resident winds, cached on the engine
@@ -76,7 +96,8 @@ def rolling_ftle(u, v, lat, lon, window_levels, timestep, SETTLS_order=4, interp
 
     Start times are processed in chunks of ``chunk`` windows (148 = one cluster pair per SM for the
     outer-clamp kernel).  With host-resident winds the chunks are pipelined over three streams:
-    upload of chunk i+1's levels and download of chunk i-1's fields overlap chunk i's kernels.
+    upload of chunk i+1's levels and download of chunk i-1's fields overlap chunk i's kernels; the
+    middle chunks are twice as long as the first and the last (``chunk_schedule``).
     """
     lat = np.asarray(lat, dtype=np.float64)
     lon = np.asarray(lon, dtype=np.float64)
@@ -100,10 +121,10 @@ def rolling_ftle(u, v, lat, lon, window_levels, timestep, SETTLS_order=4, interp
     if to_host and own_out:
         out = torch.empty((count, lat.size, lon.size), dtype=torch.float64).pin_memory()
     sigma = None if to_host else torch.empty((count, lat.size, lon.size), dtype=torch.float64, device=dev)
-    chunks = chunk_starts(0, count, chunk)
+    chunks = chunk_starts(0, count, chunk) if on_device else chunk_schedule(count, chunk)
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream(dev)
-        pipe = _pipeline(engine, (min(chunk, count) + nsteps,) + tuple(u.shape[1:]), u.dtype, need_in=not on_device)
+        pipe = _pipeline(engine, (max(n for _, n in chunks) + nsteps,) + tuple(u.shape[1:]), u.dtype, need_in=not on_device)
         up, down = pipe['up'], pipe['down']
         for i, (s, n) in enumerate(chunks):
             lo, hi = first + s, first + s + n + nsteps          # levels this chunk touches

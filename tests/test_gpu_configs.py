@@ -71,6 +71,8 @@ def test_c4_rolling_equals_independent_windows(cuda_device):
         assert torch.equal(eng.epilogue(xs, ys)[0], fields[s])
     host = rolling_ftle(u, v, lat, lon, nt, -3600, engine=eng, chunk=24)       # pipelined host path
     assert np.array_equal(host, fields.cpu().numpy())
+    host = rolling_ftle(u, v, lat, lon, nt, -3600, engine=eng, chunk=8)        # ramped schedule 8, 16, 8, 8 windows
+    assert np.array_equal(host, fields.cpu().numpy())
 
 
 def test_c5_refined_particle_grid_trajectories(cuda_device):

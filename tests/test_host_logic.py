@@ -141,3 +141,15 @@ def test_numa_binding_helper_is_best_effort():
     assert res is None or set(res) == {'node', 'cpus'}
     if res is None:
         assert os.sched_getaffinity(0) == before
+
+
+def test_chunk_schedule_covers_the_series_with_short_ends():
+    from lagrangiancoherence_b200.rolling import chunk_schedule
+    assert chunk_schedule(1184, 148) == [(0, 148), (148, 296), (444, 296), (740, 296), (1036, 148)]
+    for count in (1, 7, 148, 149, 296, 443, 444, 445, 600, 1095, 8760):
+        for chunk in (24, 148):
+            sched = chunk_schedule(count, chunk)
+            assert sched[0][0] == 0 and sum(n for _, n in sched) == count
+            assert all(a + n == b for (a, n), (b, _) in zip(sched, sched[1:]))
+            assert all(0 < n <= 2 * chunk for _, n in sched)
+            assert sched[0][1] <= chunk and sched[-1][1] <= chunk
