@@ -226,9 +226,20 @@ def run_b200(args):
     gather_mode = os.environ.get('LCS_BENCH_GATHER', 'p2p')          # 'p2p' (NVLink peer copies) | 'nccl' (all_gather)
     gathered = peer = None
     if world > 1 and gather_mode == 'p2p':
-        from lagrangiancoherence_b200.peer import PeerFields
-        peer = PeerFields([B] * world, lat.size, lon.size, device=dev)
-    elif world > 1:
+        # symmetric memory needs CUDA VMM handle exchange between the ranks; where the box forbids it every rank
+        # falls back to the NCCL all_gather (agreed through an all_reduce so that no rank is left behind)
+        try:
+            from lagrangiancoherence_b200.peer import PeerFields
+            peer = PeerFields([B] * world, lat.size, lon.size, device=dev)
+        except Exception as exc:                                    # noqa: BLE001
+            sys.stderr.write(f'[bench] rank {rank}: peer gather unavailable ({exc!r}); using NCCL all_gather\n')
+            peer = None
+        agree = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+        if int(agree.item()) == 0:
+            peer, gather_mode = None, 'nccl'
+            os.environ['LCS_BENCH_GATHER'] = 'nccl'
+    if world > 1 and peer is None:
         gathered = [torch.empty((B, lat.size, lon.size), dtype=torch.float64, device=dev) for _ in range(world)]
     x = torch.empty((B, lat.size, lon.size), dtype=torch.float64, device=dev)
     y = torch.empty_like(x)

@@ -196,9 +196,11 @@ int lcs_spectral_norm_3x3(const double* vals, int64_t n, double* out, void* stre
  * (inf, NaN -> 0), eigen-decompose [[hxx, hxy], [hxy, hyy]] with LAPACK's dgeev/dlanv2 conventions (order of the
  * eigenvalues, signs of the eigenvectors), dt = dot(ROW argmin(eigvals) of the eigenvector matrix, gradient) as
  * executed upstream, eigmin = eigenvalue of largest magnitude, dt_prod = 1 where not(|dt| > tolerance) and
- * eigmin < 0 else 0.  All arrays: device f64 [n]. */
+ * eigmin < 0 else 0.  Optional (NULL to skip) diagnostics of return_eigvectors=True (tools.py:148-152): dt_raw = the
+ * unthresholded dt, evec0/evec1 = the two entries of that eigenvector row.  All arrays: device f64 [n]. */
 int lcs_ridge_classify(const double* hxx, const double* hxy, const double* hyy, const double* gx, const double* gy,
-                       int64_t n, double tolerance, double* dt_prod, double* eigmin, void* stream);
+                       int64_t n, double tolerance, double* dt_prod, double* eigmin,
+                       double* dt_raw, double* evec0, double* evec1, void* stream);
 
 /* ---------------------------------------------------------------- roofline microbenchmark
  * Same taps x taps vector-gather pattern and thread tiling as the integrator with nothing else in the

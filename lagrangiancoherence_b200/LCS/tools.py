@@ -72,10 +72,10 @@ def find_ridges_spherical_hessian(da, sigma=.5, scheme='first_order', tolerance_
     Gaussian smoothing on the (longitude, latitude) transpose, five stencil passes that each re-cast to f32, the
     Hessian's inf/NaN zeroed, and a per-point 2x2 eigen-decomposition whose eigenvector ROW (sic, tools.py:108) is
     dotted with the gradient.  Returns ``(dt_prod, eigmin)`` in the input's dimension order; ``scheme`` is accepted
-    and ignored, as upstream.  ``return_eigvectors=True`` (four more diagnostic arrays) is not implemented."""
+    and ignored, as upstream.  ``return_eigvectors=True`` returns the six arrays of tools.py:148-152:
+    ``dt_prod, eigmin, dt_prod_`` (the unthresholded dot product), ``eigvectors`` (dim ``eigvectors``; zero where
+    eigmin >= 0), ``gradient`` (dim ``elements``) and ``angle = 180/pi * arctan(e0/e1)``."""
     import torch
-    if return_eigvectors:
-        raise NotImplementedError('return_eigvectors=True is not implemented')
     dims_in = tuple(da.dims)
     d2 = da.sortby('latitude').sortby('longitude').transpose('latitude', 'longitude')
     lat, lon = coord_values(d2, 'latitude'), coord_values(d2, 'longitude')
@@ -91,13 +91,32 @@ def find_ridges_spherical_hessian(da, sigma=.5, scheme='first_order', tolerance_
         d2y2 = _dsc_device(ddady, lat, lon, 0, isglobal, dev)
         d2xy = _dsc_device(ddadx, lat, lon, 0, isglobal, dev)
         dt_prod, eigmin = torch.empty_like(f), torch.empty_like(f)
+        dt_raw = ev0 = ev1 = None
+        if return_eigvectors:
+            dt_raw, ev0, ev1 = torch.empty_like(f), torch.empty_like(f), torch.empty_like(f)
         lib = _engine._lib.load()
+        ddadx, ddady = ddadx.contiguous(), ddady.contiguous()
         _engine._lib.check(lib.lcs_ridge_classify(*[_engine._ptr(t.contiguous()) for t in (d2x2, d2xy, d2y2, ddadx, ddady)],
                                                   f.numel(), float(tolerance_threshold), _engine._ptr(dt_prod),
-                                                  _engine._ptr(eigmin), _engine._stream(dev)), 'lcs_ridge_classify')
+                                                  _engine._ptr(eigmin), _engine._ptr(dt_raw), _engine._ptr(ev0),
+                                                  _engine._ptr(ev1), _engine._stream(dev)), 'lcs_ridge_classify')
     coords = {'latitude': lat, 'longitude': lon}
     out = []
     for t in (dt_prod, eigmin):
         r = make_like(da, t.cpu().numpy(), ('latitude', 'longitude'), coords)
         out.append(r.transpose(*dims_in))
+    if not return_eigvectors:
+        return tuple(out)
+    out.append(make_like(da, dt_raw.cpu().numpy(), ('latitude', 'longitude'), coords).transpose(*dims_in))   # dt_prod_, :129
+    e0, e1, em = ev0.cpu().numpy(), ev1.cpu().numpy(), eigmin.cpu().numpy()
+    with np.errstate(all='ignore'):
+        angle = 180 / np.pi * np.arctan(e0 / e1)                                      # tools.py:125 (before the zeroing)
+    evec = np.where(em < 0, np.stack([e0, e1]), 0.0)                                  # tools.py:132
+    # labels as upstream leaves them: isel(elements=[1, 2]) of the Hessian renamed to 'eigvectors' (tools.py:123-124)
+    ecoords = dict(coords, eigvectors=np.array(['d2dadxdy', 'd2dadydx']))
+    out.append(make_like(da, evec, ('eigvectors', 'latitude', 'longitude'), ecoords).transpose('eigvectors', *dims_in))
+    gcoords = dict(coords, elements=np.array(['ddadx', 'ddady']))
+    grad = np.stack([ddadx.cpu().numpy(), ddady.cpu().numpy()])
+    out.append(make_like(da, grad, ('elements', 'latitude', 'longitude'), gcoords).transpose('elements', *dims_in))
+    out.append(make_like(da, angle, ('latitude', 'longitude'), coords).transpose(*dims_in))
     return tuple(out)

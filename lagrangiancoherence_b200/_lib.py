@@ -63,7 +63,8 @@ SIGNATURES = {
                                     c_int, c_int, c_void_p, c_void_p]),
     'lcs_fourth_order_derivative': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'lcs_spectral_norm_3x3': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
-    'lcs_ridge_classify': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p, c_void_p]),
+    'lcs_ridge_classify': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p,
+                                   c_void_p, c_void_p, c_void_p, c_void_p]),
     'lcs_gather_peak': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int,
                                 c_void_p, c_void_p]),
 }

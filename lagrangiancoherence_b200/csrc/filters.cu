@@ -107,7 +107,8 @@ __device__ __forceinline__ double clean_hess(double h) { return (isinf(h) || isn
 __global__ void __launch_bounds__(256)
 ridge_classify_kernel(const double* __restrict__ hxx, const double* __restrict__ hxy, const double* __restrict__ hyy,
                       const double* __restrict__ gx, const double* __restrict__ gy, long long n, double tol,
-                      double* __restrict__ dt_prod, double* __restrict__ eigmin) {
+                      double* __restrict__ dt_prod, double* __restrict__ eigmin,
+                      double* __restrict__ dt_raw, double* __restrict__ evec0, double* __restrict__ evec1) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double a = clean_hess(hxx[i]), b = clean_hess(hxy[i]), d = clean_hess(hyy[i]);
@@ -130,18 +131,21 @@ ridge_classify_kernel(const double* __restrict__ hxx, const double* __restrict__
     const double em = (fabs(rt1) >= fabs(rt2)) ? rt1 : rt2;                                  // tools.py:119
     eigmin[i] = em;
     dt_prod[i] = (!(fabs(dt) > tol) && em < 0.0) ? 1.0 : 0.0;                                 // tools.py:134-136
+    if (dt_raw) dt_raw[i] = dt;                                                               // dt_prod_, tools.py:129
+    if (evec0) { evec0[i] = r0; evec1[i] = r1; }                                              // the row taken at :108
 }
 
 }  // namespace lcs
 
 extern "C" int lcs_ridge_classify(const double* hxx, const double* hxy, const double* hyy, const double* gx,
                                   const double* gy, int64_t n, double tolerance, double* dt_prod, double* eigmin,
-                                  void* stream) {
+                                  double* dt_raw, double* evec0, double* evec1, void* stream) {
     if (!hxx || !hxy || !hyy || !gx || !gy || !dt_prod || !eigmin) return lcs_fail(LCS_E_INVALID, "lcs_ridge_classify: null argument");
     if (n < 0) return lcs_fail(LCS_E_INVALID, "lcs_ridge_classify: negative n");
+    if ((evec0 == nullptr) != (evec1 == nullptr)) return lcs_fail(LCS_E_INVALID, "lcs_ridge_classify: evec0/evec1 must both be set");
     if (n == 0) return LCS_OK;
     lcs::ridge_classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        hxx, hxy, hyy, gx, gy, n, tolerance, dt_prod, eigmin);
+        hxx, hxy, hyy, gx, gy, n, tolerance, dt_prod, eigmin, dt_raw, evec0, evec1);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_ridge_classify");
     lcs_count_launches(1);

@@ -312,8 +312,12 @@ def subdomain_mask(lat, lon, subdomain):
 # --------------------------------------------------------------------------------------
 # find_ridges_spherical_hessian (tools.py:52-155)
 # --------------------------------------------------------------------------------------
-def find_ridges_spherical_hessian(field, lat, lon, sigma=.5, tolerance_threshold=0.0005e-3, isglobal=True):
-    """Hessian ridge filter of an FTLE field ``(nlat, nlon)``; returns ``(dt_prod, eigmin)``.
+def find_ridges_spherical_hessian(field, lat, lon, sigma=.5, tolerance_threshold=0.0005e-3, isglobal=True,
+                                  return_eigvectors=False):
+    """Hessian ridge filter of an FTLE field ``(nlat, nlon)``; returns ``(dt_prod, eigmin)``, or with
+    ``return_eigvectors`` the six arrays of tools.py:148-152: ``dt_prod, eigmin, dt (unthresholded), eigvectors
+    [2, nlat, nlon] (zeroed where eigmin >= 0, :132), gradient [2, nlat, nlon], angle = 180/pi*arctan(e0/e1)`` (:125,
+    from the eigenvectors BEFORE the zeroing).
 
     As executed: Gaussian smoothing on the (longitude, latitude) transpose (tools.py:70-76), five
     derivative_spherical_coords passes, each re-casting its input to f32 (:78-82), inf/NaN of the Hessian set to 0
@@ -336,10 +340,17 @@ def find_ridges_spherical_hessian(field, lat, lon, sigma=.5, tolerance_threshold
     w, v = np.linalg.eig(H)                                                             # :107, one LAPACK call per point
     n = np.arange(H.shape[0])
     row = v[n, np.argmin(w, axis=1)]                                                    # :108 (a row, not a column)
-    dt = row[:, 0] * grad[0] + row[:, 1] * grad[1]                                      # :116 np.dot of two 2-vectors
+    gT = np.ascontiguousarray(grad.T)
+    dt = np.array([np.dot(row[i], gT[i]) for i in range(row.shape[0])])                # :116 np.dot of two 2-vectors (BLAS ddot: fused)
     eigmin = w[n, np.argmax(np.abs(w), axis=1)]                                         # :119
     dt_prod = np.where(np.abs(dt) > tolerance_threshold, 0.0, 1.0)                      # :134-135 (NaN -> 1)
     dt_prod = np.where(np.sign(eigmin) == -1, dt_prod, 0.0)                             # :136
+    if return_eigvectors:
+        with np.errstate(all='ignore'):
+            angle = 180 / np.pi * np.arctan(row[:, 0] / row[:, 1])                      # :125
+        evec = np.where(eigmin < 0, row.T, 0.0)                                         # :132
+        return (dt_prod.reshape(f.shape), eigmin.reshape(f.shape), dt.reshape(f.shape),
+                evec.reshape((2,) + f.shape), grad.reshape((2,) + f.shape), angle.reshape(f.shape))
     return dt_prod.reshape(f.shape), eigmin.reshape(f.shape)
 
 

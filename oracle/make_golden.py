@@ -180,6 +180,11 @@ def main():
     fda = xr.DataArray(ftle, {'latitude': lat, 'longitude': lon}, ('latitude', 'longitude'))
     ridges, eigmin = ref_tools.find_ridges_spherical_hessian(fda, sigma=1.2, tolerance_threshold=0.002e-3)
     seams['ridge_input'], seams['ridge_dt_prod'], seams['ridge_eigmin'] = ftle, ridges.values, eigmin.values
+    six = ref_tools.find_ridges_spherical_hessian(fda, sigma=1.2, tolerance_threshold=0.002e-3, return_eigvectors=True)
+    assert np.array_equal(six[0].values, ridges.values) and np.array_equal(six[1].values, eigmin.values)
+    seams['ridge_dt_raw'], seams['ridge_eigvectors'] = six[2].values, six[3].values            # tools.py:148-152
+    seams['ridge_gradient'], seams['ridge_angle'] = six[4].values, six[5].values
+    assert six[3].dims == ('eigvectors', 'latitude', 'longitude') and six[4].dims == ('elements', 'latitude', 'longitude')
     seams['subdomain_sigma'] = eig.values
     seams['subdomain_lat'], seams['subdomain_lon'] = eig.coords['latitude'], eig.coords['longitude']
     np.savez_compressed(os.path.join(GOLDEN, 'seams.npz'), **seams)

@@ -221,7 +221,12 @@ class DataArray:
         m = dict(mapping or {}, **kw)
         dims = tuple(m.get(d, d) for d in self.dims)
         coords = {m.get(k, k): v for k, v in self.coords.items()}
-        return DataArray(self.values, coords, dims, self.name, self.attrs)
+        out = DataArray(self.values, coords, dims, self.name, self.attrs)
+        if self._stack is not None:                    # renaming another dimension keeps the stacked index (tools.py:123)
+            new, (a, b) = self._stack
+            if not {new, a, b} & set(m):
+                out._stack = self._stack
+        return out
 
     # ------------------------------------------------------------- resample(...).interpolate('linear')  (LCS.py:89-90)
     def resample(self, indexer=None, **kw):

@@ -110,6 +110,11 @@ def test_ridge_filter_reproduces_reference_bitwise():
     _, _, lat, lon, _ = make_inputs(CASES['regional_outer_p3'])
     dt_prod, eigmin = O.find_ridges_spherical_hessian(g['ridge_input'], lat, lon, sigma=1.2, tolerance_threshold=0.002e-3)
     assert np.array_equal(dt_prod, g['ridge_dt_prod']) and np.array_equal(eigmin, g['ridge_eigmin'])
+    six = O.find_ridges_spherical_hessian(g['ridge_input'], lat, lon, sigma=1.2, tolerance_threshold=0.002e-3,
+                                          return_eigvectors=True)                       # tools.py:148-152
+    for got, key in zip(six, ('ridge_dt_prod', 'ridge_eigmin', 'ridge_dt_raw', 'ridge_eigvectors', 'ridge_gradient',
+                              'ridge_angle')):
+        assert np.array_equal(got, g[key], equal_nan=True), key
     assert 0.02 < dt_prod.mean() < 0.98                           # a non-trivial mask
 
 
