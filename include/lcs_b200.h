@@ -132,6 +132,19 @@ int lcs_pack_es(const void* u, const void* v, int in_dtype, void* e_out, void* s
 int lcs_time_lerp(const void* in, int in_dtype, const int32_t* lo, const double* w_hi, const double* w_lo,
                   int nnew, int64_t plane, double* out, void* stream);
 
+/* lcs_regrid_linear_nearest: the regrid of the global path, LCS.py:105-114: `u.interp(latitude=, longitude=,
+ * method='linear')` with its NaNs (targets outside the source coordinates) filled from `u.reindex(..., method='nearest')`.
+ * Per axis the host supplies, for every target coordinate, the bracket `lo`, the weights of scipy's interp1d
+ * (new = w_hi*y[lo+1] + w_lo*y[lo]), `valid` (inside the source range) and the `nearest` source index
+ * (lagrangiancoherence_b200/regrid.py).  in: device [nlev][nlat_src][nlon_src] of in_dtype; out: device f64
+ * [nlev][nlat_dst][nlon_dst]; plan arrays: device, length nlat_dst / nlon_dst. */
+int lcs_regrid_linear_nearest(const void* in, int in_dtype, int nlev, int nlat_src, int nlon_src,
+                              const int32_t* lat_lo, const double* lat_w_hi, const double* lat_w_lo,
+                              const uint8_t* lat_valid, const int32_t* lat_nearest,
+                              const int32_t* lon_lo, const double* lon_w_hi, const double* lon_w_lo,
+                              const uint8_t* lon_valid, const int32_t* lon_nearest,
+                              int nlat_dst, int nlon_dst, double* out, void* stream);
+
 /* ---------------------------------------------------------------- integrator
  * lcs_advect replaces parcel_propagation's loop, trajectory.py:80-126, together with the
  * xr_map_coordinates calls inside it (tools.py:11-41).

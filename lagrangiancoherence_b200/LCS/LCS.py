@@ -65,11 +65,13 @@ class LCS:
         assert set(u.dims) == {'latitude', 'longitude', timedim}, \
             'array dims should be latitude and longitude only'                               # LCS.py:96
         if isglobal:                                                 # LCS.py:105-120
-            if interp_to_common_grid or truncation is not None:
+            if truncation is not None:
                 raise NotImplementedError(
-                    'isglobal=True with interp_to_common_grid/truncation needs the 360x721 regrid and a T20 '
-                    'spherical-harmonic truncation (windspharm upstream); pass interp_to_common_grid=False, '
-                    'truncation=None to run the cyclic path on the native grid')
+                    'isglobal=True with truncation needs a spherical-harmonic truncation of the winds (windspharm / '
+                    'SPHEREPACK upstream, LCS.py:115-118), which has no counterpart here; pass truncation=None '
+                    '(the 360x721 regrid of interp_to_common_grid=True is supported)')
+            if interp_to_common_grid:                                # LCS.py:106-114
+                u, v = (_to_common_grid(a, timedim, device) for a in (u, v))
             cyclic_xboundary = True
             self.subdomain = None
         else:
@@ -129,6 +131,18 @@ class LCS:
         elif return_traj:
             return eigenvalues, x_trajs, y_trajs
         return eigenvalues
+
+
+def _to_common_grid(da, timedim, device):
+    """LCS.py:101-114 for one component: sort, then ``interp(linear)`` to the 360 x 721 grid with the NaNs filled from
+    ``reindex(nearest)`` -- one device kernel (engine.regrid_device)."""
+    from ..engine import regrid_device
+    from ..regrid import common_grid
+    d = da.sortby('latitude').sortby('longitude').transpose(timedim, 'latitude', 'longitude')
+    lats, lons = common_grid()
+    out = regrid_device(d.values, coord_values(d, 'latitude'), coord_values(d, 'longitude'), lats, lons, device=device)
+    coords = {timedim: coord_values(d, timedim), 'latitude': lats, 'longitude': lons}
+    return make_like(da, out.cpu().numpy(), (timedim, 'latitude', 'longitude'), coords)
 
 
 def drop_unused_levels(sigma, lat, lon):

@@ -120,3 +120,17 @@ def find_ridges_spherical_hessian(da, sigma=.5, scheme='first_order', tolerance_
     out.append(make_like(da, grad, ('elements', 'latitude', 'longitude'), gcoords).transpose('elements', *dims_in))
     out.append(make_like(da, angle, ('latitude', 'longitude'), coords).transpose(*dims_in))
     return tuple(out)
+
+
+def latlonsel(array, lat, lon, latname='lat', lonname='lon'):
+    """Crop to the open intervals ``lat[0] < latitude < lat[-1]``, ``lon[0] < longitude < lon[-1]`` (slice or list), the
+    in-tree analogue of the ``xr_tools.latlonsel`` that LCS.py:143-144 calls (tools.py:158-188: two strict-inequality
+    masks applied with ``where(mask, drop=True)``).  Pure label selection, done on the host."""
+    assert latname in array.coords, f"Coord. {latname} not present in array"          # tools.py:168
+    assert lonname in array.coords, f"Coord. {lonname} not present in array"          # tools.py:169
+    lat1, lat2 = (lat.start, lat.stop) if isinstance(lat, slice) else (lat[0], lat[-1])
+    lon1, lon2 = (lon.start, lon.stop) if isinstance(lon, slice) else (lon[0], lon[-1])
+    lonv, latv = coord_values(array, lonname), coord_values(array, latname)
+    lonmask = (lonv < lon2) & (lonv > lon1)                                           # tools.py:184
+    latmask = (latv < lat2) & (latv > lat1)                                           # tools.py:185
+    return array.isel({lonname: np.flatnonzero(lonmask)}).isel({latname: np.flatnonzero(latmask)})

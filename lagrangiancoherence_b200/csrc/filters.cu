@@ -92,6 +92,66 @@ extern "C" int lcs_gaussian_filter2d(const double* in, double* out, double* scra
 }
 
 // ---------------------------------------------------------------------------------------------
+// Global-path regrid (LCS.py:105-114): linear interpolation along latitude, then along longitude, exactly as the two
+// successive scipy interp1d passes xarray makes (w_hi*y_hi + w_lo*y_lo, no fused multiply-add), NaN outside the source
+// range, and every NaN replaced by the nearest-label value (`u_interp.where(~isnan(u_interp), u_reindex)`).
+namespace lcs {
+struct AxisPlan { const int* lo; const double* w_hi; const double* w_lo; const unsigned char* valid; const int* nearest; };
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+regrid_kernel(const T* __restrict__ in, int nlev, int nlat_s, int nlon_s, AxisPlan py, AxisPlan px,
+              int nlat_d, int nlon_d, double* __restrict__ out) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long per = (long long)nlat_d * nlon_d;
+    if (idx >= per * nlev) return;
+    const int lev = (int)(idx / per);
+    const int rem = (int)(idx - (long long)lev * per);
+    const int j = rem / nlon_d, i = rem - j * nlon_d;
+    const T* f = in + (size_t)lev * nlat_s * nlon_s;
+    double r = nan("");
+    if (py.valid[j] && px.valid[i]) {
+        const int r0 = py.lo[j], c0 = px.lo[i];
+        const double wyh = py.w_hi[j], wyl = py.w_lo[j], wxh = px.w_hi[i], wxl = px.w_lo[i];
+        const T* a = f + (size_t)r0 * nlon_s + c0;
+        // pass 1 (latitude) at the two source longitudes, pass 2 (longitude) between them
+        const double t0 = __dadd_rn(__dmul_rn(wyh, (double)a[nlon_s]), __dmul_rn(wyl, (double)a[0]));
+        const double t1 = __dadd_rn(__dmul_rn(wyh, (double)a[nlon_s + 1]), __dmul_rn(wyl, (double)a[1]));
+        r = __dadd_rn(__dmul_rn(wxh, t1), __dmul_rn(wxl, t0));
+    }
+    if (isnan(r)) r = (double)f[(size_t)py.nearest[j] * nlon_s + px.nearest[i]];
+    out[idx] = r;
+}
+}  // namespace lcs
+
+extern "C" int lcs_regrid_linear_nearest(const void* in, int in_dtype, int nlev, int nlat_src, int nlon_src,
+                                         const int32_t* lat_lo, const double* lat_w_hi, const double* lat_w_lo,
+                                         const uint8_t* lat_valid, const int32_t* lat_nearest,
+                                         const int32_t* lon_lo, const double* lon_w_hi, const double* lon_w_lo,
+                                         const uint8_t* lon_valid, const int32_t* lon_nearest,
+                                         int nlat_dst, int nlon_dst, double* out, void* stream) {
+    if (!in || !out || !lat_lo || !lat_w_hi || !lat_w_lo || !lat_valid || !lat_nearest ||
+        !lon_lo || !lon_w_hi || !lon_w_lo || !lon_valid || !lon_nearest)
+        return lcs_fail(LCS_E_INVALID, "lcs_regrid_linear_nearest: null argument");
+    if (nlev < 1 || nlat_src < 2 || nlon_src < 2 || nlat_dst < 1 || nlon_dst < 1)
+        return lcs_fail(LCS_E_INVALID, "lcs_regrid_linear_nearest: bad sizes");
+    const long long n = (long long)nlev * nlat_dst * nlon_dst;
+    const lcs::AxisPlan py = {lat_lo, lat_w_hi, lat_w_lo, lat_valid, lat_nearest};
+    const lcs::AxisPlan px = {lon_lo, lon_w_hi, lon_w_lo, lon_valid, lon_nearest};
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned gb = (unsigned)((n + 255) / 256);
+    if (in_dtype == LCS_F64)
+        lcs::regrid_kernel<double><<<gb, 256, 0, st>>>((const double*)in, nlev, nlat_src, nlon_src, py, px, nlat_dst, nlon_dst, out);
+    else if (in_dtype == LCS_F32)
+        lcs::regrid_kernel<float><<<gb, 256, 0, st>>>((const float*)in, nlev, nlat_src, nlon_src, py, px, nlat_dst, nlon_dst, out);
+    else return lcs_fail(LCS_E_INVALID, "lcs_regrid_linear_nearest: bad in_dtype");
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_regrid_linear_nearest");
+    lcs_count_launches(1);
+    return LCS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Ridge classification of find_ridges_spherical_hessian (tools.py:93-136), one thread per point.
 // The reference loops np.linalg.eig over 2x2 Hessians (tools.py:105-121); LAPACK's dgeev reduces a
 // symmetric [[a,b],[b,d]] with dlanv2, which fixes both the ORDER of the eigenvalues (rt1 is the one

@@ -330,6 +330,27 @@ def map_coordinates_device(field, pos_x, pos_y, lat, lon, order=1, device='cuda:
     return out
 
 
+def regrid_device(series, lat, lon, new_lat, new_lon, device='cuda:0'):
+    """LCS.py:108-113 on the device: linear interpolation (latitude, then longitude) of ``[nlev, nlat, nlon]`` to the
+    new coordinates, NaNs (outside the source range) filled with the nearest-label value.  Returns an f64 tensor."""
+    from .regrid import axis_plan
+    lib = _lib.load()
+    device = torch.device(device)
+    a = np.asarray(series)
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)
+    with torch.cuda.device(device):
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        plans = []
+        for src, dst in ((lat, new_lat), (lon, new_lon)):
+            plans += [torch.from_numpy(np.ascontiguousarray(p)).to(device) for p in axis_plan(src, dst)]
+        out = torch.empty((t.shape[0], len(new_lat), len(new_lon)), dtype=torch.float64, device=device)
+        _lib.check(lib.lcs_regrid_linear_nearest(_ptr(t), _dtype_code(t), t.shape[0], t.shape[1], t.shape[2],
+                                                 *[_ptr(p) for p in plans], len(new_lat), len(new_lon), _ptr(out),
+                                                 _stream(device)), 'lcs_regrid_linear_nearest')
+    return out
+
+
 def prefilter_device(u, v, device='cuda:0', order=3):
     """B-spline coefficients (order 2..5) of ``[nlev, nlat, nlon]`` series (f64 tensors on the device)."""
     lib = _lib.load()

@@ -396,6 +396,27 @@ def resample_linear(U, times, freq):
 
 
 # --------------------------------------------------------------------------------------
+# SURVEY 8f rank 4 (the feasible half): the fixed common grid of the global path, LCS.py:105-114
+# --------------------------------------------------------------------------------------
+def regrid_to_common_grid(U, lat, lon):
+    """``u.interp(latitude=lats, longitude=lons, method='linear')`` with NaNs filled from
+    ``u.reindex(..., method='nearest')`` (LCS.py:106-113), through the third-party calls xarray makes: successive
+    ``scipy.interpolate.interp1d`` along latitude then longitude (xarray decomposes orthogonal linear interpolation
+    in indexer order) and ``pandas.Index.get_indexer(method='nearest')``.  Returns ``(U_new, lats, lons)``."""
+    from scipy.interpolate import interp1d
+    import pandas as pd
+    lats = np.linspace(-89.75, 89.75, 180 * 2)                                         # :106
+    lons = np.linspace(-180, 179.5, 360 * 2 + 1)                                       # :107
+    U = np.asarray(U)
+    near = U[:, pd.Index(lat).get_indexer(lats, method='nearest')][:, :, pd.Index(lon).get_indexer(lons, method='nearest')]
+    it = interp1d(np.asarray(lat, dtype=np.float64), U, kind='linear', axis=1, bounds_error=False, fill_value=np.nan,
+                  assume_sorted=True)(lats)
+    it = interp1d(np.asarray(lon, dtype=np.float64), it, kind='linear', axis=2, bounds_error=False, fill_value=np.nan,
+                  assume_sorted=True)(lons)
+    return np.where(~np.isnan(it), it, near), lats, lons                               # :112-113
+
+
+# --------------------------------------------------------------------------------------
 # a2: LCS.__call__ (LCS.py:48-168), regional path and the cheap isglobal/truncation=None path
 # --------------------------------------------------------------------------------------
 def lcs_field(U, V, lat, lon, timestep, SETTLS_order=0, traj_interp_order=3,

@@ -185,6 +185,25 @@ def main():
     seams['ridge_dt_raw'], seams['ridge_eigvectors'] = six[2].values, six[3].values            # tools.py:148-152
     seams['ridge_gradient'], seams['ridge_angle'] = six[4].values, six[5].values
     assert six[3].dims == ('eigvectors', 'latitude', 'longitude') and six[4].dims == ('elements', 'latitude', 'longitude')
+    # isglobal=True with the 360 x 721 regrid (LCS.py:105-114), truncation=None; coarse 2-degree
+    # vortex winds, so the target rows beyond +-88 degrees and the last longitudes take the nearest-label branch.
+    # The fields are stored on a stride-5 subgrid to keep the fixture small.
+    from lagrangiancoherence_b200 import synthetic as S
+    gu, gv, glat, glon = S.ideal_vortex(**S.vortex_config_subtropical)
+    gu, gv = gu[:4], gv[:4]
+    gt = (np.datetime64('2000-01-01T00') + np.arange(4) * np.timedelta64(6, 'h')).astype('datetime64[ns]')
+    gc = {'time': gt, 'latitude': glat, 'longitude': glon}
+    gdu = xr.DataArray(gu, gc, ('time', 'latitude', 'longitude'))
+    gdv = xr.DataArray(gv, gc, ('time', 'latitude', 'longitude'))
+    with contextlib.redirect_stdout(quiet):
+        geig, gxd, gyd = ref_lcs.LCS(timestep=-21600, timedim='time', SETTLS_order=2, return_dpts=True)(
+            u=gdu, v=gdv, verbose=False, isglobal=True, interp_to_common_grid=True, truncation=None)
+    lats, lons = np.linspace(-89.75, 89.75, 360), np.linspace(-180, 179.5, 721)
+    ur = gdu.interp(latitude=lats, longitude=lons, method='linear')
+    ur = ur.where(~xr.ufuncs.isnan(ur), gdu.reindex(latitude=lats, longitude=lons, method='nearest'))   # LCS.py:108-112
+    seams['regrid_u'] = ur.values[:, ::5, ::5]
+    seams['regrid_sigma'], seams['regrid_x_dep'], seams['regrid_y_dep'] = (a[..., ::5, ::5] for a in (geig.values, gxd.values, gyd.values))
+    seams['regrid_lat'], seams['regrid_lon'] = np.asarray(geig.coords['latitude']), np.asarray(geig.coords['longitude'])
     seams['subdomain_sigma'] = eig.values
     seams['subdomain_lat'], seams['subdomain_lon'] = eig.coords['latitude'], eig.coords['longitude']
     np.savez_compressed(os.path.join(GOLDEN, 'seams.npz'), **seams)

@@ -21,6 +21,7 @@ emulated xarray" (see oracle/__init__.py).
 from __future__ import annotations
 
 import numpy as np
+import pandas as pd
 
 __version__ = '0.0-refshim'
 
@@ -100,6 +101,36 @@ class DataArray:
         coords = {k: (v[idx] if k.startswith('_') else v) for k, v in self.coords.items()}
         out = DataArray(np.take(self.values, idx, axis=ax), coords, self.dims, self.name)
         out._stack = self._stack
+        return out
+
+    # ------------------------------------------------------------- reindex / interp (LCS.py:108-111, the global regrid)
+    def reindex(self, indexers=None, method=None, **kw):
+        """xarray: label lookup through pandas ``Index.get_indexer(target, method=...)``; with method='nearest' and no
+        tolerance every new label finds a source label (ties go to the larger one on an increasing index)."""
+        assert method == 'nearest', 'refshim: reindex is only implemented for method="nearest"'
+        out = self
+        for dim, target in dict(indexers or {}, **kw).items():
+            idx = pd.Index(out.coords[dim]).get_indexer(np.asarray(target), method='nearest')
+            out = out.isel({dim: idx})
+            out.coords[dim] = np.asarray(target)
+        return out
+
+    def interp(self, coords=None, method='linear', assume_sorted=False, **kw):
+        """xarray: orthogonal linear interpolation over several dimensions is decomposed into successive 1-D
+        interpolations in the order the indexers are given (xarray.core.missing.decompose_interp), each one
+        ``scipy.interpolate.interp1d(x, y, kind='linear', axis=..., bounds_error=False, fill_value=nan)``."""
+        from scipy.interpolate import interp1d
+        assert method == 'linear', 'refshim: interp is only implemented for method="linear"'
+        out = self
+        for dim, target in dict(coords or {}, **kw).items():
+            if not assume_sorted:
+                out = out.sortby(dim)
+            ax = out.dims.index(dim)
+            x = np.asarray(out.coords[dim], dtype=np.float64)
+            f = interp1d(x, out.values, kind='linear', axis=ax, bounds_error=False, fill_value=np.nan, assume_sorted=True)
+            newc = dict(out.coords)
+            newc[dim] = np.asarray(target)
+            out = DataArray(f(np.asarray(target, dtype=np.float64)), newc, out.dims, out.name, out.attrs)
         return out
 
     def _new(self, values, dims=None, coords=None):

@@ -153,3 +153,18 @@ def test_chunk_schedule_covers_the_series_with_short_ends():
             assert all(a + n == b for (a, n), (b, _) in zip(sched, sched[1:]))
             assert all(0 < n <= 2 * chunk for _, n in sched)
             assert sched[0][1] <= chunk and sched[-1][1] <= chunk
+
+
+def test_latlonsel_strict_open_intervals():
+    """tools.py:158-188: both bounds are strict, slices and lists are accepted, either coordinate name works."""
+    from lagrangiancoherence_b200 import DataArray
+    from lagrangiancoherence_b200.LCS.tools import latlonsel
+    lat, lon = np.arange(-4.0, 5.0), np.arange(10.0, 20.0)
+    da = DataArray(np.arange(90.0).reshape(9, 10), ('lat', 'lon'), {'lat': lat, 'lon': lon})
+    out = latlonsel(da, slice(-2, 2), [12, 15])
+    assert np.array_equal(out.coords['lat'], [-1, 0, 1]) and np.array_equal(out.coords['lon'], [13, 14])
+    assert np.array_equal(out.values, da.values[3:6, 3:5])
+    da2 = DataArray(da.values, ('latitude', 'longitude'), {'latitude': lat, 'longitude': lon})
+    assert latlonsel(da2, slice(-2, 2), slice(12, 15), latname='latitude', lonname='longitude').shape == (3, 2)
+    with pytest.raises(AssertionError):
+        latlonsel(da2, slice(-2, 2), slice(12, 15))

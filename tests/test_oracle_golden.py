@@ -9,6 +9,7 @@ import pytest
 
 from oracle import lcs_oracle as O
 from oracle.make_golden import CASES, make_inputs
+from lagrangiancoherence_b200 import synthetic as S
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
@@ -133,3 +134,18 @@ def test_lapack_2x2_conventions_closed_form():
     assert np.array_equal(w[:, 0], rt1) and np.array_equal(w[:, 1], rt2)
     for got, ref in ((v[:, 0, 0], cs), (v[:, 1, 0], sn), (v[:, 0, 1], -sn), (v[:, 1, 1], cs)):
         assert np.abs(got - ref).max() <= 2.3e-16
+
+
+def test_global_regrid_path_reproduces_reference_bitwise():
+    """SURVEY 8f rank 4 (feasible half): LCS(...)(isglobal=True, interp_to_common_grid=True, truncation=None) through the
+    unmodified reference (LCS.py:105-114: interp(linear) + reindex(nearest) fill to the 360 x 721 grid, cyclic
+    boundary); fixture on a stride-5 subgrid."""
+    g = load('seams')
+    u, v, lat, lon = S.ideal_vortex(**S.vortex_config_subtropical)
+    U, lats, lons = O.regrid_to_common_grid(u[:4], lat, lon)
+    V, _, _ = O.regrid_to_common_grid(v[:4], lat, lon)
+    assert np.array_equal(lats, g['regrid_lat']) and np.array_equal(lons, g['regrid_lon'])
+    assert np.array_equal(U[:, ::5, ::5], g['regrid_u'])
+    sig, xd, yd = O.lcs_field(U, V, lats, lons, -21600, SETTLS_order=2, cyclic_xboundary=True, return_dpts=True)
+    assert np.array_equal(sig[::5, ::5], g['regrid_sigma'][0], equal_nan=True)
+    assert np.array_equal(xd[::5, ::5], g['regrid_x_dep']) and np.array_equal(yd[::5, ::5], g['regrid_y_dep'])
