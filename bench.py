@@ -35,15 +35,19 @@ DT = -21600
 METRIC = 'particle-steps/s'
 
 
+DEFAULT_BATCH = {'C2': 1184, 'C4': 1184, 'C3': 8}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=1184,
-                    help='start times per step and per GPU: 1184 = 8 windows per SM = one GPU\'s share (1095) of a year of '
-                         'hourly start times sharded 8-way (BASELINE configs[3]) rounded up to whole waves of 296')
+    ap.add_argument('--batch', type=int, default=None,
+                    help='start times per step and per GPU.  Default for C2/C4: 1184 = 8 windows per SM = one GPU\'s share '
+                         '(1095) of a year of hourly start times sharded 8-way (BASELINE configs[3]) rounded up to whole waves '
+                         'of 296; for C3 (1 M particles per window): 8')
     ap.add_argument('--xclamp', default='outer', choices=['outer', 'pointwise'],
                     help="x-boundary: 'outer' = what the reference executes (quirk Q6)")
     ap.add_argument('--order', type=int, default=3, choices=[1, 3])
@@ -53,7 +57,10 @@ def parse():
     ap.add_argument('--workload', default='C2', choices=['C2', 'C3', 'C4'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--chunk', type=int, default=148, help='windows per launch in the pipelined end-to-end path')
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.batch is None:
+        args.batch = DEFAULT_BATCH[args.workload]
+    return args
 
 
 def workload(name):
@@ -65,7 +72,7 @@ def workload(name):
         lat, lon = S.grid_c2()
         return lat, lon, 49, -3600, 'C4 rolling series on the C2 grid 281x321, hourly, 48 h backward (nt=49)'
     lat, lon = S.grid_c3()
-    return lat, lon, 13, -3600, 'C3 near-global 0.25deg 721x1440, hourly, 12 h backward (nt=13)'
+    return lat, lon, 73, -3600, 'C3 near-global 0.25deg 721x1440, hourly, 72 h backward (nt=73)'
 
 
 def config_dict(args, desc, B, world):
@@ -131,10 +138,17 @@ def _oracle_window(job):
     from oracle import lcs_oracle as O
     from lagrangiancoherence_b200 import synthetic as S
     lat, lon, nt, dt, _ = workload(name)
+    nt = cpu_levels(name, nt)
     u, v = S.era5_like_winds(lat, lon, nt, t0=s)
     t = time.perf_counter()
     O.lcs_field(u, v, lat, lon, dt, SETTLS_order=S_ORDER, traj_interp_order=order, xclamp=xclamp)
     return time.perf_counter() - t
+
+
+def cpu_levels(name, nt):
+    """Wind levels of one CPU sample window: the whole window, except on C3 where one 73-level window of 1 M particles
+    is minutes of scipy time per core -- there the sample is the first 2 intervals (cost is linear in the intervals)."""
+    return min(nt, 3) if name == 'C3' else nt
 
 
 def cpu_pool_run(name, order, xclamp, cores, nwindows, first=0):
@@ -157,7 +171,7 @@ def run_reference(args):
         return
     lat, lon, nt, dt, desc = workload(args.workload)
     cores = os.cpu_count() or 1
-    psteps_window = lat.size * lon.size * (nt - 1)
+    psteps_window = lat.size * lon.size * (cpu_levels(args.workload, nt) - 1)
     for _ in range(args.warmup):
         cpu_pool_run(args.workload, args.order, args.xclamp, cores, cores)
     times = [cpu_pool_run(args.workload, args.order, args.xclamp, cores, cores, first=100 * (k + 1))
@@ -432,9 +446,10 @@ def run_b200(args):
         cores = os.cpu_count() or 1
         lat2, lon2, nt2, _, desc2 = workload(args.workload)
         secs = cpu_pool_run(args.workload, args.order, args.xclamp, cores, cores)
-        line['cpu_baseline'] = {'value': lat2.size * lon2.size * (nt2 - 1) * cores / secs, 'unit': 'particle-steps/s',
+        line['cpu_baseline'] = {'value': lat2.size * lon2.size * (cpu_levels(args.workload, nt2) - 1) * cores / secs, 'unit': 'particle-steps/s',
                                 'cores': cores, 'kind': 'port',
-                                'sample': f'{cores} windows of the same workload, one per worker process '
+                                'sample': f'{cores} windows of the same workload'
+                                          + (' (first 2 intervals of each)' if args.workload == 'C3' else '') + ', one per worker process '
                                           f'({secs:.1f} s wall): oracle = scipy map_coordinates + numba-typed stencil '
                                           f'+ scipy.linalg.norm'}
     print(json.dumps(line), flush=True)
