@@ -224,6 +224,12 @@ int lcs_ridge_classify(const double* hxx, const double* hxy, const double* hyy, 
 int lcs_gather_peak(const void* pairs, int pair_dtype, int vec_width, int nlat, int nlon, int nrow, int ncol,
                     int nwindows, int taps, double jitter, int iters, double* sink, void* stream);
 
+/* The same pattern with the block's tap bounding box staged through shared memory every round (f64 2-value elements,
+ * 4x4 taps, zero jitter): the measured ceiling of a shared-memory-tile design in its best case, reported beside the
+ * direct-gather ceiling in DESIGN.md.  Bytes are counted as for lcs_gather_peak (taps only). */
+int lcs_gather_peak_smem(const void* pairs, int nlat, int nlon, int nrow, int ncol, int nwindows, int iters,
+                         double* sink, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,7 @@ SIGNATURES = {
     'lcs_spectral_norm_3x3': (c_int, [c_void_p, c_int64, c_void_p, c_void_p]),
     'lcs_ridge_classify': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p]),
+    'lcs_gather_peak_smem': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'lcs_gather_peak': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double, c_int,
                                 c_void_p, c_void_p]),
 }
