@@ -20,7 +20,6 @@
 // same bytes through the same 128 B/clk port and was not pursued).
 #include <cooperative_groups.h>
 #include <stdio.h>
-#include <limits.h>
 #include "lcs_internal.h"
 #include "lcs_device.cuh"
 
@@ -227,185 +226,6 @@ advect_fused_kernel(const AdvectParams P) {
     }
     P.x_out[wnp + o] = x;
     P.y_out[wnp + o] = y;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Shared-memory tile variant of the fused kernel (cubic, ES / ES32 layouts, cyclic or pointwise boundary).
-// A block owns a compact 16 x 16 patch of particles (warp = 2 x 16, as in the fused kernel).  Every stage the block
-// reduces the bounding box of its particles' 4x4 tap footprints; while that box is small (<= kTileCap elements) it is
-// staged into shared memory with coalesced loads and the taps become LDS reads -- 4 data-pipe cycles per warp request,
-// conflict-free, against ~6.6 for the unaligned L1 gathers (measured ceilings: 24.7 vs 18.6 TB/s, lcs_gather_peak_smem).
-// A block whose particles have spread, and any particle on the edge / pole path, gathers from global memory exactly as
-// the fused kernel does.  Same taps, same weights, same accumulation order: results are bit-identical to it (tested).
-constexpr int kTileCap = 1536;                  // elements per block tile: 24 KB of f64 pairs, 12 KB of f32 pairs
-
-template <typename ET> __device__ __forceinline__ ET ld_elem(const ET* p);
-template <> __device__ __forceinline__ d2 ld_elem<d2>(const d2* p) {
-    d2 r; asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p)); return r;
-}
-template <> __device__ __forceinline__ float2 ld_elem<float2>(const float2* p) { return __ldg(p); }
-
-// 16 taps from `base` (global or shared) with row pitch `pitch`, f64 accumulation in the fused kernel's order
-template <bool SHARED>
-__device__ __forceinline__ void taps_f64(const d2* base, int pitch, const double (&wy)[4], const double (&wx)[4], double (&out)[2]) {
-    out[0] = 0.0; out[1] = 0.0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        d2 c[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) c[j] = SHARED ? base[j] : ld_elem<d2>(base + j);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const double wyx = wy[i] * wx[j];
-            out[0] = fma(c[j].x, wyx, out[0]);
-            out[1] = fma(c[j].y, wyx, out[1]);
-        }
-        base += pitch;
-    }
-}
-// f32 elements, f64 arithmetic (precision='f32')
-template <bool SHARED>
-__device__ __forceinline__ void taps_f32_f64(const float2* base, int pitch, const double (&wy)[4], const double (&wx)[4], double (&out)[2]) {
-    out[0] = 0.0; out[1] = 0.0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float2 c[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) c[j] = SHARED ? base[j] : __ldg(base + j);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const double wyx = wy[i] * wx[j];
-            out[0] = fma((double)c[j].x, wyx, out[0]);
-            out[1] = fma((double)c[j].y, wyx, out[1]);
-        }
-        base += pitch;
-    }
-}
-// f32 elements, f32 arithmetic (precision='f32fast'): gather_cubic_wrap_f32's order
-template <bool SHARED>
-__device__ __forceinline__ void taps_f32(const float2* base, int pitch, const float2 (&wy)[4], const float2 (&wx)[4], double (&out)[2]) {
-    float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float2 c[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) c[j] = SHARED ? base[j] : __ldg(base + j);
-        float2 r = __fmul2_rn(c[0], wx[0]);
-#pragma unroll
-        for (int j = 1; j < 4; ++j) r = __ffma2_rn(c[j], wx[j], r);
-        acc = __ffma2_rn(r, wy[i], acc);
-        base += pitch;
-    }
-    out[0] = (double)acc.x; out[1] = (double)acc.y;
-}
-
-template <typename T, int LAYOUT>
-__global__ void __launch_bounds__(256, LCS_FUSED_MINBLOCKS)
-advect_tile_kernel(const AdvectParams P) {
-    using ET = typename Vec2Of<T>::type;
-    constexpr bool A32 = (LAYOUT == kES32);
-    extern __shared__ __align__(16) unsigned char tile_raw[];
-    ET* tile = reinterpret_cast<ET*>(tile_raw);
-    // [stage % 3][min sy, min sx, max sy, max sx]: stage n accumulates into buffer n % 3 and, after its barrier, re-arms
-    // buffer (n + 2) % 3 -- last read during stage n - 1, next written during stage n + 2, with the barrier of stage n + 1
-    // in between -- so one barrier per stage orders everything
-    __shared__ int s_box[3][4];
-    const int w = blockIdx.z;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row = blockIdx.y * 16 + warp * 2 + (lane >> 4);
-    const int col = blockIdx.x * 16 + (lane & 15);
-    const bool active = row < P.nrow && col < P.ncol;
-    const int rrow = active ? row : 0, rcol = active ? col : 0;
-    const int grow = P.row0 + rrow;
-    const bool pole = (grow < 3) || (grow >= P.nrow_global - 3);           // tools.py:31-33
-    const double kx = __ldg(P.kx + rrow), hx = __ldg(P.hx + rrow);
-    double x = __ldg(P.lon + rcol), y = __ldg(P.lat + rrow);               // trajectory.py:68-70
-    const size_t o = (size_t)rrow * P.ncol + rcol;
-    const size_t wnp = (size_t)w * P.np;
-    double* xt = (P.x_traj && active) ? P.x_traj + wnp * (P.nsteps + 1) + o : nullptr;
-    double* yt = (P.y_traj && active) ? P.y_traj + wnp * (P.nsteps + 1) + o : nullptr;
-    if (xt) { xt[0] = x; yt[0] = y; }
-    if (threadIdx.x < 12) s_box[threadIdx.x >> 2][threadIdx.x & 3] = (threadIdx.x & 3) < 2 ? INT_MAX : INT_MIN;
-    __syncthreads();
-    const int pair0 = P.level0 + w * P.level_stride;
-    int parity = 0;
-    double ua = 0.0, va = 0.0;
-    for (int t = 0; t < P.nsteps; ++t) {
-        for (int k = 0; k <= P.S; ++k) {
-            const bool euler = (k == 0);
-            const ET* field = reinterpret_cast<const ET*>(euler ? P.coef_a : P.coef_b) + (size_t)(pair0 + t) * P.plane;
-            // ---- index map, fold, weights (as gather_cubic_wrap / gather_cubic_wrap_f32)
-            const double cy = fold_wrap(index_map_fast(y, P.lat_min, P.nlat_over_span), P.nlat);
-            const double cx = fold_wrap(index_map_fast(x, P.lon_min, P.nlon_over_span), P.nlon);
-            const double fy = floor(cy), fx = floor(cx);
-            const int sy = (int)fy - 1, sx = (int)fx - 1;
-            const bool interior = active && !pole && sy >= 0 && sy + 3 < P.nlat && sx >= 0 && sx + 3 < P.nlon;
-            // ---- bounding box of the block's interior footprints
-            const unsigned m = __ballot_sync(0xffffffffu, interior);
-            if (m) {
-                const int lo_y = __reduce_min_sync(0xffffffffu, interior ? sy : INT_MAX);
-                const int lo_x = __reduce_min_sync(0xffffffffu, interior ? sx : INT_MAX);
-                const int hi_y = __reduce_max_sync(0xffffffffu, interior ? sy : INT_MIN);
-                const int hi_x = __reduce_max_sync(0xffffffffu, interior ? sx : INT_MIN);
-                if (lane == 0) {
-                    atomicMin(&s_box[parity][0], lo_y); atomicMin(&s_box[parity][1], lo_x);
-                    atomicMax(&s_box[parity][2], hi_y); atomicMax(&s_box[parity][3], hi_x);
-                }
-            }
-            __syncthreads();
-            const int by0 = s_box[parity][0], bx0 = s_box[parity][1];
-            const int bh = s_box[parity][2] - by0 + 4, bw = s_box[parity][3] - bx0 + 4;
-            const int rearm = parity == 0 ? 2 : parity - 1;                                  // (stage + 2) % 3
-            if (threadIdx.x < 4) s_box[rearm][threadIdx.x] = threadIdx.x < 2 ? INT_MAX : INT_MIN;
-            parity = parity == 2 ? 0 : parity + 1;
-            const bool use_tile = by0 != INT_MAX && (long long)bh * bw <= kTileCap;      // block-uniform
-            if (use_tile) {
-                for (int tr = warp; tr < bh; tr += 8) {
-                    const ET* src = field + (size_t)(by0 + tr) * P.nlon + bx0;
-                    for (int tc = lane; tc < bw; tc += 32) tile[tr * bw + tc] = ld_elem<ET>(src + tc);
-                }
-                __syncthreads();
-            }
-            double s[2] = {0.0, 0.0};
-            if (interior) {
-                const ET* base = use_tile ? tile + (sy - by0) * bw + (sx - bx0) : field + (size_t)sy * P.nlon + sx;
-                const int pitch = use_tile ? bw : P.nlon;
-                if constexpr (A32) {
-                    float2 wy[4], wx[4];
-                    cubic_weights_f32((float)(cy - fy), wy);
-                    cubic_weights_f32((float)(cx - fx), wx);
-                    if (use_tile) taps_f32<true>(base, pitch, wy, wx, s); else taps_f32<false>(base, pitch, wy, wx, s);
-                } else {
-                    double wy[4], wx[4];
-                    cubic_weights<false>(__dsub_rn(cy, fy), wy);
-                    cubic_weights<false>(__dsub_rn(cx, fx), wx);
-                    if constexpr (sizeof(T) == 8) {
-                        if (use_tile) taps_f64<true>(base, pitch, wy, wx, s); else taps_f64<false>(base, pitch, wy, wx, s);
-                    } else {
-                        if (use_tile) taps_f32_f64<true>(base, pitch, wy, wx, s); else taps_f32_f64<false>(base, pitch, wy, wx, s);
-                    }
-                }
-            } else if (active) {                          // edge or pole path: exactly the fused kernel's sample
-                if (pole && P.raw_planar) {
-                    if (euler) pole_sample_planar<false>(P, pair0 + t, x, y, s); else pole_sample_planar<true>(P, pair0 + t, x, y, s);
-                } else {
-                    sample<typename EsPolicy<T, LAYOUT>::type, false, 3>(P, euler ? P.raw_a : P.raw_b, euler ? P.coef_a : P.coef_b,
-                                                                         pair0 + t, pole, x, y, s);
-                }
-            }
-            if (euler) {
-                ua = s[0]; va = s[1];
-                y = __dadd_rn(y, __dmul_rn(P.ky, va));
-                x = __dadd_rn(x, __dmul_rn(kx, ua));
-            } else {
-                y = __dadd_rn(y, __dmul_rn(P.hy, __dadd_rn(va, s[1])));
-                x = __dadd_rn(x, __dmul_rn(hx, __dadd_rn(ua, s[0])));
-            }
-            bounds_local(P, x, y);
-        }
-        if (xt) { xt[(size_t)(t + 1) * P.np] = x; yt[(size_t)(t + 1) * P.np] = y; }
-    }
-    if (active) { P.x_out[wnp + o] = x; P.y_out[wnp + o] = y; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -752,15 +572,6 @@ static cudaError_t launch_advect(const AdvectParams& P, int nwindows, cudaStream
     const int tw = 256 >> P.band_log2;
     const dim3 grid((unsigned)((P.ncol + tw - 1) / tw), (unsigned)((P.nrow + P.band - 1) / P.band), (unsigned)nwindows);
     if (P.xmode != LCS_X_CLAMP_OUTER) {
-        if constexpr (ORDER == 3 && !STRICT && (LAYOUT == kES || LAYOUT == kES32)) {
-            if (lcs_env_int("LCS_ADVECT_TILE", 0)) {        // shared-memory tile variant (opt-in while it is being evaluated)
-                const dim3 tgrid((unsigned)((P.ncol + 15) / 16), (unsigned)((P.nrow + 15) / 16), (unsigned)nwindows);
-                if (tgrid.y > 65535) return cudaErrorInvalidConfiguration;
-                advect_tile_kernel<T, LAYOUT><<<tgrid, block, kTileCap * sizeof(typename Vec2Of<T>::type), st>>>(P);
-                lcs_count_launches(1);
-                return cudaGetLastError();
-            }
-        }
         advect_fused_kernel<T, STRICT, ORDER, LAYOUT><<<grid, block, 0, st>>>(P);
         lcs_count_launches(1);
         return cudaGetLastError();

@@ -259,22 +259,3 @@ def test_planar_and_packed_raw_winds_agree(cuda_device, xmode, dtype):
     with pytest.raises(ValueError):
         eng.stage(u, v, raw='texture')
 
-
-@pytest.mark.parametrize('prec', [dict(pair_dtype='f64'), dict(pair_dtype='f32'), dict(pair_dtype='f32', arith='f32')])
-@pytest.mark.parametrize('xmode', ['pointwise', 'cyclic'])
-def test_shared_memory_tile_variant_is_bit_identical(cuda_device, monkeypatch, xmode, prec):
-    """LCS_ADVECT_TILE=1: the fused kernel with a block's tap bounding box staged through shared memory while the block is
-    compact.  Same taps, weights and accumulation order, so trajectories equal the direct-gather kernel's bit for bit --
-    on ragged grids (partial 16 x 16 blocks), with exits, pole rows, edge taps and several windows."""
-    from lagrangiancoherence_b200.engine import FtleEngine
-    for shape in ((41, 57), (64, 33), (19, 150)):
-        lat = np.linspace(-30.0, 10.0, shape[0])
-        lon = np.linspace(-80.0, -24.0, shape[1]) if xmode == 'pointwise' else np.linspace(-180.0, 178.0, shape[1])
-        u, v = S.era5_like_winds(lat, lon, 7, seed=shape[0])
-        eng = FtleEngine(lat, lon, -21600, SETTLS_order=4, xmode=xmode, device=cuda_device, **prec)
-        st = eng.stage(u, v)
-        monkeypatch.setenv('LCS_ADVECT_TILE', '0')
-        xa, ya, xta, yta = eng.advect(st, nsteps=4, nwindows=3, return_traj=True)
-        monkeypatch.setenv('LCS_ADVECT_TILE', '1')
-        xb, yb, xtb, ytb = eng.advect(st, nsteps=4, nwindows=3, return_traj=True)
-        assert torch.equal(xa, xb) and torch.equal(ya, yb) and torch.equal(xta, xtb) and torch.equal(yta, ytb), shape
