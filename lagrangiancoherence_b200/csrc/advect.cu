@@ -72,7 +72,17 @@ template <> struct EsPolicy<float, kES32> { using type = Vec2F32Arith; };
 // Thread -> particle: a block is a (band x 256/band) tile of the particle grid, a warp a
 // (band x 32/band) patch (smaller unique tap footprint than a 1x32 strip: better L1 hit rate);
 // grid = (column tiles, row bands, windows), so no integer division is needed.
+// STRIP: block = 8 rows x 32 columns, warp = one row of 32 particles with the block's warps stacked (they share tap
+// rows).  Measured against the 2 x 16 patches: the same at C2 (14.3 ms), 4 % slower with f32 taps, 3 % faster with hourly
+// winds (C4) and 18-21 % faster on the 721 x 1440 grid (C3: 3.17 vs 4.00 ms for four 12-interval windows), where the
+// compact block keeps its taps in L1 while the 2 x 128 strip of the default mapping does not.  Chosen by launch_advect.
+template <bool STRIP = false>
 __device__ __forceinline__ bool particle_rc(const AdvectParams& P, int& row, int& col) {
+    if (STRIP) {
+        row = blockIdx.y * 8 + (threadIdx.x >> 5);
+        col = blockIdx.x * 32 + (threadIdx.x & 31);
+        return row < P.nrow && col < P.ncol;
+    }
     const int r = threadIdx.x & (P.band - 1);
     const int c = threadIdx.x >> P.band_log2;
     row = blockIdx.y * P.band + r;
@@ -198,12 +208,12 @@ __device__ __forceinline__ void bounds_local(const AdvectParams& P, double& x, d
 #ifndef LCS_FUSED_MINBLOCKS
 #define LCS_FUSED_MINBLOCKS 4       // 64 registers, 1024 threads per SM (measured against 3 and 2 blocks: see DESIGN.md)
 #endif
-template <typename T, bool STRICT, int ORDER, int LAYOUT>
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool STRIP = false>
 __global__ void __launch_bounds__(256, LCS_FUSED_MINBLOCKS)
 advect_fused_kernel(const AdvectParams P) {
     const int w = blockIdx.z;
     int row, col;
-    if (!particle_rc(P, row, col)) return;
+    if (!particle_rc<STRIP>(P, row, col)) return;
     const int grow = P.row0 + row;
     const bool pole = (grow < ORDER) || (grow >= P.nrow_global - ORDER);   // tools.py:31-33
     const double kx = __ldg(P.kx + row), hx = __ldg(P.hx + row);
@@ -572,6 +582,18 @@ static cudaError_t launch_advect(const AdvectParams& P, int nwindows, cudaStream
     const int tw = 256 >> P.band_log2;
     const dim3 grid((unsigned)((P.ncol + tw - 1) / tw), (unsigned)((P.nrow + P.band - 1) / P.band), (unsigned)nwindows);
     if (P.xmode != LCS_X_CLAMP_OUTER) {
+        if constexpr (sizeof(T) == 8 && !STRICT && ORDER == 3 && LAYOUT == kES) {
+            // wide grids: 8 x 32 blocks of one-row warps (see particle_rc); LCS_ADVECT_STRIP=0/1 forces the choice
+            const int strip = lcs_env_int("LCS_ADVECT_STRIP", -1);
+            if (strip == 1 || (strip < 0 && P.ncol >= 640)) {
+                const dim3 sgrid((unsigned)((P.ncol + 31) / 32), (unsigned)((P.nrow + 7) / 8), (unsigned)nwindows);
+                if (sgrid.y <= 65535) {
+                    advect_fused_kernel<T, STRICT, ORDER, LAYOUT, true><<<sgrid, block, 0, st>>>(P);
+                    lcs_count_launches(1);
+                    return cudaGetLastError();
+                }
+            }
+        }
         advect_fused_kernel<T, STRICT, ORDER, LAYOUT><<<grid, block, 0, st>>>(P);
         lcs_count_launches(1);
         return cudaGetLastError();

@@ -259,3 +259,20 @@ def test_planar_and_packed_raw_winds_agree(cuda_device, xmode, dtype):
     with pytest.raises(ValueError):
         eng.stage(u, v, raw='texture')
 
+
+def test_strip_warp_mapping_is_bit_identical(cuda_device, monkeypatch):
+    """Wide grids run the fused kernel with 8 x 32 blocks of one-row warps instead of 2 x 16 patches (launch_advect, ncol >= 640).
+    Particles are independent under the cyclic / pointwise boundary, so the thread -> particle mapping cannot change a bit:
+    forced on and off on ragged grids, with trajectories and a row band."""
+    from lagrangiancoherence_b200.engine import FtleEngine
+    for shape, xmode in (((41, 57), 'pointwise'), ((19, 150), 'cyclic'), ((64, 33), 'pointwise')):
+        lat = np.linspace(-30.0, 10.0, shape[0])
+        lon = np.linspace(-80.0, -24.0, shape[1]) if xmode == 'pointwise' else np.linspace(-180.0, 178.0, shape[1])
+        u, v = S.era5_like_winds(lat, lon, 6, seed=shape[1])
+        eng = FtleEngine(lat, lon, -21600, SETTLS_order=4, xmode=xmode, device=cuda_device)
+        st = eng.stage(u, v)
+        res = {}
+        for strip in ('0', '1'):
+            monkeypatch.setenv('LCS_ADVECT_STRIP', strip)
+            res[strip] = eng.advect(st, nsteps=4, nwindows=2, return_traj=True) + eng.advect(st, nsteps=4, rows=(5, 17))
+        assert all(torch.equal(a, b) for a, b in zip(res['0'], res['1'])), shape
