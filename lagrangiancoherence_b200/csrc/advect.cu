@@ -262,12 +262,12 @@ __device__ __forceinline__ double apply_pending(const AdvectParams& P, int w, in
     return x;
 }
 
-template <typename T, bool STRICT, int ORDER, int LAYOUT>
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool STRIP = false>
 __global__ void __launch_bounds__(256)
 advect_phase_move(const AdvectParams P, int q /* global sub-step index */, int t /* interval */, int k /* 0: Euler */) {
     const int w = blockIdx.z;
     int row, col;
-    if (!particle_rc(P, row, col)) return;
+    if (!particle_rc<STRIP>(P, row, col)) return;
     const int p = row * P.ncol + col;
     const int grow = P.row0 + row;
     const bool pole = (grow < ORDER) || (grow >= P.nrow_global - ORDER);
@@ -611,8 +611,17 @@ static cudaError_t launch_advect(const AdvectParams& P, int nwindows, cudaStream
         }
     }
     const dim3 ggrid(4, (unsigned)nwindows);
+    bool strip = false;
+    const dim3 sgrid((unsigned)((P.ncol + 31) / 32), (unsigned)((P.nrow + 7) / 8), (unsigned)nwindows);
+    if constexpr (sizeof(T) == 8 && !STRICT && ORDER == 3 && LAYOUT == kES) {       // wide grids, as for the fused kernel
+        const int s = lcs_env_int("LCS_ADVECT_STRIP", -1);
+        strip = (s == 1 || (s < 0 && P.ncol >= 640)) && sgrid.y <= 65535;
+    }
     for (int q = 0; q < P.nsub; ++q) {
-        advect_phase_move<T, STRICT, ORDER, LAYOUT><<<grid, block, 0, st>>>(P, q, q / (1 + P.S), q % (1 + P.S));
+        if constexpr (sizeof(T) == 8 && !STRICT && ORDER == 3 && LAYOUT == kES) {
+            if (strip) advect_phase_move<T, STRICT, ORDER, LAYOUT, true><<<sgrid, block, 0, st>>>(P, q, q / (1 + P.S), q % (1 + P.S));
+        }
+        if (!strip) advect_phase_move<T, STRICT, ORDER, LAYOUT><<<grid, block, 0, st>>>(P, q, q / (1 + P.S), q % (1 + P.S));
         advect_phase_gtpass<<<ggrid, block, 0, st>>>(P, q);
     }
     advect_phase_final<<<grid, block, 0, st>>>(P);

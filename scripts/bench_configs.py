@@ -109,7 +109,7 @@ def c2():
 def c3():
     """configs[2]: 721x1440 hourly, 72 h backward (nt=73), one field and a batch of 8 start times, one GPU."""
     lat, lon = S.grid_c3()
-    for B, xmode in ((1, 'pointwise'), (8, 'pointwise'), (8, 'outer')):
+    for B, xmode in ((1, 'pointwise'), (1, 'outer'), (8, 'pointwise'), (8, 'outer')):
         nt = 73
         u, v = S.era5_like_winds(lat, lon, nt - 1 + B, noise=0.0)
         eng = FtleEngine(lat, lon, -3600, SETTLS_order=4, xmode=xmode, device=dev)
