@@ -53,8 +53,13 @@ class LCS:
         if is_dataset(ds):                                           # LCS.py:81-83
             u, v = ds.u.copy(), ds.v.copy()
         elif isinstance(ds, str):                                    # LCS.py:84-87
-            raise NotImplementedError('opening NetCDF paths needs xarray/netCDF4, which this image lacks; '
-                                      'pass u= and v= arrays')
+            try:
+                import xarray as xr
+            except ImportError:
+                raise NotImplementedError('opening a NetCDF path needs xarray (+ netCDF4), which is not installed; '
+                                          'pass u= and v= arrays') from None
+            ds = xr.open_dataset(ds)
+            u, v = ds.u.copy(), ds.v.copy()
         resample_plan_ = None
         if isinstance(resample, str):                                # LCS.py:88-91: linear refinement in time
             from ..timeaxis import resample_plan
