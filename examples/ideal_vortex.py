@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """The reference's idealised-vortex example (examples/ideal_vortex.py:211-288) on the B200 engine:
 departure points backward (S=4) and forward (S=2) on the cyclic 2-degree grid, then the attracting and
-repelling FTLE fields, `0.5*log(sigma)` applied by the caller exactly as upstream does.  No plotting:
-prints the statistics the reference's figures show (FTLE range 0..~0.14, latitude-of-origin range).
+repelling FTLE fields on the 360x721 common grid of the global path, `0.5*log(sigma)` applied by the caller exactly
+as upstream does.  No plotting: prints summary statistics of what the reference's figures show.  (Upstream's figures
+come from winds that were additionally truncated to T20 by windspharm, which smooths the vortex; that step has no
+counterpart here)
 
     python examples/ideal_vortex.py            # needs a B200 and the built liblcs_b200.so
 """
@@ -29,16 +31,17 @@ def main():
                                                  copy=True, return_traj=True, cyclic_xboundary=True, verbose=False)
     x, y = trajectory.parcel_propagation(ds.u, ds.v, timestep=6 * 3600, propdim='time', SETTLS_order=2,
                                          copy=True, return_traj=True, cyclic_xboundary=True, verbose=False)
-    # upstream calls isglobal=True with its 360x721 regrid and T20 truncation (windspharm); here the cyclic
-    # boundary on the native grid
+    # upstream calls isglobal=True with its defaults: the 360x721 regrid (done here, on the device) followed by a T20
+    # spherical-harmonic truncation of the winds through windspharm (not available here: truncation=None)
     rcs = LCS.LCS(timestep=6 * 3600, timedim='time', SETTLS_order=4)
-    ftle_r = np.log(rcs(ds.copy(), isglobal=True, interp_to_common_grid=False, truncation=None, verbose=False)) / 2
+    ftle_r = np.log(rcs(ds.copy(), isglobal=True, truncation=None, verbose=False)) / 2
     acs = LCS.LCS(timestep=-6 * 3600, timedim='time', SETTLS_order=4)
-    ftle_a = np.log(acs(ds.copy(), isglobal=True, interp_to_common_grid=False, truncation=None, verbose=False)) / 2
+    ftle_a = np.log(acs(ds.copy(), isglobal=True, truncation=None, verbose=False)) / 2
     dt = time.perf_counter() - t0
+    lat, lon = ftle_a.coords['latitude'], ftle_a.coords['longitude']           # the common grid now
 
     origin = y_dye.isel(time=0).values - y_dye.isel(time=-1).values
-    print(f'grid {lat.size}x{lon.size}, {u.shape[0]} levels; four calls in {dt * 1e3:.1f} ms')
+    print(f'winds {u.shape[1]}x{u.shape[2]}, FTLE grid {len(lat)}x{len(lon)}, {u.shape[0]} levels; four calls in {dt * 1e3:.1f} ms')
     print(f'latitude displacement of the dye (backward, 42 h): {np.nanmin(origin):+.2f} .. {np.nanmax(origin):+.2f} deg')
     for name, f in (('attracting', ftle_a), ('repelling', ftle_r)):
         vals = f.values[np.isfinite(f.values)]
