@@ -403,7 +403,7 @@ __device__ __forceinline__ double2 ld_state(const double2* p) {
 template <typename T, bool STRICT, int ORDER, int LAYOUT, bool EULER>
 __device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, const int w, const int q, const int t,
                                                 const int tid_w, const int nthr_w,
-                                                const unsigned char* s_lt, const unsigned char* s_gt) {
+                                                const unsigned char* s_f) {
     const unsigned sbase = (unsigned)w * (unsigned)P.nslots;        // host guarantees nwindows*nslots < 2^32
     for (int e = tid_w; e < P.nslots; e += nthr_w) {
         double2* const ps = reinterpret_cast<double2*>(P.spos) + (sbase + (unsigned)e);
@@ -421,8 +421,9 @@ __device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, const int
         else {
             const double2 s = ld_state(ps);
             x = s.x; y = s.y;
-            if (s_lt[row] && s_lt[P.nrow + col]) x = P.lon_min;      // trajectory.py:96
-            if (s_gt[row] && s_gt[P.nrow + col]) x = P.lon_max;      // trajectory.py:97
+            const unsigned m = (unsigned)s_f[row] & (unsigned)s_f[P.nrow + col];   // bit 0: "< x_min" pass, bit 1: "> x_max" pass
+            if (m & 1u) x = P.lon_min;                               // trajectory.py:96
+            if (m & 2u) x = P.lon_max;                               // trajectory.py:97
         }
         const int pair = P.level0 + w * P.level_stride + t;
         if (EULER) {
@@ -457,35 +458,33 @@ __device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, const int
 template <typename T, bool STRICT, int ORDER, int LAYOUT, bool CLUSTERED>
 __global__ void __launch_bounds__(kClusterThreads, LCS_CLUSTER_MINBLOCKS)
 advect_outer_cluster_kernel(const AdvectParams P, const int cs /* CTAs per window = cluster size (1..8) */) {
-    extern __shared__ unsigned char s_flags[];            // [lt rows | lt cols | gt rows | gt cols]
+    extern __shared__ unsigned char s_f[];                // [rows | cols], bit 0 = "< x_min" flag, bit 1 = "> x_max" flag
     const int w = blockIdx.x / cs;
     const int rank = blockIdx.x - w * cs;
     const int tid_w = rank * kClusterThreads + threadIdx.x;
     const int nthr_w = cs * kClusterThreads;
     const int nflag = P.nrow + P.ncol;
-    unsigned char* s_lt = s_flags;
-    unsigned char* s_gt = s_flags + nflag;
     int q = 0;
     for (int t = 0; t < P.nsteps; ++t) {
         for (int k = 0; k <= P.S; ++k, ++q) {
             // ---- phase A: pending clamps of q-1 (mirrored in smem), stage, y clamp, raise "< x_min" flags
-            if (k == 0) cluster_phase_a<T, STRICT, ORDER, LAYOUT, true>(P, w, q, t, tid_w, nthr_w, s_lt, s_gt);
-            else cluster_phase_a<T, STRICT, ORDER, LAYOUT, false>(P, w, q, t, tid_w, nthr_w, s_lt, s_gt);
+            if (k == 0) cluster_phase_a<T, STRICT, ORDER, LAYOUT, true>(P, w, q, t, tid_w, nthr_w, s_f);
+            else cluster_phase_a<T, STRICT, ORDER, LAYOUT, false>(P, w, q, t, tid_w, nthr_w, s_f);
             window_sync<CLUSTERED>();
             // ---- phase B: mirror the "< x_min" flags; candidates that survive that pass raise "> x_max" flags
             const unsigned char* g_lt = flag_slot(P, w, q, 0);
             unsigned char* g_gt = flag_slot(P, w, q, 1);
-            for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_lt[i] = __ldcg(g_lt + i);
+            for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_f[i] = __ldcg(g_lt + i);          // 0 / 1
             __syncthreads();
             const int ncand = __ldcg(P.cand_count + (size_t)w * P.nsub + q);
             const int* cand = P.cand + (size_t)w * P.nslots;
             for (int i = tid_w; i < ncand; i += nthr_w) {
                 int row, col;
                 slot_rc(P, __ldcg(cand + i), row, col);
-                if (!(s_lt[row] && s_lt[P.nrow + col])) { g_gt[row] = 1; g_gt[P.nrow + col] = 1; }
+                if (!(s_f[row] & s_f[P.nrow + col] & 1)) { g_gt[row] = 1; g_gt[P.nrow + col] = 1; }
             }
             window_sync<CLUSTERED>();
-            for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_gt[i] = __ldcg(g_gt + i);
+            for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_f[i] |= (unsigned char)(__ldcg(g_gt + i) << 1);
             __syncthreads();
         }
     }
@@ -499,8 +498,9 @@ advect_outer_cluster_kernel(const AdvectParams P, const int cs /* CTAs per windo
         else {
             const double2 s = __ldcs(spos + e);
             x = s.x; y = s.y;
-            if (s_lt[row] && s_lt[P.nrow + col]) x = P.lon_min;
-            if (s_gt[row] && s_gt[P.nrow + col]) x = P.lon_max;
+            const unsigned m = (unsigned)s_f[row] & (unsigned)s_f[P.nrow + col];
+            if (m & 1u) x = P.lon_min;
+            if (m & 2u) x = P.lon_max;
         }
         const size_t o = (size_t)row * P.ncol + col;
         P.x_out[(size_t)w * P.np + o] = x; P.y_out[(size_t)w * P.np + o] = y;
@@ -601,7 +601,7 @@ static cudaError_t launch_advect(const AdvectParams& P, int nwindows, cudaStream
     // Enough windows to fill the machine: one persistent cluster per window (cluster barriers).
     // Few windows: one launch pair per sub-step over all particles (kernel-boundary barriers).
     const int mode = lcs_env_int("LCS_OUTER_MODE", 0);          // 0 auto, 1 phased launches, 2 clusters
-    const size_t smem = 2 * (size_t)(P.nrow + P.ncol);
+    const size_t smem = (size_t)(P.nrow + P.ncol);
     if (P.nsub > 0 && smem <= 48 * 1024 && mode != 1) {
         double busy = 0.0;
         const int cs = choose_cluster_size<T, STRICT, ORDER, LAYOUT>(P, nwindows, smem, &busy);
