@@ -112,53 +112,36 @@ iir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__
                             : out_a + (size_t)p * plane;
     auto ld = [&](int i) { return (double)__ldg(src + (size_t)i * n1); };
     // causal sum just before the run: a[r0-1] = sum_{k>=0} z^k s[r0-1-k], Horner from the far end
-    // (the end sums take their loads eight at a time: a rolled load->FMA chain pays one memory latency per term;
-    //  `kh` is a multiple of 8 minus 1 -- extra far terms weigh less than the truncation bound)
-    double a = 0.0;
+    // (taking the loads of the end sums eight at a time, and those of the run ahead of its recursions, was measured
+    //  8 % slower than these plain loops: the kernel is occupancy-, not latency-limited at 96 registers)
+    double a;
     {
         MirrorWalk w(r0 - 1 - kh, n0, +1);
-        for (int k = 0; k <= kh; k += 8) {
-            double s8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { s8[j] = ld(w.i); w.next(); }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) a = fma(z, a, s8[j]);
-        }
+        a = ld(w.i);
+        for (int k = 0; k < kh; ++k) { w.next(); a = fma(z, a, ld(w.i)); }
     }
     double av[KQ];
     {
         MirrorWalk w(r0, n0, +1);
 #pragma unroll
-        for (int j = 0; j < KQ; ++j) { av[j] = ld(w.i); w.next(); }
-#pragma unroll
-        for (int j = 0; j < KQ; ++j) { a = fma(z, a, av[j]); av[j] = a; }
+        for (int j = 0; j < KQ; ++j) { a = fma(z, a, ld(w.i)); av[j] = a; w.next(); }
     }
     // anticausal sum just after the run: m[r0+KQ] = sum_{k>=0} z^k s[r0+KQ+k]
-    double m = 0.0;
+    double m;
     {
         MirrorWalk w(r0 + KQ + kh, n0, -1);
-        for (int k = 0; k <= kh; k += 8) {
-            double s8[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { s8[j] = ld(w.i); w.next(); }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) m = fma(z, m, s8[j]);
-        }
+        m = ld(w.i);
+        for (int k = 0; k < kh; ++k) { w.next(); m = fma(z, m, ld(w.i)); }
     }
     double* o = dst + (size_t)c * n0 + r0;
     {
         MirrorWalk w(r0 + KQ - 1, n0, -1);
 #pragma unroll
-        for (int jb = KQ - 8; jb >= 0; jb -= 8) {
-            double s8[8];
-#pragma unroll
-            for (int j = 7; j >= 0; --j) { s8[j] = ld(w.i); w.next(); }
-#pragma unroll
-            for (int j = 7; j >= 0; --j) {
-                const double out = h0 * fma(z, m, av[jb + j]);
-                m = fma(z, m, s8[j]);
-                if (r0 + jb + j < n0) o[jb + j] = out;
-            }
+        for (int j = KQ - 1; j >= 0; --j) {
+            const double out = h0 * fma(z, m, av[j]);
+            m = fma(z, m, ld(w.i));
+            w.next();
+            if (r0 + j < n0) o[j] = out;
         }
     }
 }
@@ -253,7 +236,7 @@ extern "C" int lcs_prefilter(const void* u, const void* v, int in_dtype, double*
         const double z = poles[ip];
         const double h0 = (1.0 - z) * (1.0 - 1.0 / z) * (-z) / (1.0 - z * z);
         int kh = (int)ceil(log(1e-18) / log(fabs(z)));                  // |z|^kh < 1e-18: below one f64 ulp of the sum
-        kh = (kh + 8) / 8 * 8 - 1;                                      // kh + 1 terms, a multiple of 8 (see the kernel)
+        if (kh < 4) kh = 4;
         const void* src_u = ip == 0 ? u : (const void*)coef_u;
         const void* src_v = ip == 0 ? v : (const void*)coef_v;
         const int src_dtype = ip == 0 ? in_dtype : LCS_F64;
