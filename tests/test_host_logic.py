@@ -168,3 +168,24 @@ def test_latlonsel_strict_open_intervals():
     assert latlonsel(da2, slice(-2, 2), slice(12, 15), latname='latitude', lonname='longitude').shape == (3, 2)
     with pytest.raises(AssertionError):
         latlonsel(da2, slice(-2, 2), slice(12, 15))
+
+
+def test_bench_reference_arm_line_has_the_contract_keys():
+    """`bench.py --impl reference` (the reference's CPU arithmetic on the host cores) prints ONE JSON line with the keys
+    the driver reads; it needs no GPU, so the contract is checked here."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1',
+                          '--warmup', '0'], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ('impl', 'metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'cpu_baseline', 'e2e', 'gpu_launches'):
+        assert key in d, key
+    assert d['impl'] == 'reference' and d['metric'] == 'particle-steps/s' and d['value'] > 0
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+    assert 'workload' in d['config'] and d['vs_baseline'] is None
