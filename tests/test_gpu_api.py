@@ -151,3 +151,30 @@ def test_rolling_matches_per_window_calls(cuda_device):
     for s in (0, 3, 4):
         ref = O.lcs_field(u[s:s + 5], v[s:s + 5], lat, lon, -21600, SETTLS_order=4)
         assert close_fraction(fields[s], ref, FTLE_REL) >= 0.995
+
+
+def test_bench_line_has_the_contract_keys(cuda_device):
+    """`python bench.py` prints ONE JSON line carrying the driver's contract (value, e2e with the copied bytes, kernel
+    launch count, clocks, roofline with the live-measured ceiling, cpu_baseline unless skipped)."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--steps', '3', '--warmup', '3', '--batch', '296',
+                          '--no-cpu-baseline'], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+                'vs_baseline', 'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline'):
+        assert key in d, key
+    assert d['metric'] == 'particle-steps/s' and d['n_gpus'] == 1 and d['steps'] == 3 and d['dtype'] == 'f64'
+    assert d['value'] > 1e9 and 0 < d['e2e']['value'] < d['value']                 # copies inside the timed region cost something
+    assert d['e2e']['h2d_bytes_per_step'] == 2 * 304 * 281 * 321 * 8 and d['e2e']['d2h_bytes_per_step'] == 296 * 281 * 321 * 8
+    assert d['gpu_launches'] == 3 * 5                                            # prefilter x2, pack, integrator, epilogue per step
+    r = d['roofline']
+    assert set(('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic')) <= set(r)
+    assert r['unit'] == 'GB/s' and 0.3 < r['frac'] < 1.3 and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9
+    assert 'workload' in d['config'] and 'sm_mhz' in d['clocks']
