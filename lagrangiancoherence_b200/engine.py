@@ -141,7 +141,9 @@ class FtleEngine:
 
         ``raw``: how the 2*order pole rows of the spline orders get the raw winds they sample -- ``'planar'`` (default)
         lets them read ``u, v`` themselves, ``'packed'`` stages a second E/S copy of the series for them (a third more
-        staging traffic and memory; same integrator time: measured 14.26 vs 14.29 ms per 296 C2 windows)."""
+        staging traffic and memory; same integrator time: measured 14.26 vs 14.29 ms per 296 C2 windows).  With
+        ``'planar'`` the returned object keeps ``u, v`` (their device copies) alive and the integrator reads them: do
+        not overwrite them in place between ``stage`` and ``advect``."""
         u = self._to_device(u)
         v = self._to_device(v)
         if u.shape != v.shape or u.dim() != 3 or tuple(u.shape[1:]) != (self.nlat, self.nlon):
