@@ -427,6 +427,10 @@ def run_b200(args):
             'kernel': kernel_name,
             'achieved': achieved, 'peak': gather_peak_es, 'unit': 'GB/s', 'frac': achieved / gather_peak_es,
             'bytes_per_particle_step': issued_bytes_pstep,
+            # SURVEY 8(d) / BASELINE.md figure beside it: the reference formulation's (2+4S)(p+1)^2 w bytes per particle-step
+            # over the same kernel time, against the measured ceiling for 4-value taps (details in reference_formulation)
+            'algorithmic_bytes_per_particle_step': survey_bytes_pstep,
+            'achieved_algorithmic': achieved_survey, 'frac_algorithmic': achieved_survey / gather_peak,
             'peak_source': 'lcs_gather_peak measured in this run: %dx%d-tap gathers of %d-B elements (what the ES kernel '
                            'issues) on an L2-resident level, same thread tiling, coherent positions, no dependent arithmetic'
                            % (args.order + 1, args.order + 1, 2 * elt),
