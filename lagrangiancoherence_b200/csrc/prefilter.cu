@@ -79,7 +79,13 @@ fir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__
 // and only their values at the ends of the run need the truncated (|k| <= KH, remainder < 1e-18) mirror sums.  Per run:
 // 2*(KH+1) Horner steps for the two ends + 2*KQ recursion steps, instead of KQ*65 FMAs -- the filter becomes a
 // streaming kernel (ncu: the FIR form ran the FP64 pipe at ~45 %).  Agreement with scipy stays ~1e-15 of the field.
-constexpr int KQ = 32;    // outputs per thread in the recursive form
+#ifndef LCS_PREFILTER_RUN
+#define LCS_PREFILTER_RUN 24        // measured with the register cap below: 24 -> 3.73 ms, 32 (80 regs) 3.80, 16 -> 4.02, uncapped 32 (96 regs) 5.06 per 1192 C2 levels
+#endif
+#ifndef LCS_PREFILTER_MINBLOCKS
+#define LCS_PREFILTER_MINBLOCKS 8   // 64 registers, 1024 threads per SM: the recursions are latency-bound, occupancy hides it
+#endif
+constexpr int KQ = LCS_PREFILTER_RUN;    // outputs per thread in the recursive form
 
 struct MirrorWalk {        // index into the mirror extension d c b | a b c d | c b a, stepped by +-1
     int i, dir, n;
@@ -97,7 +103,7 @@ struct MirrorWalk {        // index into the mirror extension d c b | a b c d | 
 };
 
 template <typename Tin>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, LCS_PREFILTER_MINBLOCKS)
 iir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b, int interleaved_planes,
                            double* __restrict__ out_a, double* __restrict__ out_b, int split_out,
                            int n0, int n1, double z, double h0, int kh) {
