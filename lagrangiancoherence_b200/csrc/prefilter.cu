@@ -80,10 +80,11 @@ fir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__
 // 2*(KH+1) Horner steps for the two ends + 2*KQ recursion steps, instead of KQ*65 FMAs -- the filter becomes a
 // streaming kernel (ncu: the FIR form ran the FP64 pipe at ~45 %).  Agreement with scipy stays ~1e-15 of the field.
 #ifndef LCS_PREFILTER_RUN
-#define LCS_PREFILTER_RUN 24        // measured with the register cap below: 24 -> 3.73 ms, 32 (80 regs) 3.80, 16 -> 4.02, uncapped 32 (96 regs) 5.06 per 1192 C2 levels
+#define LCS_PREFILTER_RUN 32        // ncu launch lists, 1192 C2 levels x 2 components, lat + lon pass: runs of 32 uncapped (96 registers)
+                                    // 1.31 + 1.37 ms; runs of 24 capped at 64 registers (1024 threads per SM) 1.40 + 1.45 ms
 #endif
 #ifndef LCS_PREFILTER_MINBLOCKS
-#define LCS_PREFILTER_MINBLOCKS 8   // 64 registers, 1024 threads per SM: the recursions are latency-bound, occupancy hides it
+#define LCS_PREFILTER_MINBLOCKS 1
 #endif
 constexpr int KQ = LCS_PREFILTER_RUN;    // outputs per thread in the recursive form
 
