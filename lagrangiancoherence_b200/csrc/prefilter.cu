@@ -83,9 +83,6 @@ fir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__
 #define LCS_PREFILTER_RUN 32        // ncu launch lists, 1192 C2 levels x 2 components, lat + lon pass: runs of 32 uncapped (96 registers)
                                     // 1.31 + 1.37 ms; runs of 24 capped at 64 registers (1024 threads per SM) 1.40 + 1.45 ms
 #endif
-#ifndef LCS_PREFILTER_MINBLOCKS
-#define LCS_PREFILTER_MINBLOCKS 1
-#endif
 constexpr int KQ = LCS_PREFILTER_RUN;    // outputs per thread in the recursive form
 
 struct MirrorWalk {        // index into the mirror extension d c b | a b c d | c b a, stepped by +-1
@@ -104,7 +101,7 @@ struct MirrorWalk {        // index into the mirror extension d c b | a b c d | 
 };
 
 template <typename Tin>
-__global__ void __launch_bounds__(128, LCS_PREFILTER_MINBLOCKS)
+__global__ void __launch_bounds__(128)
 iir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b, int interleaved_planes,
                            double* __restrict__ out_a, double* __restrict__ out_b, int split_out,
                            int n0, int n1, double z, double h0, int kh) {
