@@ -80,8 +80,8 @@ fir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__
 // 2*(KH+1) Horner steps for the two ends + 2*KQ recursion steps, instead of KQ*65 FMAs -- the filter becomes a
 // streaming kernel (ncu: the FIR form ran the FP64 pipe at ~45 %).  Agreement with scipy stays ~1e-15 of the field.
 #ifndef LCS_PREFILTER_RUN
-#define LCS_PREFILTER_RUN 32        // ncu launch lists, 1192 C2 levels x 2 components, lat + lon pass: runs of 32 uncapped (96 registers)
-                                    // 1.31 + 1.37 ms; runs of 24 capped at 64 registers (1024 threads per SM) 1.40 + 1.45 ms
+#define LCS_PREFILTER_RUN 32        // ncu launch lists, 1192 C2 levels x 2 components, lat + lon pass: runs of 32 at 96 registers
+                                    // 1.31 + 1.37 / 1.45 + 1.50 ms on two boxes; runs of 24 capped at 64 registers 1.40 + 1.45 ms
 #endif
 constexpr int KQ = LCS_PREFILTER_RUN;    // outputs per thread in the recursive form
 
