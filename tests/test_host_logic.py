@@ -189,3 +189,29 @@ def test_bench_reference_arm_line_has_the_contract_keys():
     assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': d['unit'], 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert 'workload' in d['config'] and d['vs_baseline'] is None
+
+
+def test_regrid_axis_plan_reproduces_interp1d_and_nearest():
+    """regrid.axis_plan feeds lcs_regrid_linear_nearest; applied in numpy with the kernel's arithmetic (w_hi*y_hi + w_lo*y_lo,
+    NaN outside the source range, nearest-label fill) it must equal scipy's interp1d + pandas' nearest reindex bit for bit,
+    on irregular ascending coordinates, targets outside the range, and targets that hit source points exactly."""
+    import pandas as pd
+    from scipy.interpolate import interp1d
+    from lagrangiancoherence_b200.regrid import axis_plan, common_grid
+    rng = np.random.default_rng(7)
+    for n_src, n_dst in ((5, 40), (89, 360), (180, 721), (2, 9)):
+        src = np.sort(rng.uniform(-80, 80, n_src))
+        src[1:] += np.arange(1, n_src) * 1e-3                      # strictly ascending
+        dst = np.sort(np.concatenate([rng.uniform(-95, 95, n_dst - 3), src[:2], [src[-1]]]))
+        y = rng.normal(size=(3, n_src))
+        lo, w_hi, w_lo, valid, near = axis_plan(src, dst)
+        got = w_hi * y[:, lo + 1] + w_lo * y[:, lo]
+        got = np.where(valid.astype(bool), got, np.nan)
+        got = np.where(np.isnan(got), y[:, near], got)
+        ref = interp1d(src, y, kind='linear', axis=1, bounds_error=False, fill_value=np.nan, assume_sorted=True)(dst)
+        ref = np.where(np.isnan(ref), y[:, pd.Index(src).get_indexer(dst, method='nearest')], ref)
+        assert np.array_equal(got, ref)
+    lats, lons = common_grid()
+    assert lats.size == 360 and lons.size == 721 and lats[0] == -89.75 and lons[-1] == 179.5     # LCS.py:106-107
+    with pytest.raises(ValueError):
+        axis_plan([0.0, 0.0, 1.0], [0.5])
