@@ -108,3 +108,21 @@ def test_nan_derivative_drops_the_point_and_inf_raises():
     dt[0, 5, 5] = np.inf
     with pytest.raises(ValueError):
         O.spectral_norm_field(dt)
+
+
+@pytest.mark.parametrize('order', [1, 2, 3, 4, 5])
+def test_displacement_law_holds_for_every_spline_order(order):
+    """B-spline interpolation of any order reproduces a constant field exactly (weights sum to one, prefilter has unit
+    DC gain), so the (1+S) displacement law of uniform flow does not depend on `traj_interp_order`; what does is the
+    number of pole rows (first/last `order` arrival rows sample with order 1/'constant', tools.py:31-39)."""
+    lat, lon = np.linspace(-30.0, 0.0, 31), np.linspace(-180.0, 180.0, 73)
+    nt, U0, dt, S_ = 3, 5.0, 3600.0, 2
+    u = np.full((nt, lat.size, lon.size), U0)
+    x, y = O.parcel_propagation(u, np.zeros_like(u), lat, lon, dt, SETTLS_order=S_, interp_order=order, xclamp='pointwise')
+    cx, _ = O.conversions(lat)
+    X, Y = np.meshgrid(lon, lat)
+    expect = X + (1 + S_) * (nt - 1) * dt * U0 * cx[:, None]
+    inner = np.s_[order:-order, 2:-12]
+    assert np.array_equal(y, Y)
+    assert np.abs(x[inner] - expect[inner]).max() <= 1e-9
+    assert np.array_equal(x[-1], X[-1])                    # the last row's index is nlat > nlat-1: samples 0, never moves (Q4)
