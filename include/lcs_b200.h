@@ -26,9 +26,10 @@
 extern "C" {
 #endif
 
-#define LCS_ABI_VERSION 2
+#define LCS_ABI_VERSION 3
 
-enum { LCS_OK = 0, LCS_E_INVALID = -1, LCS_E_CUDA = -2, LCS_E_WORKSPACE = -3, LCS_E_UNSUPPORTED = -4 };
+enum { LCS_OK = 0, LCS_E_INVALID = -1, LCS_E_CUDA = -2, LCS_E_WORKSPACE = -3, LCS_E_UNSUPPORTED = -4,
+       LCS_E_TIMEOUT = -5 };
 enum { LCS_F64 = 0, LCS_F32 = 1 };
 /* device layouts of a staged wind series, see lcs_pack_pairs / lcs_pack_es */
 enum { LCS_LAYOUT_PAIR4 = 0, LCS_LAYOUT_ES = 1 };
@@ -41,6 +42,14 @@ enum { LCS_ARITH_F64 = 0,         /* weights, products and sums in f64 whatever 
 enum { LCS_X_CYCLIC = 0,          /* cyclic_xboundary=True: the two `where` with Python-sign % 180 */
        LCS_X_CLAMP_POINTWISE = 1, /* per-particle clamp to [lon_min, lon_max] */
        LCS_X_CLAMP_OUTER = 2 };   /* as executed: xarray orthogonal assignment (rows x cols having any exit) */
+
+/* Halo of the LCS_LAYOUT_ES arrays: every level is stored as (nlat + LO + HI) x (nlon + LO + HI) elements, grid point
+ * (i, j) at row i + LO, column j + LO, and the halo cells hold the mirror-reflected values (scipy's spline boundary
+ * d c b | a b c d | c b a), so a gather never reflects a tap index.  2 + 3 covers the tap range [-2, n+2] of every
+ * spline order up to 5 after the coordinate fold. */
+#define LCS_HALO_LO 2
+#define LCS_HALO_HI 3
+#define LCS_ES_LEVEL_ELEMS(nlat, nlon) ((size_t)((nlat) + LCS_HALO_LO + LCS_HALO_HI) * (size_t)((nlon) + LCS_HALO_LO + LCS_HALO_HI))
 
 /* Wind grid; min/max are coord.min()/coord.max() used by the index map of tools.py:19-22. */
 typedef struct lcs_grid {
@@ -78,8 +87,9 @@ typedef struct lcs_advect_opts {
 /* Staged winds handed to the integrator.
  *   LCS_LAYOUT_PAIR4: raw_a / coef_a = pairs[k][lat][lon] = (u_k, v_k, u_{k+1}, v_{k+1}), k < nlev-1;
  *                     raw_b / coef_b unused.
- *   LCS_LAYOUT_ES   : raw_a / coef_a = E[k][lat][lon] = (u_k, v_k), k < nlev;
- *                     raw_b / coef_b = S[k][lat][lon] = (2u_k - u_{k+1}, 2v_k - v_{k+1}), k < nlev-1.
+ *   LCS_LAYOUT_ES   : raw_a / coef_a = E[k] = (u_k, v_k), k < nlev;
+ *                     raw_b / coef_b = S[k] = (2u_k - u_{k+1}, 2v_k - v_{k+1}), k < nlev-1;
+ *                     each level in the halo layout above (LCS_ES_LEVEL_ELEMS elements per level).
  * raw_* hold the winds themselves (order-1 pole rows, or interp_order == 1); coef_* their cubic
  * B-spline coefficients (interp_order == 3, else NULL).  dtype is the element storage type. */
 typedef struct lcs_winds {
@@ -121,7 +131,8 @@ int lcs_pack_pairs(const void* u, const void* v, int in_dtype, void* pairs, int 
  * (trajectory.py:110-112); interpolation is linear in the field, so the combination is formed once
  * per grid point: E[k] = (u_k, v_k) for k < nlev and S[k] = (2u_k - u_{k+1}, 2v_k - v_{k+1}) for
  * k < nlev-1 (evaluated in f64, then stored as es_dtype).  A SETTLS stage then gathers 16 B (f64)
- * per tap instead of 32 B. */
+ * per tap instead of 32 B.  Levels are written in the halo layout: e_out holds nlev and s_out nlev-1 levels of
+ * LCS_ES_LEVEL_ELEMS(nlat, nlon) two-value elements. */
 int lcs_pack_es(const void* u, const void* v, int in_dtype, void* e_out, void* s_out, int es_dtype,
                 int nlev, int nlat, int nlon, void* stream);
 
@@ -153,12 +164,19 @@ int lcs_regrid_linear_nearest(const void* in, int in_dtype, int nlev, int nlat_s
  *   x_traj,y_traj: NULL, or device f64 [nwindows][nsteps+1][nrow][ncol] (level 0 = start grid,
  *                  trajectory.py:76-77,125-126)
  *   workspace : device scratch of lcs_advect_workspace_bytes() bytes (only LCS_X_CLAMP_OUTER
- *               needs any: positions, Euler samples and per-sub-step row/column exit flags) */
+ *               needs any: positions, Euler samples and per-sub-step row/column exit flags of the
+ *               windows in flight -- a few dozen at most, not of every window of the call) */
 size_t lcs_advect_workspace_bytes(const lcs_particles* p, const lcs_advect_opts* o);
 int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_advect_opts* o,
                const lcs_winds* w,
                double* x_out, double* y_out, double* x_traj, double* y_traj,
                void* workspace, size_t workspace_bytes, void* stream);
+
+/* The outer-clamp kernel synchronises the CTAs that share a window through barriers in global memory; a barrier
+ * that is not completed within ~10 s gives up instead of hanging the device and records that in the workspace.
+ * lcs_advect_check synchronises `stream` and returns LCS_E_TIMEOUT if that happened in the last lcs_advect call
+ * that used `workspace` (LCS_OK otherwise, and for the other x-boundary modes). */
+int lcs_advect_check(const void* workspace, void* stream);
 
 /* ---------------------------------------------------------------- fused epilogue
  * lcs_ftle_epilogue replaces flowmap_gradient (LCS.py:171-225), the six

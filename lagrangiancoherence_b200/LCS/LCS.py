@@ -95,15 +95,18 @@ class LCS:
         if isinstance(self.gauss_sigma, (float, int)):               # LCS.py:187-190 (inside flowmap_gradient upstream)
             xs, ys = engine.gaussian(x_dep, self.gauss_sigma), engine.gaussian(y_dep, self.gauss_sigma)
         latkeep = lonkeep = None
-        out_rows = None
+        out_rows = mask = None
         if isinstance(self.subdomain, dict):                         # LCS.py:143-144 (crop after the derivatives)
             latkeep = _crop_index(lat, self.subdomain.get('latitude'))
             lonkeep = _crop_index(lon, self.subdomain.get('longitude'))
             rows = np.flatnonzero(latkeep)
             if rows.size:
-                out_rows = (int(rows[0]), int(rows[-1]) + 1)         # only these rows are computed
+                out_rows = (int(rows[0]), int(rows[-1]) + 1)         # only these rows are computed ...
+                # ... and only the kept points are checked for inf: upstream crops before dropna / norm (LCS.py:143-154)
+                mask = np.outer(latkeep[out_rows[0]:out_rows[1]], lonkeep)
         verboseprint("*---- Computing eigenvalues ----*")
-        sigma = engine.epilogue(xs, ys, out_rows=out_rows)
+        engine.reset_status()
+        sigma = engine.epilogue(xs, ys, out_rows=out_rows, mask=mask)
         engine.check_finite()                                        # ValueError on inf, as scipy.linalg.norm (LCS.py:154)
         sigma = sigma[0].cpu().numpy()
         verboseprint("*---- Done eigenvalues ----*")
@@ -165,8 +168,9 @@ def drop_unused_levels(sigma, lat, lon):
 
 def flowmap_gradient(x_departure, y_departure, sigma=None, *, device='cuda:0'):
     """The nine stacked 'derivatives' ``(derivatives, latitude, longitude)`` of LCS.py:171-225."""
-    xd = x_departure.transpose('latitude', 'longitude')
-    yd = y_departure.transpose('latitude', 'longitude')
+    # derivative_spherical_coords sorts by latitude, then longitude (tools.py:251-252)
+    xd = x_departure.sortby('latitude').sortby('longitude').transpose('latitude', 'longitude')
+    yd = y_departure.sortby('latitude').sortby('longitude').transpose('latitude', 'longitude')
     lat, lon = coord_values(xd, 'latitude'), coord_values(xd, 'longitude')
     engine = FtleEngine(lat, lon, 1, device=device)
     dev = torch.device(device)

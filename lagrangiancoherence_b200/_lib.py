@@ -14,7 +14,8 @@ LCS_F64, LCS_F32 = 0, 1
 LCS_X_CYCLIC, LCS_X_CLAMP_POINTWISE, LCS_X_CLAMP_OUTER = 0, 1, 2
 LCS_LAYOUT_PAIR4, LCS_LAYOUT_ES = 0, 1
 LCS_ARITH_F64, LCS_ARITH_F32 = 0, 1
-ABI_VERSION = 2
+LCS_HALO_LO, LCS_HALO_HI = 2, 3          # include/lcs_b200.h
+ABI_VERSION = 3
 
 c_void_p, c_int, c_double, c_size_t, c_int64 = C.c_void_p, C.c_int, C.c_double, C.c_size_t, C.c_int64
 
@@ -55,6 +56,7 @@ SIGNATURES = {
     'lcs_regrid_linear_nearest': (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 10 + [c_int, c_int, c_void_p, c_void_p]),
     'lcs_gaussian_filter2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     'lcs_advect_workspace_bytes': (c_size_t, [C.POINTER(Particles), C.POINTER(AdvectOpts)]),
+    'lcs_advect_check': (c_int, [c_void_p, c_void_p]),
     'lcs_pack_es': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'lcs_advect': (c_int, [C.POINTER(Grid), C.POINTER(Particles), C.POINTER(AdvectOpts), C.POINTER(Winds),
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

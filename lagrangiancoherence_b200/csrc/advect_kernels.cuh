@@ -1,0 +1,1011 @@
+// Departure-point integrator: parcel_propagation's loop (trajectory.py:80-126) with the
+// xr_map_coordinates calls inside it (tools.py:11-41) as CUDA kernels for sm_100a.
+//
+// Two launch shapes share the same stage functions:
+//  * advect_fused_kernel  -- one thread per particle carries it across every wind interval and
+//    SETTLS sub-iteration (cyclic / pointwise x-boundary, where particles are independent);
+//  * advect_phase_*       -- the as-executed outer-product x-clamp (quirk Q6) couples all
+//    particles of a window after every sub-step, so each sub-step is a pair of launches that
+//    meet through per-substep row/column exit flags.
+//
+// Data, two layouts (include/lcs_b200.h):
+//  * PAIR4: pairs[k][lat][lon] = (u_k, v_k, u_{k+1}, v_{k+1}); one 32-B (f64) vector load per tap
+//    feeds the four operands of a SETTLS stage, which are combined in the reference's order
+//    (bit-faithful `strict` evaluation is only offered here);
+//  * ES   : E[k] = (u_k, v_k) and S[k] = (2u_k - u_{k+1}, 2v_k - v_{k+1}); a SETTLS stage needs one
+//    16-B load per tap -- the kernel is bound by L1 data-pipe wavefronts (ncu: 79 % of peak with
+//    PAIR4), so halving the bytes per tap is the lever that matters.
+// Positions stay in registers in the fused kernel.  Gathers go through the read-only L1 path (L1
+// hit rate 91 %, L2 throughput 5 % in ncu: staging tiles through shared memory/TMA would move the
+// same bytes through the same 128 B/clk port and was not pursued).
+#pragma once
+#include <cooperative_groups.h>
+#include <stdio.h>
+#include <mutex>
+#include "lcs_internal.h"
+#include "lcs_device.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace lcs {
+
+struct AdvectParams {
+    // winds: PAIR4 layout -> raw_a/coef_a = packed pairs; ES layout -> *_a = E levels, *_b = S intervals
+    const void* raw_a;
+    const void* raw_b;
+    int raw_planar;               // ES layout, orders >= 2: raw_a / raw_b are the planar u / v series themselves
+    int raw_f32;                  //   ... stored as f32 (else f64)
+    const void* coef_a;
+    const void* coef_b;
+    size_t plane;                 // nlat*nlon (elements per level of the dense arrays: PAIR4 pairs, planar raw winds)
+    size_t plane_es;              // elements per level of the ES arrays (halo layout, include/lcs_b200.h)
+    int halo_off;                 // offset of grid point (0, 0) inside an ES level
+    int nlat, nlon;
+    double nlat_d, nlon_d;
+    double lat_min, lat_span, lon_min, lon_span, lat_max, lon_max;
+    double nlat_over_span, nlon_over_span;
+    // particles
+    int nrow, ncol, row0, nrow_global;
+    int np;                       // nrow*ncol (< 2^31)
+    const double* lat;
+    const double* lon;
+    const double* kx;
+    const double* hx;
+    double ky, hy;
+    int nsteps, S, xmode, level0, level_stride, band, band_log2;
+    double* x_out;
+    double* y_out;
+    double* x_traj;
+    double* y_traj;
+    // phased (outer clamp) state, indexed by the particle's enumeration index p
+    d2* spos;                     // [nwindows][np] (x, y)
+    d2* swind;                    // [nwindows][np] (ua, va) of the interval's Euler stage
+    int* cand;                    // [nwindows][np] particles with x > lon_max after the current sub-step
+    int* cand_count;              // [nwindows][nsub]
+    unsigned char* flags;         // [nwindows][nsub][2][nrow+ncol]
+    int nsub;
+    int nslots, ntc;                       // persistent kernel: slots per window (tiles of 2x16), tile columns
+    unsigned ntc_magic; int ntc_shift;     // tile / ntc as a multiply-high, see slot_rc
+};
+
+constexpr int kPair4 = LCS_LAYOUT_PAIR4, kES = LCS_LAYOUT_ES;
+constexpr int kES32 = 2;     // internal: ES layout of f32 elements with the cubic taps evaluated in f32 (LCS_ARITH_F32)
+template <typename T, int LAYOUT> struct EsPolicy { using type = Vec2<T>; };
+template <> struct EsPolicy<float, kES32> { using type = Vec2F32Arith; };
+
+// Thread -> particle: a block is a (band x 256/band) tile of the particle grid, a warp a
+// (band x 32/band) patch (smaller unique tap footprint than a 1x32 strip: better L1 hit rate);
+// grid = (column tiles, row bands, windows), so no integer division is needed.
+// STRIP: block = 8 rows x 32 columns, warp = one row of 32 particles with the block's warps stacked (they share tap
+// rows).  Measured against the 2 x 16 patches: the same at C2 (14.3 ms), 4 % slower with f32 taps, 3 % faster with hourly
+// winds (C4) and 18-21 % faster on the 721 x 1440 grid (C3: 3.17 vs 4.00 ms for four 12-interval windows), where the
+// compact block keeps its taps in L1 while the 2 x 128 strip of the default mapping does not.  Chosen by launch_advect.
+template <bool STRIP = false>
+__device__ __forceinline__ bool particle_rc(const AdvectParams& P, int& row, int& col) {
+    if (STRIP) {
+        row = blockIdx.y * 8 + (threadIdx.x >> 5);
+        col = blockIdx.x * 32 + (threadIdx.x & 31);
+        return row < P.nrow && col < P.ncol;
+    }
+    const int r = threadIdx.x & (P.band - 1);
+    const int c = threadIdx.x >> P.band_log2;
+    row = blockIdx.y * P.band + r;
+    col = blockIdx.x * (256 >> P.band_log2) + c;
+    return row < P.nrow && col < P.ncol;
+}
+
+// One xr_map_coordinates evaluation (tools.py:19-41) of the element policy E at (x, y):
+// index map, then the order-1/'constant' branch on pole rows, else order ORDER/'wrap'.
+template <typename E, bool STRICT, int ORDER>
+__device__ __forceinline__ void sample(const AdvectParams& P, const void* raw, const void* coef, int level,
+                                       bool pole, double x, double y, double (&out)[E::NV]) {
+    using ET = typename E::type;
+    double iy, ix;
+    if (STRICT) {
+        iy = index_map(y, P.lat_min, P.lat_span, P.nlat_d);
+        ix = index_map(x, P.lon_min, P.lon_span, P.nlon_d);
+    } else {
+        iy = index_map_fast(y, P.lat_min, P.nlat_over_span);
+        ix = index_map_fast(x, P.lon_min, P.nlon_over_span);
+    }
+    const size_t lvl = E::HALO ? (size_t)level * P.plane_es + P.halo_off : (size_t)level * P.plane;
+    if (pole) {
+        gather_linear_constant<E, STRICT>(reinterpret_cast<const ET*>(raw) + lvl, P.nlat, P.nlon, iy, ix, out);
+    } else if (ORDER == 3) {
+        if constexpr (E::A32) gather_cubic_wrap_f32(reinterpret_cast<const ET*>(coef) + lvl, P.nlat, P.nlon, iy, ix, out);
+        else gather_cubic_wrap<E, STRICT>(reinterpret_cast<const ET*>(coef) + lvl, P.nlat, P.nlon, iy, ix, out);
+    } else if (ORDER == 1) {
+        gather_linear_wrap<E, STRICT>(reinterpret_cast<const ET*>(raw) + lvl, P.nlat, P.nlon, iy, ix, out);
+    } else {
+        if constexpr (ORDER == 2 || ORDER == 4 || ORDER == 5)
+            gather_spline_wrap<E, STRICT, ORDER>(reinterpret_cast<const ET*>(coef) + lvl, P.nlat, P.nlon, iy, ix, out);
+    }
+}
+
+// Pole rows of the spline orders (>= 2) sample the winds themselves with order 1 / 'constant' (tools.py:31-39).
+// Those are 2*ORDER particle rows out of hundreds.  With `raw_planar` the ES layout does not pack a second copy of
+// the series for them: they read the planar u, v input directly -- tap offsets and weights once, then four scalar
+// taps per field.  SETTLS = true returns 2 f_k(pos) - f_{k+1}(pos) from two separate samples, which is the
+// reference's own order (trajectory.py:105-112).  Saves a third of the staging traffic at no measurable integrator
+// cost (a first version that called the generic bilinear gather four times cost 2.7 %).
+template <typename TR, bool SETTLS>
+__device__ __forceinline__ void pole_taps_planar(const TR* __restrict__ u, const TR* __restrict__ v, size_t plane,
+                                                 const int (&off)[4], const double (&w)[4], double (&out)[2]) {
+    double su = 0.0, sv = 0.0, su1 = 0.0, sv1 = 0.0;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        su = fma((double)__ldg(u + off[t]), w[t], su);
+        sv = fma((double)__ldg(v + off[t]), w[t], sv);
+        if (SETTLS) {
+            su1 = fma((double)__ldg(u + plane + off[t]), w[t], su1);
+            sv1 = fma((double)__ldg(v + plane + off[t]), w[t], sv1);
+        }
+    }
+    out[0] = SETTLS ? 2.0 * su - su1 : su;
+    out[1] = SETTLS ? 2.0 * sv - sv1 : sv;
+}
+
+template <bool SETTLS>
+__device__ __forceinline__ void pole_sample_planar(const AdvectParams& P, int k, double x, double y, double (&out)[2]) {
+    const double iy = index_map_fast(y, P.lat_min, P.nlat_over_span);
+    const double ix = index_map_fast(x, P.lon_min, P.nlon_over_span);
+    out[0] = 0.0; out[1] = 0.0;
+    if (!(iy >= 0.0 && iy <= (double)(P.nlat - 1) && ix >= 0.0 && ix <= (double)(P.nlon - 1))) return;   // mode='constant', cval 0
+    const double fy = floor(iy), fx = floor(ix);
+    const double wy0 = 1.0 - (iy - fy), wx0 = 1.0 - (ix - fx);
+    const double wy1 = 1.0 - wy0, wx1 = 1.0 - wx0;                   // scipy: last weight = 1 - sum(others)
+    const int r0 = (int)fy, c0 = (int)fx;
+    const int r1 = mirror_near(r0 + 1, P.nlat), c1 = mirror_near(c0 + 1, P.nlon);
+    const int off[4] = {r0 * P.nlon + c0, r0 * P.nlon + c1, r1 * P.nlon + c0, r1 * P.nlon + c1};
+    const double w[4] = {wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1};
+    const size_t o = (size_t)k * P.plane;
+    if (P.raw_f32) pole_taps_planar<float, SETTLS>(static_cast<const float*>(P.raw_a) + o, static_cast<const float*>(P.raw_b) + o, P.plane, off, w, out);
+    else pole_taps_planar<double, SETTLS>(static_cast<const double*>(P.raw_a) + o, static_cast<const double*>(P.raw_b) + o, P.plane, off, w, out);
+}
+
+// Euler stage, trajectory.py:82-87 (samples level k only), boundaries excluded.
+template <typename T, bool STRICT, int ORDER, int LAYOUT>
+__device__ __forceinline__ void stage_euler(const AdvectParams& P, int k, bool pole, double kx,
+                                            double& x, double& y, double& ua, double& va) {
+    double s[2];
+    if (LAYOUT == kPair4) sample<Pair4Lo<T>, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, s);
+    else if (ORDER >= 2 && pole && P.raw_planar) pole_sample_planar<false>(P, k, x, y, s);
+    else sample<typename EsPolicy<T, LAYOUT>::type, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, s);
+    ua = s[0]; va = s[1];
+    y = __dadd_rn(y, __dmul_rn(P.ky, va));
+    x = __dadd_rn(x, __dmul_rn(kx, ua));
+}
+
+// SETTLS stage, trajectory.py:105-112: pos += 0.5*dt*conv*(va + 2*v_k(pos) - v_{k+1}(pos)).
+// PAIR4: the four samples are taken separately and combined in the reference's order.
+// ES   : interpolation is linear in the field, so S_k = 2*c_k - c_{k+1} is combined once per grid
+//        point at staging time and a single 2-value sample yields 2*v_k(pos) - v_{k+1}(pos):
+//        half the gather bytes and half the FMAs of the stage (results differ by rounding only).
+template <typename T, bool STRICT, int ORDER, int LAYOUT>
+__device__ __forceinline__ void stage_settls(const AdvectParams& P, int k, bool pole, double hx,
+                                             double ua, double va, double& x, double& y) {
+    if (LAYOUT == kPair4) {
+        double s[4];
+        sample<Pair4<T>, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, s);
+        y = __dadd_rn(y, __dmul_rn(P.hy, __dsub_rn(__dadd_rn(va, __dmul_rn(2.0, s[1])), s[3])));
+        x = __dadd_rn(x, __dmul_rn(hx, __dsub_rn(__dadd_rn(ua, __dmul_rn(2.0, s[0])), s[2])));
+    } else {
+        double s[2];
+        if (ORDER >= 2 && pole && P.raw_planar) pole_sample_planar<true>(P, k, x, y, s);
+        else sample<typename EsPolicy<T, LAYOUT>::type, STRICT, ORDER>(P, P.raw_b, P.coef_b, k, pole, x, y, s);
+        y = __dadd_rn(y, __dmul_rn(P.hy, __dadd_rn(va, s[1])));
+        x = __dadd_rn(x, __dmul_rn(hx, __dadd_rn(ua, s[0])));
+    }
+}
+
+__device__ __forceinline__ void bounds_local(const AdvectParams& P, double& x, double& y) {
+    y = clamp_y(y, P.lat_min, P.lat_max);
+    if (P.xmode == LCS_X_CYCLIC) x = wrap_x_cyclic(x);
+    else x = clamp_x_pointwise(x, P.lon_min, P.lon_max);
+}
+
+// ---------------------------------------------------------------------------------------------
+#ifndef LCS_FUSED_MINBLOCKS
+#define LCS_FUSED_MINBLOCKS 4       // 64 registers, 1024 threads per SM (measured against 3 and 2 blocks: see DESIGN.md)
+#endif
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool STRIP = false>
+__global__ void __launch_bounds__(256, LCS_FUSED_MINBLOCKS)
+advect_fused_kernel(const AdvectParams P) {
+    const int w = blockIdx.z;
+    int row, col;
+    if (!particle_rc<STRIP>(P, row, col)) return;
+    const int grow = P.row0 + row;
+    const bool pole = (grow < ORDER) || (grow >= P.nrow_global - ORDER);   // tools.py:31-33
+    const double kx = __ldg(P.kx + row), hx = __ldg(P.hx + row);
+    double x = __ldg(P.lon + col), y = __ldg(P.lat + row);                 // trajectory.py:68-70
+    const size_t o = (size_t)row * P.ncol + col;
+    const size_t wnp = (size_t)w * P.np;
+    double* xt = P.x_traj ? P.x_traj + wnp * (P.nsteps + 1) + o : nullptr;
+    double* yt = P.y_traj ? P.y_traj + wnp * (P.nsteps + 1) + o : nullptr;
+    if (xt) { xt[0] = x; yt[0] = y; }
+    const int pair0 = P.level0 + w * P.level_stride;
+    for (int t = 0; t < P.nsteps; ++t) {
+        double ua, va;
+        stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair0 + t, pole, kx, x, y, ua, va);
+        bounds_local(P, x, y);
+        for (int k = 0; k < P.S; ++k) {
+            stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair0 + t, pole, hx, ua, va, x, y);
+            bounds_local(P, x, y);
+        }
+        if (xt) { xt[(size_t)(t + 1) * P.np] = x; yt[(size_t)(t + 1) * P.np] = y; }
+    }
+    P.x_out[wnp + o] = x;
+    P.y_out[wnp + o] = y;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Outer-product clamp (trajectory.py:96-97 / 122-123).  `px[np.where(px < x_min)] = x_min` on a
+// DataArray is an ORTHOGONAL assignment: every (row, col) with row in {rows holding an exit} and
+// col in {columns holding an exit} is set, then the same for x_max on the updated array.  This
+// couples all particles of a window after every sub-step, so a sub-step q is
+//   move(q)  : apply the pending x_min / x_max passes of q-1 (flags are complete by then), run the
+//              stage, clamp y, store the state, raise the (row, col) "<x_min" flags of q and append
+//              particles with x > x_max to the window's candidate list;
+//   gtpass(q): tiny launch over the candidates: x' = x_min if rowflag&colflag, and if still
+//              x' > x_max raise the ">x_max" flags of q.
+// Flags of sub-step q, window w: flags + ((w*nsub + q)*2 + which)*(nrow+ncol); bytes [0,nrow) rows,
+// [nrow,nrow+ncol) columns.  Flags and candidate counters start at zero (cleared by lcs_advect).
+__device__ __forceinline__ unsigned char* flag_slot(const AdvectParams& P, int w, int q, int which) {
+    return P.flags + ((size_t)((size_t)w * P.nsub + q) * 2 + which) * (size_t)(P.nrow + P.ncol);
+}
+
+__device__ __forceinline__ double apply_pending(const AdvectParams& P, int w, int q_prev, int row, int col, double x) {
+    const unsigned char* lt = flag_slot(P, w, q_prev, 0);
+    const unsigned char* gt = flag_slot(P, w, q_prev, 1);
+    if (lt[row] && lt[P.nrow + col]) x = P.lon_min;           // trajectory.py:96
+    if (gt[row] && gt[P.nrow + col]) x = P.lon_max;           // trajectory.py:97
+    return x;
+}
+
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool STRIP = false>
+__global__ void __launch_bounds__(256)
+advect_phase_move(const AdvectParams P, int q /* global sub-step index */, int t /* interval */, int k /* 0: Euler */) {
+    const int w = blockIdx.z;
+    int row, col;
+    if (!particle_rc<STRIP>(P, row, col)) return;
+    const int p = row * P.ncol + col;
+    const int grow = P.row0 + row;
+    const bool pole = (grow < ORDER) || (grow >= P.nrow_global - ORDER);
+    const size_t o = (size_t)w * P.np + p;
+    double x, y;
+    if (q == 0) {
+        x = __ldg(P.lon + col); y = __ldg(P.lat + row);
+    } else {
+        const d2 s = P.spos[o];
+        x = apply_pending(P, w, q - 1, row, col, s.x); y = s.y;
+    }
+    if (k == 0 && P.x_traj) {                         // level t is final once the pending passes ran
+        const size_t to = ((size_t)w * (P.nsteps + 1) + t) * P.np + p;
+        P.x_traj[to] = x; P.y_traj[to] = y;
+    }
+    const int pair = P.level0 + w * P.level_stride + t;
+    if (k == 0) {
+        double ua, va;
+        stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
+        d2 e; e.x = ua; e.y = va;
+        P.swind[o] = e;
+    } else {
+        const d2 e = P.swind[o];
+        stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.hx + row), e.x, e.y, x, y);
+    }
+    y = clamp_y(y, P.lat_min, P.lat_max);
+    d2 s; s.x = x; s.y = y;
+    P.spos[o] = s;
+    if (x < P.lon_min) {
+        unsigned char* f = flag_slot(P, w, q, 0);
+        f[row] = 1; f[P.nrow + col] = 1;
+    } else if (x > P.lon_max) {
+        const int slot = atomicAdd(P.cand_count + (size_t)w * P.nsub + q, 1);
+        P.cand[(size_t)w * P.np + slot] = p;
+    }
+}
+
+static __global__ void __launch_bounds__(256)
+advect_phase_gtpass(const AdvectParams P, int q) {
+    const int w = blockIdx.y;
+    const int n = P.cand_count[(size_t)w * P.nsub + q];
+    const unsigned char* lt = flag_slot(P, w, q, 0);
+    unsigned char* gt = flag_slot(P, w, q, 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int p = P.cand[(size_t)w * P.np + i];
+        const int row = p / P.ncol, col = p - row * P.ncol;
+        // x > lon_max here; it survives the x_min pass unless its row and column both hold an exit
+        if (!(lt[row] && lt[P.nrow + col])) { gt[row] = 1; gt[P.nrow + col] = 1; }
+    }
+}
+
+static __global__ void __launch_bounds__(256)
+advect_phase_final(const AdvectParams P) {
+    const int w = blockIdx.z;
+    int row, col;
+    if (!particle_rc(P, row, col)) return;
+    const int p = row * P.ncol + col;
+    double x, y;
+    if (P.nsub == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
+    else {
+        const d2 s = P.spos[(size_t)w * P.np + p];
+        x = apply_pending(P, w, P.nsub - 1, row, col, s.x); y = s.y;
+    }
+    const size_t o = (size_t)p;
+    P.x_out[(size_t)w * P.np + o] = x; P.y_out[(size_t)w * P.np + o] = y;
+    if (P.x_traj) {
+        const size_t to = ((size_t)w * (P.nsteps + 1) + P.nsteps) * P.np + o;
+        P.x_traj[to] = x; P.y_traj[to] = y;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Outer-product clamp, persistent form: one thread-block CLUSTER owns one window for its whole
+// integration.  The cluster's threads stride over the window's particles (state in an L2-resident
+// per-window array, touched only by its owner thread), and the two global dependencies of every
+// sub-step -- "rows/columns holding an exit below x_min" and, after that pass, "... above x_max" --
+// are resolved with hardware cluster barriers (barrier.cluster, ~0.2 us) instead of kernel
+// boundaries.  A cluster of 1 degenerates to __syncthreads().  The exit flags of the current
+// sub-step are mirrored into shared memory after each barrier so the per-particle tests are LDS.
+#ifndef LCS_CLUSTER_THREADS
+#define LCS_CLUSTER_THREADS 512
+#endif
+constexpr int kClusterThreads = LCS_CLUSTER_THREADS;   // multiple of 32: a warp owns whole 2x16 tiles
+
+// Slot enumeration of a window for the persistent kernel: warp-sized tiles of 2 rows x 16 columns
+// (6 L1 wavefronts per 16-B gather request instead of 8 for a 4x8 patch, better hit rate than a 1x32
+// strip); slot e -> tile e>>5, lane e&31.  Slots past the grid edge are idle.
+__device__ __forceinline__ bool slot_rc(const AdvectParams& P, int e, int& row, int& col) {
+    const int tile = e >> 5, lane = e & 31;
+    const int tr = P.ntc_magic ? (int)(__umulhi((unsigned)tile, P.ntc_magic) >> P.ntc_shift) : (tile >> P.ntc_shift);
+    const int tc = tile - tr * P.ntc;
+    row = tr * 2 + (lane >> 4);
+    col = tc * 16 + (lane & 15);
+    return row < P.nrow && col < P.ncol;
+}
+
+template <bool CLUSTERED>
+__device__ __forceinline__ void window_sync() {
+    if (CLUSTERED) cg::this_cluster().sync();  // release/acquire at cluster scope: global writes become visible
+    else __syncthreads();
+}
+
+// phase A of one sub-step for the slots owned by this thread.  Everything that is uniform over the CTA
+// (window, sub-step, array bases) is re-derived from the constant bank where it is used instead of being
+// carried in registers across the gathers: at 64 registers the first version spilled its loop-invariant
+// pointers and its prefetched state (ncu: local-memory wavefronts = 25 % of the global-load wavefronts).
+#ifndef LCS_CLUSTER_PREFETCH
+#define LCS_CLUSTER_PREFETCH 2      // 0 none, 1 into L1, 2 into L2 (measured: see DESIGN.md)
+#endif
+__device__ __forceinline__ void prefetch_state(const void* p) {
+#if LCS_CLUSTER_PREFETCH == 1
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#elif LCS_CLUSTER_PREFETCH == 2
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#endif
+}
+
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+// state access policy of the persistent kernel (LCS_CLUSTER_STATE_LD: 0 = ld.cs/st.cs evict-first,
+// 1 = loads that do not allocate in L1, so the L1 keeps the wind taps)
+#ifndef LCS_CLUSTER_STATE_LD
+#define LCS_CLUSTER_STATE_LD 0
+#endif
+__device__ __forceinline__ double2 ld_state(const double2* p) {
+#if LCS_CLUSTER_STATE_LD == 1
+    double2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+#else
+    return __ldcs(p);
+#endif
+}
+
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool EULER>
+__device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, const int w, const int q, const int t,
+                                                const int tid_w, const int nthr_w,
+                                                const unsigned char* s_f) {
+    const unsigned sbase = (unsigned)w * (unsigned)P.nslots;        // host guarantees nwindows*nslots < 2^32
+    for (int e = tid_w; e < P.nslots; e += nthr_w) {
+        double2* const ps = reinterpret_cast<double2*>(P.spos) + (sbase + (unsigned)e);
+        double2* const pw = reinterpret_cast<double2*>(P.swind) + (sbase + (unsigned)e);
+        if (e + nthr_w < P.nslots) {                                 // next slot's state: L2 by the time it is needed
+            if (q != 0) prefetch_state(ps + nthr_w);
+            if (!EULER) prefetch_state(pw + nthr_w);
+        }
+        int row, col;
+        if (!slot_rc(P, e, row, col)) continue;
+        const int grow = P.row0 + row;
+        const bool pole = (grow < ORDER) || (grow >= P.nrow_global - ORDER);
+        double x, y;
+        if (q == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
+        else {
+            const double2 s = ld_state(ps);
+            x = s.x; y = s.y;
+            const unsigned m = (unsigned)s_f[row] & (unsigned)s_f[P.nrow + col];   // bit 0: "< x_min" pass, bit 1: "> x_max" pass
+            if (m & 1u) x = P.lon_min;                               // trajectory.py:96
+            if (m & 2u) x = P.lon_max;                               // trajectory.py:97
+        }
+        const int pair = P.level0 + w * P.level_stride + t;
+        if (EULER) {
+            if (P.x_traj) {                                    // level t is final once the pending passes ran
+                const size_t to = ((size_t)w * (P.nsteps + 1) + t) * P.np + (size_t)row * P.ncol + col;
+                P.x_traj[to] = x; P.y_traj[to] = y;
+            }
+            double ua, va;
+            stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
+            __stcs(pw, make_double2(ua, va));
+        } else {
+            const double2 wv = ld_state(pw);
+            stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.hx + row), wv.x, wv.y, x, y);
+        }
+        y = clamp_y(y, P.lat_min, P.lat_max);
+        __stcs(ps, make_double2(x, y));
+        if (x < P.lon_min) {
+            unsigned char* g_lt = flag_slot(P, w, q, 0);
+            int r2, c2;
+            slot_rc(P, e, r2, c2);                                   // rare: re-derived rather than kept live
+            g_lt[r2] = 1; g_lt[P.nrow + c2] = 1;
+        } else if (x > P.lon_max) {
+            const int slot = atomicAdd(P.cand_count + (size_t)w * P.nsub + q, 1);
+            P.cand[(size_t)sbase + slot] = e;
+        }
+    }
+}
+
+#ifndef LCS_CLUSTER_MINBLOCKS
+#define LCS_CLUSTER_MINBLOCKS 2
+#endif
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool CLUSTERED>
+__global__ void __launch_bounds__(kClusterThreads, LCS_CLUSTER_MINBLOCKS)
+advect_outer_cluster_kernel(const AdvectParams P, const int cs /* CTAs per window = cluster size (1..8) */) {
+    extern __shared__ unsigned char s_f[];                // [rows | cols], bit 0 = "< x_min" flag, bit 1 = "> x_max" flag
+    const int w = blockIdx.x / cs;
+    const int rank = blockIdx.x - w * cs;
+    const int tid_w = rank * kClusterThreads + threadIdx.x;
+    const int nthr_w = cs * kClusterThreads;
+    const int nflag = P.nrow + P.ncol;
+    int q = 0;
+    for (int t = 0; t < P.nsteps; ++t) {
+        for (int k = 0; k <= P.S; ++k, ++q) {
+            // ---- phase A: pending clamps of q-1 (mirrored in smem), stage, y clamp, raise "< x_min" flags
+            if (k == 0) cluster_phase_a<T, STRICT, ORDER, LAYOUT, true>(P, w, q, t, tid_w, nthr_w, s_f);
+            else cluster_phase_a<T, STRICT, ORDER, LAYOUT, false>(P, w, q, t, tid_w, nthr_w, s_f);
+            window_sync<CLUSTERED>();
+            // ---- phase B: mirror the "< x_min" flags; candidates that survive that pass raise "> x_max" flags
+            const unsigned char* g_lt = flag_slot(P, w, q, 0);
+            unsigned char* g_gt = flag_slot(P, w, q, 1);
+            for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_f[i] = __ldcg(g_lt + i);          // 0 / 1
+            __syncthreads();
+            const int ncand = __ldcg(P.cand_count + (size_t)w * P.nsub + q);
+            const int* cand = P.cand + (size_t)w * P.nslots;
+            for (int i = tid_w; i < ncand; i += nthr_w) {
+                int row, col;
+                slot_rc(P, __ldcg(cand + i), row, col);
+                if (!(s_f[row] & s_f[P.nrow + col] & 1)) { g_gt[row] = 1; g_gt[P.nrow + col] = 1; }
+            }
+            window_sync<CLUSTERED>();
+            for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_f[i] |= (unsigned char)(__ldcg(g_gt + i) << 1);
+            __syncthreads();
+        }
+    }
+    // ---- final: pending clamps of the last sub-step, outputs
+    const double2* spos = reinterpret_cast<const double2*>(P.spos) + (size_t)w * P.nslots;
+    for (int e = tid_w; e < P.nslots; e += nthr_w) {
+        int row, col;
+        if (!slot_rc(P, e, row, col)) continue;
+        double x, y;
+        if (P.nsub == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
+        else {
+            const double2 s = __ldcs(spos + e);
+            x = s.x; y = s.y;
+            const unsigned m = (unsigned)s_f[row] & (unsigned)s_f[P.nrow + col];
+            if (m & 1u) x = P.lon_min;
+            if (m & 2u) x = P.lon_max;
+        }
+        const size_t o = (size_t)row * P.ncol + col;
+        P.x_out[(size_t)w * P.np + o] = x; P.y_out[(size_t)w * P.np + o] = y;
+        if (P.x_traj) {
+            const size_t to = ((size_t)w * (P.nsteps + 1) + P.nsteps) * P.np + o;
+            P.x_traj[to] = x; P.y_traj[to] = y;
+        }
+    }
+}
+
+// Cluster size for `nwindows` windows: the driver reports how many clusters of each size can be co-resident
+// (cluster placement strands SMs: GPCs hold 16/18/20 SMs, so size 4 or 8 does not tile the 148 SMs);
+// a window takes time ~1/cs and the launch runs ceil(nwindows / resident(cs)) waves, so pick the cs that
+// minimises waves/cs.  Returns 0 when even the best choice leaves most of the machine idle.
+template <typename T, bool STRICT, int ORDER, int LAYOUT>
+static int choose_cluster_size(const AdvectParams& P, int nwindows, size_t smem, double* busy_frac) {
+    static int resident[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};           // per instantiation; smem differences are tiny
+    int best = 1;
+    double best_cost = 1e30;
+    for (int cs = 1; cs <= 8; ++cs) {
+        if (!resident[cs]) {
+            int n = 0;
+            if (cs == 1) {
+                auto k1 = advect_outer_cluster_kernel<T, STRICT, ORDER, LAYOUT, false>;
+                int per_sm = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, kClusterThreads, smem) == cudaSuccess)
+                    n = per_sm * lcs_sm_count();
+            } else {
+                auto kc = advect_outer_cluster_kernel<T, STRICT, ORDER, LAYOUT, true>;
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3((unsigned)(cs * 64)); cfg.blockDim = dim3(kClusterThreads); cfg.dynamicSmemBytes = smem;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr; cfg.numAttrs = 1;
+                if (cudaOccupancyMaxActiveClusters(&n, kc, &cfg) != cudaSuccess) n = 0;
+            }
+            (void)cudaGetLastError();
+            resident[cs] = n > 0 ? n : -1;
+        }
+        if (resident[cs] <= 0) continue;
+        const int waves = (nwindows + resident[cs] - 1) / resident[cs];
+        const double cost = (double)waves / cs;
+        if (cost < best_cost - 1e-12) { best_cost = cost; best = cs; }
+    }
+    if (lcs_env_int("LCS_DEBUG_CLUSTER", 0)) {
+        fprintf(stderr, "[lcs] co-resident clusters by size 1..8:");
+        for (int cs = 1; cs <= 8; ++cs) fprintf(stderr, " %d", resident[cs]);
+        fprintf(stderr, "; %d windows -> cluster size %d\n", nwindows, best);
+    }
+    const int forced = lcs_env_int("LCS_OUTER_CLUSTER", 0);
+    if (forced >= 1 && forced <= 8 && resident[forced] > 0) best = forced;
+    if (resident[best] <= 0) { *busy_frac = 0.0; return 0; }
+    const int waves = (nwindows + resident[best] - 1) / resident[best];
+    *busy_frac = (double)nwindows * best / ((double)waves * lcs_sm_count() * LCS_CLUSTER_MINBLOCKS);
+    return best;
+}
+
+template <typename T, bool STRICT, int ORDER, int LAYOUT>
+static cudaError_t launch_outer_cluster(const AdvectParams& P, int nwindows, int cs, size_t smem, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(nwindows * cs));
+    cfg.blockDim = dim3(kClusterThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cs == 1) return cudaLaunchKernelEx(&cfg, advect_outer_cluster_kernel<T, STRICT, ORDER, LAYOUT, false>, P, cs);
+    return cudaLaunchKernelEx(&cfg, advect_outer_cluster_kernel<T, STRICT, ORDER, LAYOUT, true>, P, cs);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Outer-product clamp, group-persistent form (the default).  The cluster kernel above keeps one window per CTA
+// (or per hardware cluster) resident, so 296 windows x 3 MB of position / Euler-sample state are in flight at once
+// and every sub-step streams it through DRAM (ncu, round 1: 241 GB per 1184 windows, 42 % of the DRAM bandwidth,
+// L2 hit rate 37 %).  Here the launch is ONE cooperative grid of `ncta` resident CTAs split into `ngroups` groups; a
+// group integrates one window at a time and draws the next one from a global counter, so only `ngroups` windows
+// are in flight and their state (ngroups x 3 MB at C2) stays in L2 -- or, STATE = 1, the positions live in the
+// owning CTA's shared memory for the whole window (a thread owns the same slots in every sub-step).  The two
+// window-wide dependencies of a sub-step are resolved with a group barrier in global memory (arrive counter +
+// spin by one thread per CTA, the cooperative launch guarantees co-residency) and -- when few particles left
+// through x_max, the common case -- the second barrier is replaced by every CTA scanning the whole candidate
+// list itself.  A group of one CTA degenerates to the per-CTA kernel; a single window is integrated by the
+// whole machine (one group), which is the low-latency single-field path.
+struct GroupHdr { unsigned next_window; unsigned error; unsigned pad[30]; };           // 128 B
+struct GroupCtl { unsigned bar; int window; unsigned pad[30]; };                       // 128 B apart: own L2 line each
+struct GroupParams {
+    GroupHdr* hdr;
+    GroupCtl* ctl;                // [ngroups]
+    double2* pos;                 // [ngroups][nslots]  positions (STATE = 0)
+    double2* wind;                // [ngroups][nslots]  Euler-stage samples of the current interval
+    int* cand;                    // [ngroups][2][nslots]  slots with x > lon_max after sub-step q: buffer q & 1 (a fast CTA appends
+                                  //                       those of q+1 while a slow one still scans those of q)
+    unsigned char* wbase;         // [ngroups][2 window parities][wstride]: { int count[nsub] | u8 flags[nsub][2][nflag_pad] }
+    size_t wstride, flags_off;
+    int ngroups, ncta, nwindows, nflag_pad, sflag_bytes, redundant_max, prefetch, per_sm;
+};
+
+#ifndef LCS_GROUP_THREADS
+#define LCS_GROUP_THREADS 512
+#endif
+#ifndef LCS_GROUP_MINBLOCKS
+#define LCS_GROUP_MINBLOCKS 2
+#endif
+constexpr int kGroupThreads = LCS_GROUP_THREADS;
+constexpr unsigned kSpinLimit = 1u << 24;             // ~10 s of polling: a lost arrival flags an error instead of hanging the GPU
+
+__device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Barrier over the CTAs of one group (all resident: cooperative launch).  `target` = arrivals expected since launch.
+// The same fence / atomic / spin / fence sequence cooperative_groups uses for grid.sync().
+__device__ __forceinline__ void group_barrier(unsigned* bar, unsigned target, unsigned* err) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned spins = 0;
+        while ((int)(ld_volatile_u32(bar) - target) < 0) {
+            if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_volatile_u32(err))) { atomicExch(err, 1u); break; }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// thread-private state in global memory (LCS_GROUP_STATE_POLICY: 0 = ld.cg / st.cg, kept in L2; 1 = ld.cs / st.cs, evict-first)
+#ifndef LCS_GROUP_STATE_POLICY
+#define LCS_GROUP_STATE_POLICY 0
+#endif
+__device__ __forceinline__ double2 gld_state(const double2* p) {
+#if LCS_GROUP_STATE_POLICY == 1
+    return __ldcs(p);
+#else
+    return __ldcg(p);
+#endif
+}
+__device__ __forceinline__ void gst_state(double2* p, double2 v) {
+#if LCS_GROUP_STATE_POLICY == 1
+    __stcs(p, v);
+#else
+    __stcg(p, v);
+#endif
+}
+
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool EULER, int STATE>
+__device__ __forceinline__ void group_phase_a(const AdvectParams& P, const GroupParams& G, const int g, const int w,
+                                              const int q, const int t, const int e_begin, const int e_end,
+                                              const unsigned char* s_f, double2* s_pos, const int wsel) {
+    const unsigned sbase = (unsigned)g * (unsigned)P.nslots;        // host guarantees ngroups*nslots < 2^32
+    constexpr int nthr_w = kGroupThreads;                           // a CTA owns a contiguous block of slots (see the kernel)
+    int it = 0;
+    for (int e = e_begin; e < e_end; e += nthr_w, ++it) {
+        double2* const ps = (STATE == 1) ? s_pos + (it * kGroupThreads + threadIdx.x) : G.pos + (sbase + (unsigned)e);
+        double2* const pw = G.wind + (sbase + (unsigned)e);
+        if (G.prefetch && e + nthr_w < e_end) {                      // next slot's state: on its way by the time it is needed
+            if (G.prefetch == 1) {
+                if (STATE == 0 && q != 0) prefetch_l1(ps + nthr_w);
+                if (!EULER) prefetch_l1(pw + nthr_w);
+            } else {
+                if (STATE == 0 && q != 0) prefetch_l2(ps + nthr_w);
+                if (!EULER) prefetch_l2(pw + nthr_w);
+            }
+        }
+        int row, col;
+        if (!slot_rc(P, e, row, col)) continue;
+        const int grow = P.row0 + row;
+        const bool pole = (grow < ORDER) || (grow >= P.nrow_global - ORDER);
+        double x, y;
+        if (q == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
+        else {
+            const double2 s = (STATE == 1) ? *ps : gld_state(ps);
+            x = s.x; y = s.y;
+            const unsigned m = (unsigned)s_f[row] & (unsigned)s_f[P.nrow + col];   // bit 0: "< x_min" pass, bit 1: "> x_max" pass
+            if (m & 1u) x = P.lon_min;                               // trajectory.py:96
+            if (m & 2u) x = P.lon_max;                               // trajectory.py:97
+        }
+        const int pair = P.level0 + w * P.level_stride + t;
+        if (EULER) {
+            if (P.x_traj) {                                          // level t is final once the pending passes ran
+                const size_t to = ((size_t)w * (P.nsteps + 1) + t) * P.np + (size_t)row * P.ncol + col;
+                P.x_traj[to] = x; P.y_traj[to] = y;
+            }
+            double ua, va;
+            stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
+            gst_state(pw, make_double2(ua, va));
+        } else {
+            const double2 wv = gld_state(pw);
+            stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.hx + row), wv.x, wv.y, x, y);
+        }
+        y = clamp_y(y, P.lat_min, P.lat_max);
+        if (STATE == 1) *ps = make_double2(x, y);
+        else gst_state(ps, make_double2(x, y));
+        if (x < P.lon_min) {
+            // rare: the window's flag page and the slot's row / column are re-derived rather than kept live
+            unsigned char* g_lt = G.wbase + (size_t)wsel * G.wstride + G.flags_off + (size_t)(2 * q) * G.nflag_pad;
+            int r2, c2;
+            slot_rc(P, e, r2, c2);
+            g_lt[r2] = 1; g_lt[P.nrow + c2] = 1;
+        } else if (x > P.lon_max) {
+            const int slot = atomicAdd(reinterpret_cast<int*>(G.wbase + (size_t)wsel * G.wstride) + q, 1);
+            G.cand[((size_t)(2 * g + (q & 1))) * P.nslots + slot] = e;
+        }
+    }
+}
+
+template <typename T, bool STRICT, int ORDER, int LAYOUT, int STATE>
+__global__ void __launch_bounds__(kGroupThreads, LCS_GROUP_MINBLOCKS)
+advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    unsigned char* const s_f = s_raw;                    // [rows | cols] bit 0 = "< x_min" flag, bit 1 = "> x_max" flag
+    double2* const s_pos = reinterpret_cast<double2*>(s_raw + G.sflag_bytes);      // STATE = 1: [iterations][threads]
+    // G.per_sm > 1: CTAs b, b + nsm, ... (the ones that share an SM on an idle device) are neighbours in `bid`, so they
+    // land in the same group and an SM works on one window at a time; 1: consecutive CTAs, an SM hosts several groups
+    const int nsm_ = G.ncta / G.per_sm;
+    const int bid = G.per_sm > 1 ? (int)(blockIdx.x % nsm_) * G.per_sm + (int)(blockIdx.x / nsm_) : (int)blockIdx.x;
+    const int g = (int)(((long long)(bid + 1) * G.ngroups - 1) / G.ncta);          // CTAs [g*ncta/ngroups, (g+1)*ncta/ngroups)
+    const int c0 = (int)((long long)g * G.ncta / G.ngroups);
+    const int gsize = (int)((long long)(g + 1) * G.ncta / G.ngroups) - c0;
+    const int tid_w = (bid - c0) * kGroupThreads + threadIdx.x;
+    const int nthr_w = gsize * kGroupThreads;
+    // slots of this CTA: a contiguous block (whole 2x16 tiles), swept in order -- consecutive iterations of a warp then
+    // touch neighbouring particle rows, whose 4x4 stencils share three of five coefficient rows in L1 (a group-strided
+    // assignment lost that: ncu showed the L1 hit rate falling from 64 % to 59 % between groups of 1 and 8 CTAs)
+    const int chunk = (P.nslots + nthr_w - 1) / nthr_w * kGroupThreads;
+    const int e_begin = (bid - c0) * chunk + threadIdx.x;
+    const int e_end = min((bid - c0 + 1) * chunk, P.nslots);
+    GroupCtl* const ctl = G.ctl + g;
+    unsigned* const err = &G.hdr->error;
+    unsigned arrivals = 0;                                // arrivals of this group expected at its next barrier
+    int parity = 0;
+    for (;;) {
+        unsigned char* const wb = G.wbase + ((size_t)g * 2 + parity) * G.wstride;
+        {   // this window's candidate counters and exit flags start cleared (the other parity may still be read)
+            uint4* c = reinterpret_cast<uint4*>(wb);
+            const int n16 = (int)(G.wstride >> 4);
+            for (int i = tid_w; i < n16; i += nthr_w) __stcg(c + i, make_uint4(0u, 0u, 0u, 0u));
+        }
+        if (tid_w == 0) ctl->window = (int)atomicAdd(&G.hdr->next_window, 1u);
+        group_barrier(&ctl->bar, arrivals += gsize, err);
+        const int w = __ldcg(&ctl->window);
+        if (w >= G.nwindows) break;
+        int q = 0;
+        for (int t = 0; t < P.nsteps; ++t) {
+            for (int k = 0; k <= P.S; ++k, ++q) {
+                // ---- phase A: pending clamps of q-1 (mirrored in smem), stage, y clamp, raise "< x_min" flags
+                if (k == 0) group_phase_a<T, STRICT, ORDER, LAYOUT, true, STATE>(P, G, g, w, q, t, e_begin, e_end, s_f, s_pos, 2 * g + parity);
+                else group_phase_a<T, STRICT, ORDER, LAYOUT, false, STATE>(P, G, g, w, q, t, e_begin, e_end, s_f, s_pos, 2 * g + parity);
+                group_barrier(&ctl->bar, arrivals += gsize, err);
+                // ---- phase B: mirror the "< x_min" flags; candidates that survive that pass raise the "> x_max" flags
+                const unsigned* g_lt = reinterpret_cast<const unsigned*>(wb + G.flags_off + (size_t)(2 * q) * G.nflag_pad);
+                unsigned* const s_f32 = reinterpret_cast<unsigned*>(s_f);
+                for (int i = threadIdx.x; i < (G.nflag_pad >> 2); i += kGroupThreads) s_f32[i] = __ldcg(g_lt + i);   // bytes 0 / 1
+                __syncthreads();
+                const int ncand = __ldcg(reinterpret_cast<const int*>(wb) + q);
+                if (ncand > 0) {                                     // uniform over the group
+                    const int* cand = G.cand + (size_t)(2 * g + (q & 1)) * P.nslots;
+                    if (ncand <= G.redundant_max) {
+                        // few candidates: every CTA scans them all and sets the "> x_max" bits itself -- no second barrier
+                        for (int i = threadIdx.x; i < ncand; i += kGroupThreads) {
+                            int row, col;
+                            slot_rc(P, __ldcg(cand + i), row, col);
+                            // bit 0 is stable in this phase and bit 1 only ever goes 0 -> 1: plain byte read-modify-writes are safe
+                            if (!(s_f[row] & s_f[P.nrow + col] & 1)) { s_f[row] |= 2; s_f[P.nrow + col] |= 2; }
+                        }
+                        __syncthreads();
+                    } else {
+                        unsigned char* g_gt = wb + G.flags_off + (size_t)(2 * q + 1) * G.nflag_pad;
+                        for (int i = tid_w; i < ncand; i += nthr_w) {
+                            int row, col;
+                            slot_rc(P, __ldcg(cand + i), row, col);
+                            if (!(s_f[row] & s_f[P.nrow + col] & 1)) { g_gt[row] = 1; g_gt[P.nrow + col] = 1; }
+                        }
+                        group_barrier(&ctl->bar, arrivals += gsize, err);
+                        const unsigned* g_gt32 = reinterpret_cast<const unsigned*>(g_gt);
+                        for (int i = threadIdx.x; i < (G.nflag_pad >> 2); i += kGroupThreads) s_f32[i] |= __ldcg(g_gt32 + i) << 1;
+                        __syncthreads();
+                    }
+                }
+            }
+        }
+        // ---- final: pending clamps of the last sub-step, outputs
+        const unsigned sbase = (unsigned)g * (unsigned)P.nslots;
+        int it = 0;
+        for (int e = e_begin; e < e_end; e += kGroupThreads, ++it) {
+            int row, col;
+            if (!slot_rc(P, e, row, col)) continue;
+            const double2 s = (STATE == 1) ? s_pos[it * kGroupThreads + threadIdx.x] : gld_state(G.pos + (sbase + (unsigned)e));
+            double x = s.x;
+            const unsigned m = (unsigned)s_f[row] & (unsigned)s_f[P.nrow + col];
+            if (m & 1u) x = P.lon_min;
+            if (m & 2u) x = P.lon_max;
+            const size_t o = (size_t)row * P.ncol + col;
+            P.x_out[(size_t)w * P.np + o] = x; P.y_out[(size_t)w * P.np + o] = s.y;
+            if (P.x_traj) {
+                const size_t to = ((size_t)w * (P.nsteps + 1) + P.nsteps) * P.np + o;
+                P.x_traj[to] = x; P.y_traj[to] = s.y;
+            }
+        }
+        parity ^= 1;
+    }
+}
+
+// Occupancy of a kernel on the current device, cached per (device, kernel, block, shared memory); thread-safe.
+static int lcs_blocks_per_sm(const void* func, int threads, size_t smem) {
+    struct Key { int dev; const void* f; int threads; size_t smem; int value; };
+    static Key cache[64];
+    static int ncache = 0;
+    static std::mutex mu;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < ncache; ++i)
+        if (cache[i].dev == dev && cache[i].f == func && cache[i].threads == threads && cache[i].smem == smem) return cache[i].value;
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, func, threads, smem) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    if (ncache < 64) cache[ncache++] = Key{dev, func, threads, smem, n};
+    return n;
+}
+
+// 0: group-persistent kernel (default), 1: phased launches, 2: hardware cluster per window
+static int lcs_outer_mode() {
+    const int m = lcs_env_int("LCS_OUTER_MODE", 0);
+    return (m == 1 || m == 2) ? m : 0;
+}
+
+// Sizes of the group path that do not depend on the kernel instantiation (lcs_advect_workspace_bytes needs them
+// before the winds are known): windows in flight and the workspace layout.
+struct GroupLayout {
+    int ngroups_max;                       // upper bound of windows in flight (the launch may use fewer: ncta)
+    int nflag_pad;
+    size_t wstride, flags_off;
+    size_t hdr, ctl, pos, wind, cand, wbase, head_bytes, total;
+};
+static size_t lcs_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static GroupLayout group_layout(int nrow, int ncol, int nslots, int nsub, int nwindows) {
+    GroupLayout L;
+    // Windows in flight.  Measured (C2, 1184 windows, B200): one CTA per window is fastest -- 71.8 ms against 74.6 / 79.9 ms
+    // with 2 / 8 CTAs per window, although the latter keep the state of the windows in flight inside L2: the kernel is
+    // bound by L1 data-pipe wavefronts and issue slots, not by the DRAM round trip of the state (42 % of the DRAM
+    // bandwidth, latency hidden by the prefetch).  So: as many groups as windows, capped by the resident CTAs; fewer
+    // windows than CTAs are spread over the whole machine.  LCS_OUTER_L2_MB / LCS_OUTER_GROUPS override for experiments.
+    long long n = nwindows;
+    const int l2mb = lcs_env_int("LCS_OUTER_L2_MB", 0);
+    if (l2mb > 0) n = ((long long)l2mb << 20) / ((long long)nslots * 32);
+    const int forced = lcs_env_int("LCS_OUTER_GROUPS", 0);
+    if (forced > 0) n = forced;
+    if (n < 1) n = 1;
+    if (n > nwindows) n = nwindows;
+    if (n > 4 * lcs_sm_count()) n = 4 * lcs_sm_count();
+    L.ngroups_max = (int)n;
+    L.nflag_pad = (int)lcs_align_up((size_t)(nrow + ncol), 16);
+    L.flags_off = lcs_align_up((size_t)nsub * sizeof(int), 16);
+    L.wstride = L.flags_off + (size_t)nsub * 2 * L.nflag_pad;
+    L.hdr = 0;
+    L.ctl = L.hdr + sizeof(GroupHdr);
+    L.head_bytes = L.ctl + (size_t)n * sizeof(GroupCtl);
+    L.pos = lcs_align_up(L.head_bytes, 256);
+    L.wind = L.pos + lcs_align_up((size_t)n * nslots * sizeof(double2), 256);
+    L.cand = L.wind + lcs_align_up((size_t)n * nslots * sizeof(double2), 256);
+    L.wbase = L.cand + lcs_align_up((size_t)n * 2 * nslots * sizeof(int), 256);
+    L.total = L.wbase + (size_t)n * 2 * L.wstride;
+    return L;
+}
+
+template <typename T, bool STRICT, int ORDER, int LAYOUT>
+static cudaError_t launch_outer_group(const AdvectParams& P, int nwindows, void* workspace, cudaStream_t st, bool* launched) {
+    *launched = false;
+    const GroupLayout L = group_layout(P.nrow, P.ncol, P.nslots, P.nsub, nwindows);
+    int state = lcs_env_int("LCS_OUTER_STATE", 0);               // 0: positions in global memory (L2), 1: in shared memory
+    const int nsm = lcs_sm_count();
+    const int sflag = (int)lcs_align_up((size_t)L.nflag_pad, 16);
+    int ncta = 0, ngroups = 0, per_sm_used = 1;
+    size_t smem = 0;
+    const void* fn = nullptr;
+    const int cap = lcs_env_int("LCS_OUTER_CTAS", 0);
+    for (;; state = 0) {
+        fn = state == 1 ? (const void*)advect_outer_group_kernel<T, STRICT, ORDER, LAYOUT, 1>
+                        : (const void*)advect_outer_group_kernel<T, STRICT, ORDER, LAYOUT, 0>;
+        if (state == 0) {
+            smem = (size_t)sflag;
+            per_sm_used = lcs_blocks_per_sm(fn, kGroupThreads, smem);
+            ncta = per_sm_used * nsm;
+            if (cap > 0 && cap < ncta) { ncta = cap; per_sm_used = 1; }
+        } else {
+            // a CTA keeps ceil(nslots / (gsize * threads)) positions per thread: that depends on the group size, which
+            // depends on how many CTAs fit with that much shared memory -- try the fullest shape first
+            ncta = 0;
+            for (int per_sm = LCS_GROUP_MINBLOCKS; per_sm >= 1 && !ncta; --per_sm) {
+                int c = per_sm * nsm;
+                if (cap > 0 && cap < c) c = cap;
+                const int n = L.ngroups_max < c ? L.ngroups_max : c;
+                const int gmin = c / n;                               // smallest group
+                const int iters = (P.nslots + gmin * kGroupThreads - 1) / (gmin * kGroupThreads);
+                smem = (size_t)sflag + (size_t)iters * kGroupThreads * sizeof(double2);
+                if (smem > 200 * 1024) continue;
+                if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) continue;
+                if (lcs_blocks_per_sm(fn, kGroupThreads, smem) >= per_sm) { ncta = c; per_sm_used = (cap > 0 && cap < per_sm * nsm) ? 1 : per_sm; }
+            }
+            (void)cudaGetLastError();
+            if (!ncta) continue;                                      // does not fit: positions in global memory
+        }
+        break;
+    }
+    if (ncta < 1) return cudaSuccess;                                 // caller reports the failure
+    ngroups = L.ngroups_max < ncta ? L.ngroups_max : ncta;
+    if ((unsigned long long)ngroups * (unsigned long long)P.nslots >= (1ULL << 32)) return cudaSuccess;
+    char* wsb = static_cast<char*>(workspace);
+    GroupParams G{};
+    G.hdr = reinterpret_cast<GroupHdr*>(wsb + L.hdr);
+    G.ctl = reinterpret_cast<GroupCtl*>(wsb + L.ctl);
+    G.pos = reinterpret_cast<double2*>(wsb + L.pos);
+    G.wind = reinterpret_cast<double2*>(wsb + L.wind);
+    G.cand = reinterpret_cast<int*>(wsb + L.cand);
+    G.wbase = reinterpret_cast<unsigned char*>(wsb + L.wbase);
+    G.wstride = L.wstride; G.flags_off = L.flags_off;
+    G.ngroups = ngroups; G.ncta = ncta; G.nwindows = nwindows; G.nflag_pad = L.nflag_pad; G.sflag_bytes = sflag;
+    G.redundant_max = lcs_env_int("LCS_OUTER_REDUNDANT", 2048);
+    G.prefetch = lcs_env_int("LCS_OUTER_PREFETCH", 1);
+    G.per_sm = lcs_env_int("LCS_OUTER_SAMESM", 0) ? per_sm_used : 1;
+    cudaError_t e = cudaMemsetAsync(wsb, 0, L.head_bytes, st);        // window counter, error word, barrier counters
+    if (e != cudaSuccess) return e;
+    if (lcs_env_int("LCS_DEBUG_CLUSTER", 0))
+        fprintf(stderr, "[lcs] outer group kernel: %d windows, %d CTAs in %d groups, state %d, %zu B smem\n",
+                nwindows, ncta, ngroups, state, smem);
+    AdvectParams Pc = P;
+    void* args[2] = {&Pc, &G};
+    e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)ncta), dim3(kGroupThreads), args, smem, st);
+    if (e == cudaSuccess) { *launched = true; lcs_count_launches(1); }
+    return e;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <typename T, bool STRICT, int ORDER, int LAYOUT>
+static cudaError_t launch_advect(const AdvectParams& P, int nwindows, void* workspace, cudaStream_t st) {
+    const dim3 block(256);
+    const int tw = 256 >> P.band_log2;
+    const dim3 grid((unsigned)((P.ncol + tw - 1) / tw), (unsigned)((P.nrow + P.band - 1) / P.band), (unsigned)nwindows);
+    if (P.xmode != LCS_X_CLAMP_OUTER) {
+        if constexpr (sizeof(T) == 8 && !STRICT && ORDER == 3 && LAYOUT == kES) {
+            // wide grids: 8 x 32 blocks of one-row warps (see particle_rc); LCS_ADVECT_STRIP=0/1 forces the choice
+            const int strip = lcs_env_int("LCS_ADVECT_STRIP", -1);
+            if (strip == 1 || (strip < 0 && P.ncol >= 640)) {
+                const dim3 sgrid((unsigned)((P.ncol + 31) / 32), (unsigned)((P.nrow + 7) / 8), (unsigned)nwindows);
+                if (sgrid.y <= 65535) {
+                    advect_fused_kernel<T, STRICT, ORDER, LAYOUT, true><<<sgrid, block, 0, st>>>(P);
+                    lcs_count_launches(1);
+                    return cudaGetLastError();
+                }
+            }
+        }
+        {   // experiment knob: shrink the L1 by reserving a shared-memory carve-out (percent) the kernel does not use
+            const int carve = lcs_env_int("LCS_FUSED_CARVEOUT", -1);
+            if (carve >= 0) cudaFuncSetAttribute(advect_fused_kernel<T, STRICT, ORDER, LAYOUT>,
+                                                 cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        }
+        advect_fused_kernel<T, STRICT, ORDER, LAYOUT><<<grid, block, 0, st>>>(P);
+        lcs_count_launches(1);
+        return cudaGetLastError();
+    }
+    // Default: the group-persistent kernel (few windows in flight, state in L2 / shared memory).  LCS_OUTER_MODE=1: one
+    // launch pair per sub-step (kernel boundaries as barriers, the independent implementation the tests compare with);
+    // LCS_OUTER_MODE=2: one hardware cluster per window (round-1 kernel, kept for A/B measurements).
+    const int mode = lcs_outer_mode();
+    if (P.nsub > 0 && mode == 0) {
+        if (P.nrow + P.ncol > 48 * 1024) return cudaErrorInvalidValue;
+        bool launched = false;
+        const cudaError_t e = launch_outer_group<T, STRICT, ORDER, LAYOUT>(P, nwindows, workspace, st, &launched);
+        return (e == cudaSuccess && !launched) ? cudaErrorLaunchOutOfResources : e;
+    }
+    const size_t smem = (size_t)(P.nrow + P.ncol);
+    if (P.nsub > 0 && smem <= 48 * 1024 && mode == 2) {
+        double busy = 0.0;
+        const int cs = choose_cluster_size<T, STRICT, ORDER, LAYOUT>(P, nwindows, smem, &busy);
+        if (cs > 0) {
+            lcs_count_launches(1);
+            return launch_outer_cluster<T, STRICT, ORDER, LAYOUT>(P, nwindows, cs, smem, st);
+        }
+    }
+    const dim3 ggrid(4, (unsigned)nwindows);
+    bool strip = false;
+    const dim3 sgrid((unsigned)((P.ncol + 31) / 32), (unsigned)((P.nrow + 7) / 8), (unsigned)nwindows);
+    if constexpr (sizeof(T) == 8 && !STRICT && ORDER == 3 && LAYOUT == kES) {       // wide grids, as for the fused kernel
+        const int s = lcs_env_int("LCS_ADVECT_STRIP", -1);
+        strip = (s == 1 || (s < 0 && P.ncol >= 640)) && sgrid.y <= 65535;
+    }
+    for (int q = 0; q < P.nsub; ++q) {
+        if constexpr (sizeof(T) == 8 && !STRICT && ORDER == 3 && LAYOUT == kES) {
+            if (strip) advect_phase_move<T, STRICT, ORDER, LAYOUT, true><<<sgrid, block, 0, st>>>(P, q, q / (1 + P.S), q % (1 + P.S));
+        }
+        if (!strip) advect_phase_move<T, STRICT, ORDER, LAYOUT><<<grid, block, 0, st>>>(P, q, q / (1 + P.S), q % (1 + P.S));
+        advect_phase_gtpass<<<ggrid, block, 0, st>>>(P, q);
+    }
+    advect_phase_final<<<grid, block, 0, st>>>(P);
+    lcs_count_launches(2 * P.nsub + 1);
+    return cudaGetLastError();
+}
+
+}  // namespace lcs

@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "../../include/lcs_b200.h"
 
 namespace lcs {
 
@@ -31,13 +32,13 @@ template <> struct Vec2Of<float> { using type = float2; };
 // all four SETTLS operands of a tap with one load (256-bit LDG.E.256.CONSTANT for f64)
 template <typename T> struct Pair4;
 template <> struct Pair4<double> {
-    using type = d4; static constexpr int NV = 4; static constexpr bool A32 = false;
+    using type = d4; static constexpr int NV = 4; static constexpr bool A32 = false, HALO = false;
     static __device__ __forceinline__ void ld(const type* p, double (&o)[4]) {
         asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
     }
 };
 template <> struct Pair4<float> {
-    using type = float4; static constexpr int NV = 4; static constexpr bool A32 = false;
+    using type = float4; static constexpr int NV = 4; static constexpr bool A32 = false, HALO = false;
     static __device__ __forceinline__ void ld(const type* p, double (&o)[4]) {
         const float4 t = __ldg(p);
         o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
@@ -46,28 +47,33 @@ template <> struct Pair4<float> {
 // first half (u_k, v_k) of a 4-wide element: the Euler stage samples one level (trajectory.py:82-84)
 template <typename T> struct Pair4Lo;
 template <> struct Pair4Lo<double> {
-    using type = d4; static constexpr int NV = 2; static constexpr bool A32 = false;
+    using type = d4; static constexpr int NV = 2; static constexpr bool A32 = false, HALO = false;
     static __device__ __forceinline__ void ld(const type* p, double (&o)[2]) {
         asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "l"(p));
     }
 };
 template <> struct Pair4Lo<float> {
-    using type = float4; static constexpr int NV = 2; static constexpr bool A32 = false;
+    using type = float4; static constexpr int NV = 2; static constexpr bool A32 = false, HALO = false;
     static __device__ __forceinline__ void ld(const type* p, double (&o)[2]) {
         const float2 t = __ldg(reinterpret_cast<const float2*>(p));
         o[0] = t.x; o[1] = t.y;
     }
 };
-// dense 2-wide element (the E / S arrays of the fast layout): 16 B (f64) or 8 B (f32) per tap
+// 2-wide element (the E / S arrays of the fast layout): 16 B (f64) or 8 B (f32) per tap.  HALO: every level is
+// stored with a mirror-filled halo (LCS_HALO_LO cells before, LCS_HALO_HI after each axis; lcs_pack_es), so a tap
+// index never has to be reflected and every gather takes the one-base-address path.  That matters more than it
+// sounds: the boundary clamps park a large share of the particles exactly on the domain edge, where the 4x4
+// stencil sticks out of the grid -- ncu (round 2, C2 outer clamp) attributed 30 % of the integrator's executed
+// instructions to the reflected-index path of the dense layout.
 template <typename T> struct Vec2;
 template <> struct Vec2<double> {
-    using type = d2; static constexpr int NV = 2; static constexpr bool A32 = false;
+    using type = d2; static constexpr int NV = 2; static constexpr bool A32 = false, HALO = true;
     static __device__ __forceinline__ void ld(const type* p, double (&o)[2]) {
         asm("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "l"(p));
     }
 };
 template <> struct Vec2<float> {
-    using type = float2; static constexpr int NV = 2; static constexpr bool A32 = false;
+    using type = float2; static constexpr int NV = 2; static constexpr bool A32 = false, HALO = true;
     static __device__ __forceinline__ void ld(const type* p, double (&o)[2]) {
         const float2 t = __ldg(p);
         o[0] = t.x; o[1] = t.y;
@@ -76,7 +82,7 @@ template <> struct Vec2<float> {
 // f32 elements whose cubic taps are also weighted and accumulated in f32 (LCS_ARITH_F32, the fast path):
 // same storage and loads as Vec2<float>; the cubic gather is gather_cubic_wrap_f32 below
 struct Vec2F32Arith {
-    using type = float2; static constexpr int NV = 2; static constexpr bool A32 = true;
+    using type = float2; static constexpr int NV = 2; static constexpr bool A32 = true, HALO = true;
     static __device__ __forceinline__ void ld(const type* p, double (&o)[2]) {
         const float2 t = __ldg(p);
         o[0] = t.x; o[1] = t.y;
@@ -84,13 +90,19 @@ struct Vec2F32Arith {
 };
 // planar f64 field, one value per tap (the map_coordinates seam)
 struct Scalar32 {
-    using type = float; static constexpr int NV = 1; static constexpr bool A32 = false;
+    using type = float; static constexpr int NV = 1; static constexpr bool A32 = false, HALO = false;
     static __device__ __forceinline__ void ld(const float* p, double (&o)[1]) { o[0] = (double)__ldg(p); }
 };
 struct Scalar64 {
-    using type = double; static constexpr int NV = 1; static constexpr bool A32 = false;
+    using type = double; static constexpr int NV = 1; static constexpr bool A32 = false, HALO = false;
     static __device__ __forceinline__ void ld(const double* p, double (&o)[1]) { o[0] = __ldg(p); }
 };
+
+// row pitch (elements) of a level of policy E over an nlat x nlon grid; HALO levels are addressed from their
+// (0, 0) element, i.e. the caller passes base + LCS_HALO_LO * pitch + LCS_HALO_LO
+template <typename E> __device__ __forceinline__ int level_pitch(int nlon) {
+    return E::HALO ? nlon + LCS_HALO_LO + LCS_HALO_HI : nlon;
+}
 
 // ------------------------------------------------------------------ index arithmetic
 // tools.py:21-22: n * (pos - cmin) / (cmax - cmin)   (n points, not n-1: quirk Q4)
@@ -103,12 +115,19 @@ __device__ __forceinline__ double index_map_fast(double pos, double cmin, double
 }
 
 // scipy mode='wrap' coordinate fold: period n-1, result in [0, n-1]
+// Within one period of the range the truncated quotient scipy forms is 0 (below) or 1 (above), so the fold is one
+// exact add; that is every coordinate a clamped particle can have (index n at x = x_max: quirk Q4), and it skips
+// the f64 division (a ~30-instruction sequence) the general case needs.
 __device__ __forceinline__ double fold_wrap(double c, int n) {
-    const long long sz = n - 1;
+    const double szd = (double)(n - 1);
     if (c < 0.0) {
-        c += (double)(sz * ((long long)(__ddiv_rn(-c, (double)sz)) + 1));
-    } else if (c > (double)(n - 1)) {
-        c -= (double)(sz * (long long)(__ddiv_rn(c, (double)sz)));
+        if (-c < szd) return __dadd_rn(c, szd);
+        const long long sz = n - 1;
+        c += (double)(sz * ((long long)(__ddiv_rn(-c, szd)) + 1));
+    } else if (c > szd) {
+        if (c < 2.0 * szd) return __dsub_rn(c, szd);
+        const long long sz = n - 1;
+        c -= (double)(sz * (long long)(__ddiv_rn(c, szd)));
     }
     return c;
 }
@@ -131,11 +150,14 @@ __device__ __forceinline__ void cubic_weights(double y, double (&w)[4]) {
         w[0] = __ddiv_rn(__dmul_rn(__dmul_rn(z, z), z), 6.0);
         w[3] = __dsub_rn(__dsub_rn(__dsub_rn(1.0, w[0]), w[1]), w[2]);
     } else {
-        const double s = 1.0 / 6.0;
-        w[1] = (y * y * (y - 2.0) * 3.0 + 4.0) * s;
-        w[2] = (z * z * (z - 2.0) * 3.0 + 4.0) * s;
-        w[0] = z * z * z * s;
-        w[3] = 1.0 - w[0] - w[1] - w[2];
+        // the same cubics in Horner form, 11 operations per axis instead of 17: w1 = (y/2 - 1) y^2 + 2/3 (likewise w2 in
+        // z), w0 = z^3 / 6, w3 = y^3 / 6 (scipy forms w3 = 1 - w0 - w1 - w2; equal up to rounding)
+        const double s = 1.0 / 6.0, c23 = 2.0 / 3.0;
+        const double ty = y * y, tz = z * z;
+        w[1] = fma(fma(0.5, y, -1.0), ty, c23);
+        w[2] = fma(fma(0.5, z, -1.0), tz, c23);
+        w[0] = (z * s) * tz;
+        w[3] = (y * s) * ty;
     }
 }
 
@@ -162,22 +184,35 @@ __device__ __forceinline__ void gather_cubic_wrap(const typename E::type* __rest
     cubic_weights<STRICT>(__dsub_rn(cy, fy), wy);
     cubic_weights<STRICT>(__dsub_rn(cx, fx), wx);
     const int sy = (int)fy - 1, sx = (int)fx - 1;
+    const int pitch = level_pitch<E>(nlon);
 #pragma unroll
     for (int v = 0; v < NV; ++v) out[v] = 0.0;
-    if (sy >= 0 && sy + 3 < nlat && sx >= 0 && sx + 3 < nlon) {
-        const typename E::type* base = f + (size_t)sy * nlon + sx;
+    if (E::HALO || (sy >= 0 && sy + 3 < nlat && sx >= 0 && sx + 3 < nlon)) {
+        const typename E::type* base = f + (sy * pitch + sx);               // a level has < 2^31 elements
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             double c[4][NV];
 #pragma unroll
             for (int j = 0; j < 4; ++j) E::ld(base + j, c[j]);
+            if (STRICT) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double wyx = wy[i] * wx[j];
+                for (int j = 0; j < 4; ++j) {
 #pragma unroll
-                for (int v = 0; v < NV; ++v) out[v] = tap_acc<STRICT>(out[v], c[j][v], wy[i], wx[j], wyx);
+                    for (int v = 0; v < NV; ++v) out[v] = tap_acc<true>(out[v], c[j][v], wy[i], wx[j], 0.0);
+                }
+            } else {
+                // row sums first, then the latitude weight: 5 operations per row and value instead of 6 (no weight
+                // products) and four short dependency chains instead of one of 16 FMAs
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    double r = c[0][v] * wx[0];
+                    r = fma(c[1][v], wx[1], r);
+                    r = fma(c[2][v], wx[2], r);
+                    r = fma(c[3][v], wx[3], r);
+                    out[v] = i == 0 ? r * wy[0] : fma(r, wy[i], out[v]);
+                }
             }
-            base += nlon;
+            base += pitch;
         }
         return;
     }
@@ -263,8 +298,9 @@ __device__ __forceinline__ void gather_spline_wrap(const typename E::type* __res
     const int sx = spline_weights<ORDER, STRICT>(cx, wx);
 #pragma unroll
     for (int v = 0; v < NV; ++v) out[v] = 0.0;
-    if (sy >= 0 && sy + ORDER < nlat && sx >= 0 && sx + ORDER < nlon) {
-        const typename E::type* base = f + (size_t)sy * nlon + sx;
+    const int pitch = level_pitch<E>(nlon);
+    if (E::HALO || (sy >= 0 && sy + ORDER < nlat && sx >= 0 && sx + ORDER < nlon)) {
+        const typename E::type* base = f + (sy * pitch + sx);
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
             double c[NT][NV];
@@ -276,7 +312,7 @@ __device__ __forceinline__ void gather_spline_wrap(const typename E::type* __res
 #pragma unroll
                 for (int v = 0; v < NV; ++v) out[v] = tap_acc<STRICT>(out[v], c[j][v], wy[i], wx[j], wyx);
             }
-            base += nlon;
+            base += pitch;
         }
         return;
     }
@@ -323,34 +359,19 @@ __device__ __forceinline__ void gather_cubic_wrap_f32(const float2* __restrict__
     cubic_weights_f32((float)(cx - fx), wx);
     const int sy = (int)fy - 1, sx = (int)fx - 1;
     float2 acc = make_float2(0.0f, 0.0f);
-    if (sy >= 0 && sy + 3 < nlat && sx >= 0 && sx + 3 < nlon) {
-        const float2* base = f + (size_t)sy * nlon + sx;
+    const int pitch = nlon + LCS_HALO_LO + LCS_HALO_HI;                      // halo layout: no tap index is ever reflected
+    const float2* base = f + (sy * pitch + sx);
+    (void)nlat;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float2 c[4];
+    for (int i = 0; i < 4; ++i) {
+        float2 c[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) c[j] = __ldg(base + j);
-            float2 r = __fmul2_rn(c[0], wx[0]);
+        for (int j = 0; j < 4; ++j) c[j] = __ldg(base + j);
+        float2 r = __fmul2_rn(c[0], wx[0]);
 #pragma unroll
-            for (int j = 1; j < 4; ++j) r = __ffma2_rn(c[j], wx[j], r);
-            acc = __ffma2_rn(r, wy[i], acc);
-            base += nlon;
-        }
-    } else {
-        int col[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) col[j] = mirror_near(sx + j, nlon);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float2* rowp = f + (size_t)mirror_near(sy + i, nlat) * nlon;
-            float2 c[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) c[j] = __ldg(rowp + col[j]);
-            float2 r = __fmul2_rn(c[0], wx[0]);
-#pragma unroll
-            for (int j = 1; j < 4; ++j) r = __ffma2_rn(c[j], wx[j], r);
-            acc = __ffma2_rn(r, wy[i], acc);
-        }
+        for (int j = 1; j < 4; ++j) r = __ffma2_rn(c[j], wx[j], r);
+        acc = __ffma2_rn(r, wy[i], acc);
+        base += pitch;
     }
     out[0] = (double)acc.x; out[1] = (double)acc.y;
 }
@@ -368,12 +389,13 @@ __device__ __forceinline__ void bilinear_taps(const typename E::type* __restrict
     const double wy[2] = {wy0, __dsub_rn(1.0, wy0)};
     const double wx[2] = {wx0, __dsub_rn(1.0, wx0)};
     const int iy0 = (int)fy, ix0 = (int)fx;
-    const int col[2] = {mirror_near(ix0, nlon), mirror_near(ix0 + 1, nlon)};
+    const int pitch = level_pitch<E>(nlon);
+    const int col[2] = {E::HALO ? ix0 : mirror_near(ix0, nlon), E::HALO ? ix0 + 1 : mirror_near(ix0 + 1, nlon)};
 #pragma unroll
     for (int v = 0; v < NV; ++v) out[v] = 0.0;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-        const typename E::type* rowp = f + (size_t)mirror_near(iy0 + i, nlat) * nlon;
+        const typename E::type* rowp = f + (E::HALO ? iy0 + i : mirror_near(iy0 + i, nlat)) * pitch;
         double c[2][NV];
 #pragma unroll
         for (int j = 0; j < 2; ++j) E::ld(rowp + col[j], c[j]);

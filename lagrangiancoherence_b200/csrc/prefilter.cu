@@ -164,23 +164,30 @@ pack_pairs_kernel(const Tin* __restrict__ u, const Tin* __restrict__ v,
     pairs[idx] = o;
 }
 
-// E[k] = (u_k, v_k), k < nlev;  S[k] = (2u_k - u_{k+1}, 2v_k - v_{k+1}), k < nlev-1 (f64 arithmetic)
+// E[k] = (u_k, v_k), k < nlev;  S[k] = (2u_k - u_{k+1}, 2v_k - v_{k+1}), k < nlev-1 (f64 arithmetic), written in the
+// halo layout of include/lcs_b200.h: one thread per padded cell, halo cells read their mirror image.
 template <typename Tin, typename Tout>
 __global__ void __launch_bounds__(256)
 pack_es_kernel(const Tin* __restrict__ u, const Tin* __restrict__ v,
                typename Vec2Of<Tout>::type* __restrict__ e_out, typename Vec2Of<Tout>::type* __restrict__ s_out,
-               long long plane, int nlev) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= plane * nlev) return;
-    const double uk = (double)u[idx], vk = (double)v[idx];
+               int nlat, int nlon, int nlev) {
+    const int pitch = nlon + LCS_HALO_LO + LCS_HALO_HI;
+    const int pc = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pc >= pitch) return;
+    const int pr = blockIdx.y, k = blockIdx.z;
+    const int r = mirror_near(pr - LCS_HALO_LO, nlat), c = mirror_near(pc - LCS_HALO_LO, nlon);
+    const size_t plane = (size_t)nlat * nlon;
+    const size_t src = (size_t)k * plane + (size_t)r * nlon + c;
+    const size_t dst = ((size_t)k * (nlat + LCS_HALO_LO + LCS_HALO_HI) + pr) * pitch + pc;
+    const double uk = (double)u[src], vk = (double)v[src];
     typename Vec2Of<Tout>::type e;
     e.x = (Tout)uk; e.y = (Tout)vk;
-    e_out[idx] = e;
-    if (idx < plane * (nlev - 1)) {
+    e_out[dst] = e;
+    if (k < nlev - 1) {
         typename Vec2Of<Tout>::type s;
-        s.x = (Tout)__dsub_rn(__dmul_rn(2.0, uk), (double)u[idx + plane]);
-        s.y = (Tout)__dsub_rn(__dmul_rn(2.0, vk), (double)v[idx + plane]);
-        s_out[idx] = s;
+        s.x = (Tout)__dsub_rn(__dmul_rn(2.0, uk), (double)u[src + plane]);
+        s.y = (Tout)__dsub_rn(__dmul_rn(2.0, vk), (double)v[src + plane]);
+        s_out[dst] = s;
     }
 }
 
@@ -294,17 +301,18 @@ extern "C" int lcs_pack_es(const void* u, const void* v, int in_dtype, void* e_o
                            int nlev, int nlat, int nlon, void* stream) {
     if (!u || !v || !e_out || !s_out) return lcs_fail(LCS_E_INVALID, "lcs_pack_es: null argument");
     if (nlev < 2 || nlat < 1 || nlon < 1) return lcs_fail(LCS_E_INVALID, "lcs_pack_es: need at least two levels");
+    if (nlat < 4 || nlon < 4) return lcs_fail(LCS_E_INVALID, "lcs_pack_es: grid must be at least 4x4 (single mirror reflection of the halo)");
+    if (nlev > 65535 || nlat + LCS_HALO_LO + LCS_HALO_HI > 65535) return lcs_fail(LCS_E_INVALID, "lcs_pack_es: at most 65535 levels / 65530 rows per call");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const long long plane = (long long)nlat * nlon;
-    const unsigned gb = (unsigned)((plane * nlev + 255) / 256);
+    const dim3 gb((unsigned)((nlon + LCS_HALO_LO + LCS_HALO_HI + 255) / 256), (unsigned)(nlat + LCS_HALO_LO + LCS_HALO_HI), (unsigned)nlev);
     if (in_dtype == LCS_F64 && es_dtype == LCS_F64)
-        pack_es_kernel<double, double><<<gb, 256, 0, st>>>((const double*)u, (const double*)v, (d2*)e_out, (d2*)s_out, plane, nlev);
+        pack_es_kernel<double, double><<<gb, 256, 0, st>>>((const double*)u, (const double*)v, (d2*)e_out, (d2*)s_out, nlat, nlon, nlev);
     else if (in_dtype == LCS_F64 && es_dtype == LCS_F32)
-        pack_es_kernel<double, float><<<gb, 256, 0, st>>>((const double*)u, (const double*)v, (float2*)e_out, (float2*)s_out, plane, nlev);
+        pack_es_kernel<double, float><<<gb, 256, 0, st>>>((const double*)u, (const double*)v, (float2*)e_out, (float2*)s_out, nlat, nlon, nlev);
     else if (in_dtype == LCS_F32 && es_dtype == LCS_F64)
-        pack_es_kernel<float, double><<<gb, 256, 0, st>>>((const float*)u, (const float*)v, (d2*)e_out, (d2*)s_out, plane, nlev);
+        pack_es_kernel<float, double><<<gb, 256, 0, st>>>((const float*)u, (const float*)v, (d2*)e_out, (d2*)s_out, nlat, nlon, nlev);
     else if (in_dtype == LCS_F32 && es_dtype == LCS_F32)
-        pack_es_kernel<float, float><<<gb, 256, 0, st>>>((const float*)u, (const float*)v, (float2*)e_out, (float2*)s_out, plane, nlev);
+        pack_es_kernel<float, float><<<gb, 256, 0, st>>>((const float*)u, (const float*)v, (float2*)e_out, (float2*)s_out, nlat, nlon, nlev);
     else return lcs_fail(LCS_E_INVALID, "lcs_pack_es: bad dtype");
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_pack_es");

@@ -54,7 +54,8 @@ class StagedWinds:
     """Gather layouts of a wind series on the device (lcs_pack_pairs / lcs_pack_es).
 
     PAIR4: ``raw_a``/``coef_a`` = ``[nlev-1, nlat, nlon, 4]`` pairs.
-    ES   : ``raw_a``/``coef_a`` = E ``[nlev, nlat, nlon, 2]``, ``raw_b``/``coef_b`` = S ``[nlev-1, nlat, nlon, 2]``.
+    ES   : ``raw_a``/``coef_a`` = E ``[nlev, nlat+5, nlon+5, 2]``, ``raw_b``/``coef_b`` = S ``[nlev-1, nlat+5, nlon+5, 2]``
+           (halo layout: 2 mirror-filled cells before and 3 after each axis).
     """
     layout: int
     dtype: int
@@ -174,8 +175,10 @@ class FtleEngine:
                 return StagedWinds(self.layout, self.pair_dtype, nlev, raw_a=raw, coef_a=coef)
 
             def pack_es(a, b, code):
-                e = torch.empty((nlev,) + shape2 + (2,), dtype=tdt, device=self.device)
-                s_ = torch.empty((nlev - 1,) + shape2 + (2,), dtype=tdt, device=self.device)
+                # halo layout (include/lcs_b200.h): every level carries a mirror-filled rim so no gather reflects an index
+                padded = (self.nlat + _lib.LCS_HALO_LO + _lib.LCS_HALO_HI, self.nlon + _lib.LCS_HALO_LO + _lib.LCS_HALO_HI)
+                e = torch.empty((nlev,) + padded + (2,), dtype=tdt, device=self.device)
+                s_ = torch.empty((nlev - 1,) + padded + (2,), dtype=tdt, device=self.device)
                 _lib.check(self.lib.lcs_pack_es(_ptr(a), _ptr(b), code, _ptr(e), _ptr(s_), self.pair_dtype,
                                                 nlev, self.nlat, self.nlon, st), 'lcs_pack_es')
                 return e, s_
@@ -258,7 +261,8 @@ class FtleEngine:
             d_mask = None
             if mask is not None:
                 d_mask = torch.as_tensor(np.ascontiguousarray(mask, dtype=np.uint8)).to(self.device)
-            self.d_status.zero_()
+            # the status word is NOT cleared here: kernels OR into it, so one check_finite() after several epilogue
+            # launches (rolling chunks, row bands) sees an inf raised by any of them
             _lib.check(self.lib.lcs_ftle_epilogue(_ptr(x_dep.contiguous()), _ptr(y_dep.contiguous()), nfields,
                                                   self.nlat, nlon, in_row0, nrow_in, o0, o1 - o0,
                                                   _ptr(self.d_dx), self.dy, _ptr(d_mask), int(bool(log_scale)),
@@ -293,9 +297,21 @@ class FtleEngine:
                                               int(t[0].numel()), _ptr(out), _stream(self.device)), 'lcs_time_lerp')
         return out
 
+    def reset_status(self):
+        """Clear the inf flag the epilogue launches OR into (call once before a series of epilogue launches)."""
+        with torch.cuda.device(self.device):
+            self.d_status.zero_()
+
     def check_finite(self):
-        """Raise like scipy.linalg.norm(check_finite=True) does at LCS.py:154 (synchronises)."""
-        if int(self.d_status.item()) & 1:
+        """Raise like scipy.linalg.norm(check_finite=True) does at LCS.py:154 if any epilogue launch since the last
+        reset_status() / check_finite() met an inf derivative (synchronises, then clears the flag)."""
+        if self._ws is not None and self.xmode == _lib.LCS_X_CLAMP_OUTER:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.lcs_advect_check(_ptr(self._ws), _stream(self.device)), 'lcs_advect')
+        status = int(self.d_status.item())
+        if status:
+            self.d_status.zero_()                               # read-and-clear: the next series starts clean
+        if status & 1:
             raise ValueError('array must not contain infs or NaNs')
 
     # ------------------------------------------------------------------ whole path

@@ -104,7 +104,7 @@ def rolling_ftle(u, v, lat, lon, window_levels, timestep, SETTLS_order=4, interp
     nlev = u.shape[0]
     nsteps = window_levels - 1
     first, count = (0, nlev - window_levels + 1) if starts is None else starts
-    if count < 1 or first + count + nsteps > nlev:
+    if count < 0 or first < 0 or first + count + nsteps > nlev:
         raise ValueError('start-time range runs past the wind series')
     if engine is None:
         engine = FtleEngine(lat, lon, timestep, SETTLS_order=SETTLS_order, interp_order=interp_order,
@@ -121,7 +121,10 @@ def rolling_ftle(u, v, lat, lon, window_levels, timestep, SETTLS_order=4, interp
     if to_host and own_out:
         out = torch.empty((count, lat.size, lon.size), dtype=torch.float64).pin_memory()
     sigma = None if to_host else torch.empty((count, lat.size, lon.size), dtype=torch.float64, device=dev)
+    if count == 0:                                       # an empty shard (more ranks than start times): nothing to integrate
+        return sigma if return_device else (out.numpy() if own_out else out)
     chunks = chunk_starts(0, count, chunk) if on_device else chunk_schedule(count, chunk)
+    engine.reset_status()                                # chunks OR into one flag, checked once after the loop
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream(dev)
         pipe = _pipeline(engine, (max(n for _, n in chunks) + nsteps,) + tuple(u.shape[1:]), u.dtype, need_in=not on_device)

@@ -69,6 +69,12 @@ CASES = {
                               timestep=-21600, S=2, order=4, cyclic=False),
     'regional_outer_p5': dict(kind='era5', nlat=33, nlon=45, lat=(-20.0, 12.0), lon=(-70.0, -26.0), nt=4, seed=8,
                               timestep=10800, S=3, order=5, cyclic=False),
+    # f32 winds on f64 coordinates (how ERA5 is stored): scipy answers in the input dtype and numpy's promotion rules
+    # (NEP 50) then decide the precision of every increment (tools.py:26-30, trajectory.py:86-87,110-112)
+    'regional_f32_winds': dict(kind='era5', nlat=41, nlon=57, lat=(-30.0, 10.0), lon=(-80.0, -24.0), nt=5, seed=9,
+                               timestep=-21600, S=4, order=3, cyclic=False, dtype='float32'),
+    'regional_f32_winds_p1': dict(kind='era5', nlat=33, nlon=45, lat=(-20.0, 12.0), lon=(-70.0, -26.0), nt=4, seed=10,
+                                  timestep=10800, S=2, order=1, cyclic=False, dtype='float32'),
     'descending_lat_dims_shuffled': dict(kind='era5', nlat=29, nlon=37, lat=(-28.0, 0.0), lon=(-72.0, -36.0), nt=4, seed=5,
                                          timestep=-21600, S=3, order=3, cyclic=False, flip_lat=True,
                                          dims=['latitude', 'time', 'longitude']),
@@ -84,6 +90,8 @@ def make_inputs(case):
         lon = np.linspace(*case['lon'], case['nlon'])
         u, v = S.era5_like_winds(lat, lon, case['nt'], seed=case['seed'], contained=case.get('contained', False))
         u, v = u * case.get('scale', 1.0), v * case.get('scale', 1.0)
+        if case.get('dtype'):
+            u, v = u.astype(case['dtype']), v.astype(case['dtype'])
     time = (np.datetime64('2000-01-01T00') + np.arange(u.shape[0]) * np.timedelta64(6, 'h')).astype('datetime64[ns]')
     return u, v, lat, lon, time
 

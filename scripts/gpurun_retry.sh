@@ -1,0 +1,9 @@
+#!/bin/bash
+# usage: scripts/gpurun_retry.sh [gpurun args...] -- retries while the pod answers "busy" (exit 3, nothing charged)
+for i in $(seq 1 40); do
+    /usr/local/graft/bin/gpurun "$@"
+    rc=$?
+    if [ $rc -ne 3 ]; then exit $rc; fi
+    sleep 45
+done
+exit 3

@@ -160,6 +160,31 @@ def test_outer_clamp_cluster_kernel_equals_phased_launches(cuda_device, cs, monk
         assert (rel_err(yb[w].cpu().numpy(), ry, np.abs(lat).max()) > REL_POS).mean() <= 1e-3
 
 
+@pytest.mark.parametrize('groups,state,redundant,ctas', [(0, 0, 2048, 0), (1, 0, 2048, 0), (2, 0, 0, 0), (3, 1, 2048, 0),
+                                                         (1, 1, 0, 0), (5, 0, 2048, 7), (2, 1, 2048, 3), (1, 0, 2048, 1)])
+def test_outer_clamp_group_kernel_equals_phased_launches(cuda_device, groups, state, redundant, ctas, monkeypatch):
+    """The group-persistent kernel (default outer-clamp path) against the launch-per-sub-step implementation: same
+    arithmetic, so bit-identical, for any number of windows in flight (1 = the whole machine on one window at a time),
+    positions in global or shared memory, the redundant candidate scan or the second barrier, ragged group sizes."""
+    from lagrangiancoherence_b200.engine import FtleEngine
+    lat = np.linspace(-30.0, 10.0, 41)
+    lon = np.linspace(-80.0, -24.0, 57)
+    u, v = S.era5_like_winds(lat, lon, 11)
+    eng = FtleEngine(lat, lon, -21600, SETTLS_order=4, xmode='outer', device=cuda_device)
+    st = eng.stage(u, v)
+    monkeypatch.setenv('LCS_OUTER_MODE', '1')
+    xa, ya, xta, yta = eng.advect(st, nsteps=4, nwindows=7, return_traj=True)
+    monkeypatch.setenv('LCS_OUTER_MODE', '0')
+    monkeypatch.setenv('LCS_OUTER_GROUPS', str(groups))
+    monkeypatch.setenv('LCS_OUTER_STATE', str(state))
+    monkeypatch.setenv('LCS_OUTER_REDUNDANT', str(redundant))
+    monkeypatch.setenv('LCS_OUTER_CTAS', str(ctas))
+    eng._ws = None
+    xb, yb, xtb, ytb = eng.advect(st, nsteps=4, nwindows=7, return_traj=True)
+    eng.check_finite()
+    assert torch.equal(xa, xb) and torch.equal(ya, yb) and torch.equal(xta, xtb) and torch.equal(yta, ytb)
+
+
 def test_f32_storage_fast_path_tolerance(cuda_device):
     """precision='f32' stores the staged winds/coefficients in f32 (positions, weights and the epilogue stay f64).
     Stated tolerance (north star: FTLE within 1e-5 relative away from ridge-singular points): departure points
