@@ -82,6 +82,14 @@ typedef struct lcs_advect_opts {
     int32_t nwindows;       /* independent start times integrated by this call (rolling series)  */
     int32_t level0, level_stride; /* window b starts at packed pair index level0 + b*level_stride  */
     int32_t arith;          /* LCS_ARITH_*; LCS_ARITH_F32 needs dtype LCS_F32, LCS_LAYOUT_ES, order 3   */
+    int32_t round32;        /* the reference's dtype propagation for f32 WINDS on f64 coordinates: scipy returns
+                               map_coordinates samples in the input dtype (tools.py:26-30) and numpy's promotion
+                               rules (NEP 50) then fix the precision of every increment (trajectory.py:86-87,110-112).
+                               0: off (f64 winds); 1: every sample rounded to f32, the SETTLS bracket and the y
+                               increments in f32 (timestep is a Python scalar); 2: as 1 but y increments in f64
+                               (timestep is a numpy f64 scalar, e.g. after resample=).  Needs LCS_LAYOUT_ES of f64
+                               coefficients computed from the f32 winds; levels k and k+1 are then sampled
+                               separately, so a SETTLS stage costs two gathers                                  */
 } lcs_advect_opts;
 
 /* Staged winds handed to the integrator.

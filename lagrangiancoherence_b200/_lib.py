@@ -34,7 +34,8 @@ class Particles(C.Structure):
 class AdvectOpts(C.Structure):
     _fields_ = [('nsteps', C.c_int32), ('settls_order', C.c_int32), ('interp_order', C.c_int32),
                 ('xmode', C.c_int32), ('strict', C.c_int32),
-                ('nwindows', C.c_int32), ('level0', C.c_int32), ('level_stride', C.c_int32), ('arith', C.c_int32)]
+                ('nwindows', C.c_int32), ('level0', C.c_int32), ('level_stride', C.c_int32), ('arith', C.c_int32),
+                ('round32', C.c_int32)]
 
 
 class Winds(C.Structure):

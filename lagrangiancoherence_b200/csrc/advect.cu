@@ -8,6 +8,7 @@ LCS_DECL(lcs_launch_f64_es3); LCS_DECL(lcs_launch_f64_es1); LCS_DECL(lcs_launch_
 LCS_DECL(lcs_launch_f64_es5); LCS_DECL(lcs_launch_f64_p3); LCS_DECL(lcs_launch_f64_p3s); LCS_DECL(lcs_launch_f64_p1);
 LCS_DECL(lcs_launch_f64_p1s); LCS_DECL(lcs_launch_f32_es3); LCS_DECL(lcs_launch_f32_es1); LCS_DECL(lcs_launch_f32_p3);
 LCS_DECL(lcs_launch_f32_p3s); LCS_DECL(lcs_launch_f32_p1); LCS_DECL(lcs_launch_f32_p1s); LCS_DECL(lcs_launch_f32_fast3);
+LCS_DECL(lcs_launch_r32_es1); LCS_DECL(lcs_launch_r32_es2); LCS_DECL(lcs_launch_r32_es3); LCS_DECL(lcs_launch_r32_es4); LCS_DECL(lcs_launch_r32_es5);
 #undef LCS_DECL
 }  // namespace lcs
 
@@ -77,6 +78,9 @@ extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_a
         return lcs_fail(LCS_E_INVALID, "lcs_advect: f32 arithmetic needs f32 winds in the ES layout, interp_order 3, strict 0");
     if (w->raw_planar && (w->layout != LCS_LAYOUT_ES || o->interp_order < 2 || (w->raw_dtype != LCS_F64 && w->raw_dtype != LCS_F32)))
         return lcs_fail(LCS_E_INVALID, "lcs_advect: planar raw winds are for the ES layout with interp_order >= 2 (raw_dtype f64/f32)");
+    if (o->round32 < 0 || o->round32 > 2) return lcs_fail(LCS_E_INVALID, "lcs_advect: round32 must be 0, 1 or 2");
+    if (o->round32 && (w->layout != LCS_LAYOUT_ES || w->dtype != LCS_F64 || o->strict || o->arith != LCS_ARITH_F64))
+        return lcs_fail(LCS_E_UNSUPPORTED, "lcs_advect: round32 (f32 dtype propagation) needs f64 ES levels, strict 0, f64 arithmetic");
     if (g->nlat < 4 || g->nlon < 4) return lcs_fail(LCS_E_INVALID, "lcs_advect: grid must be at least 4x4");
     if (p->nrow < 1 || p->ncol < 1 || o->nwindows < 1 || o->nsteps < 0 || o->settls_order < 0)
         return lcs_fail(LCS_E_INVALID, "lcs_advect: bad sizes");
@@ -102,6 +106,7 @@ extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_a
     if ((long long)p->nrow * p->ncol >= (1LL << 31)) return lcs_fail(LCS_E_INVALID, "lcs_advect: too many particles per window");
     P.np = p->nrow * p->ncol;
     P.lat = p->lat; P.lon = p->lon; P.kx = p->kx; P.hx = p->hx; P.ky = p->ky; P.hy = p->hy;
+    P.ky32 = (float)p->ky; P.hy32 = (float)p->hy; P.y_weak = o->round32 == 1;       // NEP 50: a weak Python scalar becomes f32
     P.nsteps = o->nsteps; P.S = o->settls_order; P.xmode = o->xmode;
     P.level0 = o->level0; P.level_stride = o->level_stride;
     P.band_log2 = lcs_env_int("LCS_ADVECT_BAND_LOG2", 1);      // tile = 2 rows x 128 columns, warp = 2 x 16
@@ -140,7 +145,11 @@ extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_a
     const int ord = o->interp_order;
     const int nw = o->nwindows;
     const bool es = w->layout == LCS_LAYOUT_ES;
-    if (o->arith == LCS_ARITH_F32) e = lcs_launch_f32_fast3(P, nw, workspace, st);          // validated above
+    if (o->round32) {
+        e = ord == 1 ? lcs_launch_r32_es1(P, nw, workspace, st) : ord == 2 ? lcs_launch_r32_es2(P, nw, workspace, st)
+          : ord == 3 ? lcs_launch_r32_es3(P, nw, workspace, st) : ord == 4 ? lcs_launch_r32_es4(P, nw, workspace, st)
+          : lcs_launch_r32_es5(P, nw, workspace, st);
+    } else if (o->arith == LCS_ARITH_F32) e = lcs_launch_f32_fast3(P, nw, workspace, st);          // validated above
     else if (ord == 2) e = lcs_launch_f64_es2(P, nw, workspace, st);
     else if (ord == 4) e = lcs_launch_f64_es4(P, nw, workspace, st);
     else if (ord == 5) e = lcs_launch_f64_es5(P, nw, workspace, st);

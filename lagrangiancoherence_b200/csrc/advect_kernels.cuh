@@ -19,13 +19,10 @@
 // hit rate 91 %, L2 throughput 5 % in ncu: staging tiles through shared memory/TMA would move the
 // same bytes through the same 128 B/clk port and was not pursued).
 #pragma once
-#include <cooperative_groups.h>
 #include <stdio.h>
 #include <mutex>
 #include "lcs_internal.h"
 #include "lcs_device.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace lcs {
 
@@ -52,6 +49,8 @@ struct AdvectParams {
     const double* kx;
     const double* hx;
     double ky, hy;
+    float ky32, hy32;             // R32 with a weak (Python) timestep: the y increments are formed in f32 (NEP 50)
+    int y_weak;
     int nsteps, S, xmode, level0, level_stride, band, band_log2;
     double* x_out;
     double* y_out;
@@ -128,51 +127,75 @@ __device__ __forceinline__ void sample(const AdvectParams& P, const void* raw, c
 // taps per field.  SETTLS = true returns 2 f_k(pos) - f_{k+1}(pos) from two separate samples, which is the
 // reference's own order (trajectory.py:105-112).  Saves a third of the staging traffic at no measurable integrator
 // cost (a first version that called the generic bilinear gather four times cost 2.7 %).
-template <typename TR, bool SETTLS>
+template <typename TR, bool SETTLS, bool STRICT>
 __device__ __forceinline__ void pole_taps_planar(const TR* __restrict__ u, const TR* __restrict__ v, size_t plane,
-                                                 const int (&off)[4], const double (&w)[4], double (&out)[2]) {
+                                                 const int (&off)[4], const double (&wy)[2], const double (&wx)[2], double (&out)[4]) {
     double su = 0.0, sv = 0.0, su1 = 0.0, sv1 = 0.0;
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-        su = fma((double)__ldg(u + off[t]), w[t], su);
-        sv = fma((double)__ldg(v + off[t]), w[t], sv);
+        const double a = wy[t >> 1], b = wx[t & 1], ab = a * b;          // scipy: t += (value * wy) * wx, axis-1 tap inner
+        su = tap_acc<STRICT>(su, (double)__ldg(u + off[t]), a, b, ab);
+        sv = tap_acc<STRICT>(sv, (double)__ldg(v + off[t]), a, b, ab);
         if (SETTLS) {
-            su1 = fma((double)__ldg(u + plane + off[t]), w[t], su1);
-            sv1 = fma((double)__ldg(v + plane + off[t]), w[t], sv1);
+            su1 = tap_acc<STRICT>(su1, (double)__ldg(u + plane + off[t]), a, b, ab);
+            sv1 = tap_acc<STRICT>(sv1, (double)__ldg(v + plane + off[t]), a, b, ab);
         }
     }
-    out[0] = SETTLS ? 2.0 * su - su1 : su;
-    out[1] = SETTLS ? 2.0 * sv - sv1 : sv;
+    out[0] = su; out[1] = sv; out[2] = su1; out[3] = sv1;
 }
 
-template <bool SETTLS>
-__device__ __forceinline__ void pole_sample_planar(const AdvectParams& P, int k, double x, double y, double (&out)[2]) {
-    const double iy = index_map_fast(y, P.lat_min, P.nlat_over_span);
-    const double ix = index_map_fast(x, P.lon_min, P.nlon_over_span);
-    out[0] = 0.0; out[1] = 0.0;
+// out = (u_k, v_k, u_{k+1}, v_{k+1}) at (x, y); the level k+1 samples only with SETTLS
+template <bool SETTLS, bool STRICT = false>
+__device__ __forceinline__ void pole_sample_planar(const AdvectParams& P, int k, double x, double y, double (&out)[4]) {
+    const double iy = STRICT ? index_map(y, P.lat_min, P.lat_span, P.nlat_d) : index_map_fast(y, P.lat_min, P.nlat_over_span);
+    const double ix = STRICT ? index_map(x, P.lon_min, P.lon_span, P.nlon_d) : index_map_fast(x, P.lon_min, P.nlon_over_span);
+    out[0] = 0.0; out[1] = 0.0; out[2] = 0.0; out[3] = 0.0;
     if (!(iy >= 0.0 && iy <= (double)(P.nlat - 1) && ix >= 0.0 && ix <= (double)(P.nlon - 1))) return;   // mode='constant', cval 0
     const double fy = floor(iy), fx = floor(ix);
-    const double wy0 = 1.0 - (iy - fy), wx0 = 1.0 - (ix - fx);
-    const double wy1 = 1.0 - wy0, wx1 = 1.0 - wx0;                   // scipy: last weight = 1 - sum(others)
+    const double wy0 = __dsub_rn(1.0, __dsub_rn(iy, fy)), wx0 = __dsub_rn(1.0, __dsub_rn(ix, fx));
+    const double wy[2] = {wy0, __dsub_rn(1.0, wy0)}, wx[2] = {wx0, __dsub_rn(1.0, wx0)};   // scipy: last weight = 1 - sum(others)
     const int r0 = (int)fy, c0 = (int)fx;
     const int r1 = mirror_near(r0 + 1, P.nlat), c1 = mirror_near(c0 + 1, P.nlon);
     const int off[4] = {r0 * P.nlon + c0, r0 * P.nlon + c1, r1 * P.nlon + c0, r1 * P.nlon + c1};
-    const double w[4] = {wy0 * wx0, wy0 * wx1, wy1 * wx0, wy1 * wx1};
     const size_t o = (size_t)k * P.plane;
-    if (P.raw_f32) pole_taps_planar<float, SETTLS>(static_cast<const float*>(P.raw_a) + o, static_cast<const float*>(P.raw_b) + o, P.plane, off, w, out);
-    else pole_taps_planar<double, SETTLS>(static_cast<const double*>(P.raw_a) + o, static_cast<const double*>(P.raw_b) + o, P.plane, off, w, out);
+    if (P.raw_f32) pole_taps_planar<float, SETTLS, STRICT>(static_cast<const float*>(P.raw_a) + o, static_cast<const float*>(P.raw_b) + o, P.plane, off, wy, wx, out);
+    else pole_taps_planar<double, SETTLS, STRICT>(static_cast<const double*>(P.raw_a) + o, static_cast<const double*>(P.raw_b) + o, P.plane, off, wy, wx, out);
+}
+
+// R32 -- the reference's dtype propagation for f32 winds on f64 coordinates (how ERA5 is stored).  scipy allocates
+// map_coordinates' output with the INPUT dtype (tools.py:26-30,35-39): every sample is computed in f64 and rounded to
+// f32.  numpy (NEP 50) then forms `timestep * conversion_y * va` and `0.5 * timestep * conversion_y * (va + 2 v_t - v_t1)`
+// in f32 when `timestep` is a Python scalar (trajectory.py:86,110; f64 when it is a numpy scalar, e.g. after
+// resample=), while the x increments multiply the f64 array conversion_x and are f64 (trajectory.py:87,112); the
+// bracket of the SETTLS increment is f32 arithmetic on the separately rounded samples either way.
+// R32 kernels are instantiated with STRICT = true: order-1 samples of f32 data at positions whose index fractions are
+// small rationals (every particle starts on a grid node: fractions j/(n-1), quirk Q4) land EXACTLY on f32 rounding ties
+// a few per cent of the time, and the tie is then broken by the last bit of the f64 sum -- so the taps must be
+// accumulated in scipy's own order ((value * wy) * wx, sequentially) for the rounded sample to agree.
+__device__ __forceinline__ double r32(double v) { return (double)__double2float_rn(v); }
+__device__ __forceinline__ float settls_bracket32(double a, double ft, double ft1) {          // a + 2 f_t - f_t1 in f32
+    return __fsub_rn(__fadd_rn((float)a, __fmul_rn(2.0f, __double2float_rn(ft))), __double2float_rn(ft1));
+}
+__device__ __forceinline__ double y_increment32(const AdvectParams& P, bool half, float v) {
+    if (P.y_weak) return (double)__fmul_rn(half ? P.hy32 : P.ky32, v);
+    return __dmul_rn(half ? P.hy : P.ky, (double)v);
 }
 
 // Euler stage, trajectory.py:82-87 (samples level k only), boundaries excluded.
-template <typename T, bool STRICT, int ORDER, int LAYOUT>
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool R32 = false>
 __device__ __forceinline__ void stage_euler(const AdvectParams& P, int k, bool pole, double kx,
                                             double& x, double& y, double& ua, double& va) {
-    double s[2];
-    if (LAYOUT == kPair4) sample<Pair4Lo<T>, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, s);
-    else if (ORDER >= 2 && pole && P.raw_planar) pole_sample_planar<false>(P, k, x, y, s);
-    else sample<typename EsPolicy<T, LAYOUT>::type, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, s);
-    ua = s[0]; va = s[1];
-    y = __dadd_rn(y, __dmul_rn(P.ky, va));
+    double s[4];
+    if (LAYOUT == kPair4) sample<Pair4Lo<T>, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, reinterpret_cast<double(&)[2]>(s));
+    else if (ORDER >= 2 && pole && P.raw_planar) pole_sample_planar<false, STRICT>(P, k, x, y, s);
+    else sample<typename EsPolicy<T, LAYOUT>::type, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, reinterpret_cast<double(&)[2]>(s));
+    if (R32) {
+        ua = r32(s[0]); va = r32(s[1]);
+        y = __dadd_rn(y, y_increment32(P, false, (float)va));
+    } else {
+        ua = s[0]; va = s[1];
+        y = __dadd_rn(y, __dmul_rn(P.ky, va));
+    }
     x = __dadd_rn(x, __dmul_rn(kx, ua));
 }
 
@@ -181,7 +204,9 @@ __device__ __forceinline__ void stage_euler(const AdvectParams& P, int k, bool p
 // ES   : interpolation is linear in the field, so S_k = 2*c_k - c_{k+1} is combined once per grid
 //        point at staging time and a single 2-value sample yields 2*v_k(pos) - v_{k+1}(pos):
 //        half the gather bytes and half the FMAs of the stage (results differ by rounding only).
-template <typename T, bool STRICT, int ORDER, int LAYOUT>
+// R32  : (ES only) levels k and k+1 are sampled separately from E, because each sample is rounded to f32 before the
+//        bracket is formed in f32 -- twice the gathers of the f64 case, the price of the reference's rounding.
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool R32 = false>
 __device__ __forceinline__ void stage_settls(const AdvectParams& P, int k, bool pole, double hx,
                                              double ua, double va, double& x, double& y) {
     if (LAYOUT == kPair4) {
@@ -189,10 +214,24 @@ __device__ __forceinline__ void stage_settls(const AdvectParams& P, int k, bool 
         sample<Pair4<T>, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, s);
         y = __dadd_rn(y, __dmul_rn(P.hy, __dsub_rn(__dadd_rn(va, __dmul_rn(2.0, s[1])), s[3])));
         x = __dadd_rn(x, __dmul_rn(hx, __dsub_rn(__dadd_rn(ua, __dmul_rn(2.0, s[0])), s[2])));
+    } else if (R32) {
+        double s[4];
+        if (ORDER >= 2 && pole && P.raw_planar) pole_sample_planar<true, STRICT>(P, k, x, y, s);
+        else {
+            using EP = typename EsPolicy<T, LAYOUT>::type;
+            double a[2], b[2];
+            sample<EP, STRICT, ORDER>(P, P.raw_a, P.coef_a, k, pole, x, y, a);
+            sample<EP, STRICT, ORDER>(P, P.raw_a, P.coef_a, k + 1, pole, x, y, b);
+            s[0] = a[0]; s[1] = a[1]; s[2] = b[0]; s[3] = b[1];
+        }
+        y = __dadd_rn(y, y_increment32(P, true, settls_bracket32(va, s[1], s[3])));
+        x = __dadd_rn(x, __dmul_rn(hx, (double)settls_bracket32(ua, s[0], s[2])));
     } else {
-        double s[2];
-        if (ORDER >= 2 && pole && P.raw_planar) pole_sample_planar<true>(P, k, x, y, s);
-        else sample<typename EsPolicy<T, LAYOUT>::type, STRICT, ORDER>(P, P.raw_b, P.coef_b, k, pole, x, y, s);
+        double s[4];
+        if (ORDER >= 2 && pole && P.raw_planar) {
+            pole_sample_planar<true>(P, k, x, y, s);
+            s[0] = 2.0 * s[0] - s[2]; s[1] = 2.0 * s[1] - s[3];       // the reference's own order (trajectory.py:105-112)
+        } else sample<typename EsPolicy<T, LAYOUT>::type, STRICT, ORDER>(P, P.raw_b, P.coef_b, k, pole, x, y, reinterpret_cast<double(&)[2]>(s));
         y = __dadd_rn(y, __dmul_rn(P.hy, __dadd_rn(va, s[1])));
         x = __dadd_rn(x, __dmul_rn(hx, __dadd_rn(ua, s[0])));
     }
@@ -208,7 +247,7 @@ __device__ __forceinline__ void bounds_local(const AdvectParams& P, double& x, d
 #ifndef LCS_FUSED_MINBLOCKS
 #define LCS_FUSED_MINBLOCKS 4       // 64 registers, 1024 threads per SM (measured against 3 and 2 blocks: see DESIGN.md)
 #endif
-template <typename T, bool STRICT, int ORDER, int LAYOUT, bool STRIP = false>
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool STRIP = false, bool R32 = false>
 __global__ void __launch_bounds__(256, LCS_FUSED_MINBLOCKS)
 advect_fused_kernel(const AdvectParams P) {
     const int w = blockIdx.z;
@@ -226,10 +265,10 @@ advect_fused_kernel(const AdvectParams P) {
     const int pair0 = P.level0 + w * P.level_stride;
     for (int t = 0; t < P.nsteps; ++t) {
         double ua, va;
-        stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair0 + t, pole, kx, x, y, ua, va);
+        stage_euler<T, STRICT, ORDER, LAYOUT, R32>(P, pair0 + t, pole, kx, x, y, ua, va);
         bounds_local(P, x, y);
         for (int k = 0; k < P.S; ++k) {
-            stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair0 + t, pole, hx, ua, va, x, y);
+            stage_settls<T, STRICT, ORDER, LAYOUT, R32>(P, pair0 + t, pole, hx, ua, va, x, y);
             bounds_local(P, x, y);
         }
         if (xt) { xt[(size_t)(t + 1) * P.np] = x; yt[(size_t)(t + 1) * P.np] = y; }
@@ -262,7 +301,7 @@ __device__ __forceinline__ double apply_pending(const AdvectParams& P, int w, in
     return x;
 }
 
-template <typename T, bool STRICT, int ORDER, int LAYOUT, bool STRIP = false>
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool STRIP = false, bool R32 = false>
 __global__ void __launch_bounds__(256)
 advect_phase_move(const AdvectParams P, int q /* global sub-step index */, int t /* interval */, int k /* 0: Euler */) {
     const int w = blockIdx.z;
@@ -286,12 +325,12 @@ advect_phase_move(const AdvectParams P, int q /* global sub-step index */, int t
     const int pair = P.level0 + w * P.level_stride + t;
     if (k == 0) {
         double ua, va;
-        stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
+        stage_euler<T, STRICT, ORDER, LAYOUT, R32>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
         d2 e; e.x = ua; e.y = va;
         P.swind[o] = e;
     } else {
         const d2 e = P.swind[o];
-        stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.hx + row), e.x, e.y, x, y);
+        stage_settls<T, STRICT, ORDER, LAYOUT, R32>(P, pair, pole, __ldg(P.hx + row), e.x, e.y, x, y);
     }
     y = clamp_y(y, P.lat_min, P.lat_max);
     d2 s; s.x = x; s.y = y;
@@ -340,18 +379,6 @@ advect_phase_final(const AdvectParams P) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Outer-product clamp, persistent form: one thread-block CLUSTER owns one window for its whole
-// integration.  The cluster's threads stride over the window's particles (state in an L2-resident
-// per-window array, touched only by its owner thread), and the two global dependencies of every
-// sub-step -- "rows/columns holding an exit below x_min" and, after that pass, "... above x_max" --
-// are resolved with hardware cluster barriers (barrier.cluster, ~0.2 us) instead of kernel
-// boundaries.  A cluster of 1 degenerates to __syncthreads().  The exit flags of the current
-// sub-step are mirrored into shared memory after each barrier so the per-particle tests are LDS.
-#ifndef LCS_CLUSTER_THREADS
-#define LCS_CLUSTER_THREADS 512
-#endif
-constexpr int kClusterThreads = LCS_CLUSTER_THREADS;   // multiple of 32: a warp owns whole 2x16 tiles
-
 // Slot enumeration of a window for the persistent kernel: warp-sized tiles of 2 rows x 16 columns
 // (6 L1 wavefronts per 16-B gather request instead of 8 for a 4x8 patch, better hit rate than a 1x32
 // strip); slot e -> tile e>>5, lane e&31.  Slots past the grid edge are idle.
@@ -364,219 +391,8 @@ __device__ __forceinline__ bool slot_rc(const AdvectParams& P, int e, int& row, 
     return row < P.nrow && col < P.ncol;
 }
 
-template <bool CLUSTERED>
-__device__ __forceinline__ void window_sync() {
-    if (CLUSTERED) cg::this_cluster().sync();  // release/acquire at cluster scope: global writes become visible
-    else __syncthreads();
-}
-
-// phase A of one sub-step for the slots owned by this thread.  Everything that is uniform over the CTA
-// (window, sub-step, array bases) is re-derived from the constant bank where it is used instead of being
-// carried in registers across the gathers: at 64 registers the first version spilled its loop-invariant
-// pointers and its prefetched state (ncu: local-memory wavefronts = 25 % of the global-load wavefronts).
-#ifndef LCS_CLUSTER_PREFETCH
-#define LCS_CLUSTER_PREFETCH 2      // 0 none, 1 into L1, 2 into L2 (measured: see DESIGN.md)
-#endif
-__device__ __forceinline__ void prefetch_state(const void* p) {
-#if LCS_CLUSTER_PREFETCH == 1
-    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-#elif LCS_CLUSTER_PREFETCH == 2
-    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
-#endif
-}
-
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
-
-// state access policy of the persistent kernel (LCS_CLUSTER_STATE_LD: 0 = ld.cs/st.cs evict-first,
-// 1 = loads that do not allocate in L1, so the L1 keeps the wind taps)
-#ifndef LCS_CLUSTER_STATE_LD
-#define LCS_CLUSTER_STATE_LD 0
-#endif
-__device__ __forceinline__ double2 ld_state(const double2* p) {
-#if LCS_CLUSTER_STATE_LD == 1
-    double2 r;
-    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0,%1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
-    return r;
-#else
-    return __ldcs(p);
-#endif
-}
-
-template <typename T, bool STRICT, int ORDER, int LAYOUT, bool EULER>
-__device__ __forceinline__ void cluster_phase_a(const AdvectParams& P, const int w, const int q, const int t,
-                                                const int tid_w, const int nthr_w,
-                                                const unsigned char* s_f) {
-    const unsigned sbase = (unsigned)w * (unsigned)P.nslots;        // host guarantees nwindows*nslots < 2^32
-    for (int e = tid_w; e < P.nslots; e += nthr_w) {
-        double2* const ps = reinterpret_cast<double2*>(P.spos) + (sbase + (unsigned)e);
-        double2* const pw = reinterpret_cast<double2*>(P.swind) + (sbase + (unsigned)e);
-        if (e + nthr_w < P.nslots) {                                 // next slot's state: L2 by the time it is needed
-            if (q != 0) prefetch_state(ps + nthr_w);
-            if (!EULER) prefetch_state(pw + nthr_w);
-        }
-        int row, col;
-        if (!slot_rc(P, e, row, col)) continue;
-        const int grow = P.row0 + row;
-        const bool pole = (grow < ORDER) || (grow >= P.nrow_global - ORDER);
-        double x, y;
-        if (q == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
-        else {
-            const double2 s = ld_state(ps);
-            x = s.x; y = s.y;
-            const unsigned m = (unsigned)s_f[row] & (unsigned)s_f[P.nrow + col];   // bit 0: "< x_min" pass, bit 1: "> x_max" pass
-            if (m & 1u) x = P.lon_min;                               // trajectory.py:96
-            if (m & 2u) x = P.lon_max;                               // trajectory.py:97
-        }
-        const int pair = P.level0 + w * P.level_stride + t;
-        if (EULER) {
-            if (P.x_traj) {                                    // level t is final once the pending passes ran
-                const size_t to = ((size_t)w * (P.nsteps + 1) + t) * P.np + (size_t)row * P.ncol + col;
-                P.x_traj[to] = x; P.y_traj[to] = y;
-            }
-            double ua, va;
-            stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
-            __stcs(pw, make_double2(ua, va));
-        } else {
-            const double2 wv = ld_state(pw);
-            stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.hx + row), wv.x, wv.y, x, y);
-        }
-        y = clamp_y(y, P.lat_min, P.lat_max);
-        __stcs(ps, make_double2(x, y));
-        if (x < P.lon_min) {
-            unsigned char* g_lt = flag_slot(P, w, q, 0);
-            int r2, c2;
-            slot_rc(P, e, r2, c2);                                   // rare: re-derived rather than kept live
-            g_lt[r2] = 1; g_lt[P.nrow + c2] = 1;
-        } else if (x > P.lon_max) {
-            const int slot = atomicAdd(P.cand_count + (size_t)w * P.nsub + q, 1);
-            P.cand[(size_t)sbase + slot] = e;
-        }
-    }
-}
-
-#ifndef LCS_CLUSTER_MINBLOCKS
-#define LCS_CLUSTER_MINBLOCKS 2
-#endif
-template <typename T, bool STRICT, int ORDER, int LAYOUT, bool CLUSTERED>
-__global__ void __launch_bounds__(kClusterThreads, LCS_CLUSTER_MINBLOCKS)
-advect_outer_cluster_kernel(const AdvectParams P, const int cs /* CTAs per window = cluster size (1..8) */) {
-    extern __shared__ unsigned char s_f[];                // [rows | cols], bit 0 = "< x_min" flag, bit 1 = "> x_max" flag
-    const int w = blockIdx.x / cs;
-    const int rank = blockIdx.x - w * cs;
-    const int tid_w = rank * kClusterThreads + threadIdx.x;
-    const int nthr_w = cs * kClusterThreads;
-    const int nflag = P.nrow + P.ncol;
-    int q = 0;
-    for (int t = 0; t < P.nsteps; ++t) {
-        for (int k = 0; k <= P.S; ++k, ++q) {
-            // ---- phase A: pending clamps of q-1 (mirrored in smem), stage, y clamp, raise "< x_min" flags
-            if (k == 0) cluster_phase_a<T, STRICT, ORDER, LAYOUT, true>(P, w, q, t, tid_w, nthr_w, s_f);
-            else cluster_phase_a<T, STRICT, ORDER, LAYOUT, false>(P, w, q, t, tid_w, nthr_w, s_f);
-            window_sync<CLUSTERED>();
-            // ---- phase B: mirror the "< x_min" flags; candidates that survive that pass raise "> x_max" flags
-            const unsigned char* g_lt = flag_slot(P, w, q, 0);
-            unsigned char* g_gt = flag_slot(P, w, q, 1);
-            for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_f[i] = __ldcg(g_lt + i);          // 0 / 1
-            __syncthreads();
-            const int ncand = __ldcg(P.cand_count + (size_t)w * P.nsub + q);
-            const int* cand = P.cand + (size_t)w * P.nslots;
-            for (int i = tid_w; i < ncand; i += nthr_w) {
-                int row, col;
-                slot_rc(P, __ldcg(cand + i), row, col);
-                if (!(s_f[row] & s_f[P.nrow + col] & 1)) { g_gt[row] = 1; g_gt[P.nrow + col] = 1; }
-            }
-            window_sync<CLUSTERED>();
-            for (int i = threadIdx.x; i < nflag; i += kClusterThreads) s_f[i] |= (unsigned char)(__ldcg(g_gt + i) << 1);
-            __syncthreads();
-        }
-    }
-    // ---- final: pending clamps of the last sub-step, outputs
-    const double2* spos = reinterpret_cast<const double2*>(P.spos) + (size_t)w * P.nslots;
-    for (int e = tid_w; e < P.nslots; e += nthr_w) {
-        int row, col;
-        if (!slot_rc(P, e, row, col)) continue;
-        double x, y;
-        if (P.nsub == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
-        else {
-            const double2 s = __ldcs(spos + e);
-            x = s.x; y = s.y;
-            const unsigned m = (unsigned)s_f[row] & (unsigned)s_f[P.nrow + col];
-            if (m & 1u) x = P.lon_min;
-            if (m & 2u) x = P.lon_max;
-        }
-        const size_t o = (size_t)row * P.ncol + col;
-        P.x_out[(size_t)w * P.np + o] = x; P.y_out[(size_t)w * P.np + o] = y;
-        if (P.x_traj) {
-            const size_t to = ((size_t)w * (P.nsteps + 1) + P.nsteps) * P.np + o;
-            P.x_traj[to] = x; P.y_traj[to] = y;
-        }
-    }
-}
-
-// Cluster size for `nwindows` windows: the driver reports how many clusters of each size can be co-resident
-// (cluster placement strands SMs: GPCs hold 16/18/20 SMs, so size 4 or 8 does not tile the 148 SMs);
-// a window takes time ~1/cs and the launch runs ceil(nwindows / resident(cs)) waves, so pick the cs that
-// minimises waves/cs.  Returns 0 when even the best choice leaves most of the machine idle.
-template <typename T, bool STRICT, int ORDER, int LAYOUT>
-static int choose_cluster_size(const AdvectParams& P, int nwindows, size_t smem, double* busy_frac) {
-    static int resident[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};           // per instantiation; smem differences are tiny
-    int best = 1;
-    double best_cost = 1e30;
-    for (int cs = 1; cs <= 8; ++cs) {
-        if (!resident[cs]) {
-            int n = 0;
-            if (cs == 1) {
-                auto k1 = advect_outer_cluster_kernel<T, STRICT, ORDER, LAYOUT, false>;
-                int per_sm = 0;
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1, kClusterThreads, smem) == cudaSuccess)
-                    n = per_sm * lcs_sm_count();
-            } else {
-                auto kc = advect_outer_cluster_kernel<T, STRICT, ORDER, LAYOUT, true>;
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3((unsigned)(cs * 64)); cfg.blockDim = dim3(kClusterThreads); cfg.dynamicSmemBytes = smem;
-                cudaLaunchAttribute attr[1];
-                attr[0].id = cudaLaunchAttributeClusterDimension;
-                attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-                cfg.attrs = attr; cfg.numAttrs = 1;
-                if (cudaOccupancyMaxActiveClusters(&n, kc, &cfg) != cudaSuccess) n = 0;
-            }
-            (void)cudaGetLastError();
-            resident[cs] = n > 0 ? n : -1;
-        }
-        if (resident[cs] <= 0) continue;
-        const int waves = (nwindows + resident[cs] - 1) / resident[cs];
-        const double cost = (double)waves / cs;
-        if (cost < best_cost - 1e-12) { best_cost = cost; best = cs; }
-    }
-    if (lcs_env_int("LCS_DEBUG_CLUSTER", 0)) {
-        fprintf(stderr, "[lcs] co-resident clusters by size 1..8:");
-        for (int cs = 1; cs <= 8; ++cs) fprintf(stderr, " %d", resident[cs]);
-        fprintf(stderr, "; %d windows -> cluster size %d\n", nwindows, best);
-    }
-    const int forced = lcs_env_int("LCS_OUTER_CLUSTER", 0);
-    if (forced >= 1 && forced <= 8 && resident[forced] > 0) best = forced;
-    if (resident[best] <= 0) { *busy_frac = 0.0; return 0; }
-    const int waves = (nwindows + resident[best] - 1) / resident[best];
-    *busy_frac = (double)nwindows * best / ((double)waves * lcs_sm_count() * LCS_CLUSTER_MINBLOCKS);
-    return best;
-}
-
-template <typename T, bool STRICT, int ORDER, int LAYOUT>
-static cudaError_t launch_outer_cluster(const AdvectParams& P, int nwindows, int cs, size_t smem, cudaStream_t st) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(nwindows * cs));
-    cfg.blockDim = dim3(kClusterThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (cs == 1) return cudaLaunchKernelEx(&cfg, advect_outer_cluster_kernel<T, STRICT, ORDER, LAYOUT, false>, P, cs);
-    return cudaLaunchKernelEx(&cfg, advect_outer_cluster_kernel<T, STRICT, ORDER, LAYOUT, true>, P, cs);
-}
 
 // ---------------------------------------------------------------------------------------------
 // Outer-product clamp, group-persistent form (the default).  The cluster kernel above keeps one window per CTA
@@ -655,7 +471,7 @@ __device__ __forceinline__ void gst_state(double2* p, double2 v) {
 #endif
 }
 
-template <typename T, bool STRICT, int ORDER, int LAYOUT, bool EULER, int STATE>
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool EULER, int STATE, bool R32>
 __device__ __forceinline__ void group_phase_a(const AdvectParams& P, const GroupParams& G, const int g, const int w,
                                               const int q, const int t, const int e_begin, const int e_end,
                                               const unsigned char* s_f, double2* s_pos, const int wsel) {
@@ -694,11 +510,11 @@ __device__ __forceinline__ void group_phase_a(const AdvectParams& P, const Group
                 P.x_traj[to] = x; P.y_traj[to] = y;
             }
             double ua, va;
-            stage_euler<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
+            stage_euler<T, STRICT, ORDER, LAYOUT, R32>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
             gst_state(pw, make_double2(ua, va));
         } else {
             const double2 wv = gld_state(pw);
-            stage_settls<T, STRICT, ORDER, LAYOUT>(P, pair, pole, __ldg(P.hx + row), wv.x, wv.y, x, y);
+            stage_settls<T, STRICT, ORDER, LAYOUT, R32>(P, pair, pole, __ldg(P.hx + row), wv.x, wv.y, x, y);
         }
         y = clamp_y(y, P.lat_min, P.lat_max);
         if (STATE == 1) *ps = make_double2(x, y);
@@ -716,7 +532,7 @@ __device__ __forceinline__ void group_phase_a(const AdvectParams& P, const Group
     }
 }
 
-template <typename T, bool STRICT, int ORDER, int LAYOUT, int STATE>
+template <typename T, bool STRICT, int ORDER, int LAYOUT, int STATE, bool R32 = false>
 __global__ void __launch_bounds__(kGroupThreads, LCS_GROUP_MINBLOCKS)
 advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -756,8 +572,8 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
         for (int t = 0; t < P.nsteps; ++t) {
             for (int k = 0; k <= P.S; ++k, ++q) {
                 // ---- phase A: pending clamps of q-1 (mirrored in smem), stage, y clamp, raise "< x_min" flags
-                if (k == 0) group_phase_a<T, STRICT, ORDER, LAYOUT, true, STATE>(P, G, g, w, q, t, e_begin, e_end, s_f, s_pos, 2 * g + parity);
-                else group_phase_a<T, STRICT, ORDER, LAYOUT, false, STATE>(P, G, g, w, q, t, e_begin, e_end, s_f, s_pos, 2 * g + parity);
+                if (k == 0) group_phase_a<T, STRICT, ORDER, LAYOUT, true, STATE, R32>(P, G, g, w, q, t, e_begin, e_end, s_f, s_pos, 2 * g + parity);
+                else group_phase_a<T, STRICT, ORDER, LAYOUT, false, STATE, R32>(P, G, g, w, q, t, e_begin, e_end, s_f, s_pos, 2 * g + parity);
                 group_barrier(&ctl->bar, arrivals += gsize, err);
                 // ---- phase B: mirror the "< x_min" flags; candidates that survive that pass raise the "> x_max" flags
                 const unsigned* g_lt = reinterpret_cast<const unsigned*>(wb + G.flags_off + (size_t)(2 * q) * G.nflag_pad);
@@ -830,11 +646,8 @@ static int lcs_blocks_per_sm(const void* func, int threads, size_t smem) {
     return n;
 }
 
-// 0: group-persistent kernel (default), 1: phased launches, 2: hardware cluster per window
-static int lcs_outer_mode() {
-    const int m = lcs_env_int("LCS_OUTER_MODE", 0);
-    return (m == 1 || m == 2) ? m : 0;
-}
+// 0: group-persistent kernel (default), 1: phased launches
+static int lcs_outer_mode() { return lcs_env_int("LCS_OUTER_MODE", 0) == 1 ? 1 : 0; }
 
 // Sizes of the group path that do not depend on the kernel instantiation (lcs_advect_workspace_bytes needs them
 // before the winds are known): windows in flight and the workspace layout.
@@ -875,7 +688,7 @@ static GroupLayout group_layout(int nrow, int ncol, int nslots, int nsub, int nw
     return L;
 }
 
-template <typename T, bool STRICT, int ORDER, int LAYOUT>
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool R32>
 static cudaError_t launch_outer_group(const AdvectParams& P, int nwindows, void* workspace, cudaStream_t st, bool* launched) {
     *launched = false;
     const GroupLayout L = group_layout(P.nrow, P.ncol, P.nslots, P.nsub, nwindows);
@@ -887,8 +700,8 @@ static cudaError_t launch_outer_group(const AdvectParams& P, int nwindows, void*
     const void* fn = nullptr;
     const int cap = lcs_env_int("LCS_OUTER_CTAS", 0);
     for (;; state = 0) {
-        fn = state == 1 ? (const void*)advect_outer_group_kernel<T, STRICT, ORDER, LAYOUT, 1>
-                        : (const void*)advect_outer_group_kernel<T, STRICT, ORDER, LAYOUT, 0>;
+        fn = state == 1 ? (const void*)advect_outer_group_kernel<T, STRICT, ORDER, LAYOUT, 1, R32>
+                        : (const void*)advect_outer_group_kernel<T, STRICT, ORDER, LAYOUT, 0, R32>;
         if (state == 0) {
             smem = (size_t)sflag;
             per_sm_used = lcs_blocks_per_sm(fn, kGroupThreads, smem);
@@ -943,64 +756,45 @@ static cudaError_t launch_outer_group(const AdvectParams& P, int nwindows, void*
 }
 
 // ---------------------------------------------------------------------------------------------
-template <typename T, bool STRICT, int ORDER, int LAYOUT>
+template <typename T, bool STRICT, int ORDER, int LAYOUT, bool R32 = false>
 static cudaError_t launch_advect(const AdvectParams& P, int nwindows, void* workspace, cudaStream_t st) {
     const dim3 block(256);
     const int tw = 256 >> P.band_log2;
     const dim3 grid((unsigned)((P.ncol + tw - 1) / tw), (unsigned)((P.nrow + P.band - 1) / P.band), (unsigned)nwindows);
+    // wide grids: 8 x 32 blocks of one-row warps (see particle_rc); LCS_ADVECT_STRIP=0/1 forces the choice
+    constexpr bool kHasStrip = sizeof(T) == 8 && !STRICT && ORDER == 3 && LAYOUT == kES && !R32;
+    const dim3 sgrid((unsigned)((P.ncol + 31) / 32), (unsigned)((P.nrow + 7) / 8), (unsigned)nwindows);
+    bool strip = false;
+    if (kHasStrip) {
+        const int sv = lcs_env_int("LCS_ADVECT_STRIP", -1);
+        strip = (sv == 1 || (sv < 0 && P.ncol >= 640)) && sgrid.y <= 65535;
+    }
     if (P.xmode != LCS_X_CLAMP_OUTER) {
-        if constexpr (sizeof(T) == 8 && !STRICT && ORDER == 3 && LAYOUT == kES) {
-            // wide grids: 8 x 32 blocks of one-row warps (see particle_rc); LCS_ADVECT_STRIP=0/1 forces the choice
-            const int strip = lcs_env_int("LCS_ADVECT_STRIP", -1);
-            if (strip == 1 || (strip < 0 && P.ncol >= 640)) {
-                const dim3 sgrid((unsigned)((P.ncol + 31) / 32), (unsigned)((P.nrow + 7) / 8), (unsigned)nwindows);
-                if (sgrid.y <= 65535) {
-                    advect_fused_kernel<T, STRICT, ORDER, LAYOUT, true><<<sgrid, block, 0, st>>>(P);
-                    lcs_count_launches(1);
-                    return cudaGetLastError();
-                }
+        if constexpr (kHasStrip) {
+            if (strip) {
+                advect_fused_kernel<T, STRICT, ORDER, LAYOUT, true, R32><<<sgrid, block, 0, st>>>(P);
+                lcs_count_launches(1);
+                return cudaGetLastError();
             }
         }
-        {   // experiment knob: shrink the L1 by reserving a shared-memory carve-out (percent) the kernel does not use
-            const int carve = lcs_env_int("LCS_FUSED_CARVEOUT", -1);
-            if (carve >= 0) cudaFuncSetAttribute(advect_fused_kernel<T, STRICT, ORDER, LAYOUT>,
-                                                 cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-        }
-        advect_fused_kernel<T, STRICT, ORDER, LAYOUT><<<grid, block, 0, st>>>(P);
+        advect_fused_kernel<T, STRICT, ORDER, LAYOUT, false, R32><<<grid, block, 0, st>>>(P);
         lcs_count_launches(1);
         return cudaGetLastError();
     }
-    // Default: the group-persistent kernel (few windows in flight, state in L2 / shared memory).  LCS_OUTER_MODE=1: one
-    // launch pair per sub-step (kernel boundaries as barriers, the independent implementation the tests compare with);
-    // LCS_OUTER_MODE=2: one hardware cluster per window (round-1 kernel, kept for A/B measurements).
-    const int mode = lcs_outer_mode();
-    if (P.nsub > 0 && mode == 0) {
+    // Outer-product clamp.  Default: the group-persistent kernel.  LCS_OUTER_MODE=1: one launch pair per sub-step
+    // (kernel boundaries as barriers) -- the independent implementation the tests compare the persistent kernel with.
+    if (P.nsub > 0 && lcs_outer_mode() == 0) {
         if (P.nrow + P.ncol > 48 * 1024) return cudaErrorInvalidValue;
         bool launched = false;
-        const cudaError_t e = launch_outer_group<T, STRICT, ORDER, LAYOUT>(P, nwindows, workspace, st, &launched);
+        const cudaError_t e = launch_outer_group<T, STRICT, ORDER, LAYOUT, R32>(P, nwindows, workspace, st, &launched);
         return (e == cudaSuccess && !launched) ? cudaErrorLaunchOutOfResources : e;
     }
-    const size_t smem = (size_t)(P.nrow + P.ncol);
-    if (P.nsub > 0 && smem <= 48 * 1024 && mode == 2) {
-        double busy = 0.0;
-        const int cs = choose_cluster_size<T, STRICT, ORDER, LAYOUT>(P, nwindows, smem, &busy);
-        if (cs > 0) {
-            lcs_count_launches(1);
-            return launch_outer_cluster<T, STRICT, ORDER, LAYOUT>(P, nwindows, cs, smem, st);
-        }
-    }
     const dim3 ggrid(4, (unsigned)nwindows);
-    bool strip = false;
-    const dim3 sgrid((unsigned)((P.ncol + 31) / 32), (unsigned)((P.nrow + 7) / 8), (unsigned)nwindows);
-    if constexpr (sizeof(T) == 8 && !STRICT && ORDER == 3 && LAYOUT == kES) {       // wide grids, as for the fused kernel
-        const int s = lcs_env_int("LCS_ADVECT_STRIP", -1);
-        strip = (s == 1 || (s < 0 && P.ncol >= 640)) && sgrid.y <= 65535;
-    }
     for (int q = 0; q < P.nsub; ++q) {
-        if constexpr (sizeof(T) == 8 && !STRICT && ORDER == 3 && LAYOUT == kES) {
-            if (strip) advect_phase_move<T, STRICT, ORDER, LAYOUT, true><<<sgrid, block, 0, st>>>(P, q, q / (1 + P.S), q % (1 + P.S));
+        if constexpr (kHasStrip) {
+            if (strip) advect_phase_move<T, STRICT, ORDER, LAYOUT, true, R32><<<sgrid, block, 0, st>>>(P, q, q / (1 + P.S), q % (1 + P.S));
         }
-        if (!strip) advect_phase_move<T, STRICT, ORDER, LAYOUT><<<grid, block, 0, st>>>(P, q, q / (1 + P.S), q % (1 + P.S));
+        if (!strip) advect_phase_move<T, STRICT, ORDER, LAYOUT, false, R32><<<grid, block, 0, st>>>(P, q, q / (1 + P.S), q % (1 + P.S));
         advect_phase_gtpass<<<ggrid, block, 0, st>>>(P, q);
     }
     advect_phase_final<<<grid, block, 0, st>>>(P);

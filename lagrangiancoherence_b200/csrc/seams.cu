@@ -3,6 +3,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include "lcs_internal.h"
 #include "lcs_device.cuh"
 
@@ -22,14 +23,18 @@ int lcs_env_int(const char* name, int dflt) {
     return (s && *s) ? atoi(s) : dflt;
 }
 int lcs_sm_count() {
-    static int cached = 0;
-    if (!cached) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) cached = n;
-        else cached = 148;
+    // per device (a process may drive several GPUs from several threads); -1 = not queried yet
+    static int cached[64];
+    static std::once_flag once;
+    std::call_once(once, [] { for (int& c : cached) c = -1; });
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { (void)cudaGetLastError(); return 148; }
+    int n = __atomic_load_n(&cached[dev], __ATOMIC_RELAXED);
+    if (n < 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) { (void)cudaGetLastError(); n = 148; }
+        __atomic_store_n(&cached[dev], n, __ATOMIC_RELAXED);          // racing threads store the same value
     }
-    return cached;
+    return n;
 }
 static unsigned long long g_launches = 0;
 void lcs_count_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }

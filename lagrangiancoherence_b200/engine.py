@@ -65,6 +65,7 @@ class StagedWinds:
     coef_a: torch.Tensor | None = None
     coef_b: torch.Tensor | None = None
     raw_planar: bool = False      # ES, orders >= 2: raw_a / raw_b are the planar u / v series (kept alive here)
+    round32: int = 0              # lcs_advect_opts.round32: the reference's dtype propagation for f32 winds
 
     def struct(self):
         p = lambda t: t.data_ptr() if t is not None else None
@@ -82,21 +83,30 @@ class FtleEngine:
     ``'pointwise'``.  ``pair_dtype`` selects the storage of the packed winds: ``'f64'`` (parity
     path) or ``'f32'`` (fast path); positions and the epilogue stay f64 either way.
     ``part_lat``/``part_lon`` seed a particle grid different from the wind grid (extension, C5).
+    ``f32_propagation``: f32 WINDS (on f64 coordinates) are integrated the way the reference's dtypes propagate --
+    scipy returns samples in the input dtype, numpy (NEP 50) forms the y increments in f32 when ``timestep`` is a Python
+    scalar (tools.py:26-30, trajectory.py:86-87,110-112) -- which costs two gathers per SETTLS stage; ``False`` promotes
+    f32 winds to f64 instead (faster, but then only f64 inputs match the reference to 1e-10).
     """
 
     def __init__(self, lat, lon, timestep, SETTLS_order=0, interp_order=3, xmode='outer',
                  pair_dtype='f64', strict=False, device='cuda:0', part_lat=None, part_lon=None, layout='es',
-                 arith='f64'):
+                 arith='f64', f32_propagation=True):
         if not torch.cuda.is_available():
             raise _lib.LcsError('lagrangiancoherence_b200 needs a CUDA device (B200, sm_100a); there is no CPU path')
         self.lib = _lib.load()
         self.device = torch.device(device)
+        # f32 coordinates make the reference integrate entirely in f32 (np.meshgrid of f32 coordinates, trajectory.py:68-70);
+        # that case is promoted to f64 here and agrees to the reference's own f32 noise only (tests/test_gpu_edges.py)
+        self.coords_f64 = np.asarray(lat).dtype == np.float64 and np.asarray(lon).dtype == np.float64
         self.lat = np.ascontiguousarray(lat, dtype=np.float64)
         self.lon = np.ascontiguousarray(lon, dtype=np.float64)
         if np.any(np.diff(self.lat) <= 0) or np.any(np.diff(self.lon) <= 0):
             raise ValueError('latitude/longitude must be ascending (the reference sorts first, LCS.py:101-104)')
         self.nlat, self.nlon = self.lat.size, self.lon.size
         self.timestep = timestep
+        self.timestep_weak = not isinstance(timestep, np.generic)      # Python scalar: weak under NEP 50
+        self.f32_propagation = bool(f32_propagation)
         self.S = int(SETTLS_order)
         self.order = int(interp_order)
         if self.order not in (1, 2, 3, 4, 5):
@@ -154,6 +164,10 @@ class FtleEngine:
             return StagedWinds(self.layout, self.pair_dtype, nlev)
         tdt = torch.float64 if self.pair_dtype == _lib.LCS_F64 else torch.float32
         shape2 = (self.nlat, self.nlon)
+        round32 = 0
+        if (self.f32_propagation and self.coords_f64 and u.dtype == torch.float32 and v.dtype == torch.float32 and self.pair_dtype == _lib.LCS_F64
+                and self.layout == _lib.LCS_LAYOUT_ES and self.arith == _lib.LCS_ARITH_F64):
+            round32 = 1 if self.timestep_weak else 2
         with torch.cuda.device(self.device):
             st = _stream(self.device)
             cu = cv = None
@@ -189,9 +203,9 @@ class FtleEngine:
                 ce_, cs_ = pack_es(cu, cv, _lib.LCS_F64)
                 if raw == 'planar':
                     return StagedWinds(self.layout, self.pair_dtype, nlev, raw_a=u, raw_b=v, coef_a=ce_, coef_b=cs_,
-                                       raw_planar=True)
+                                       raw_planar=True, round32=round32)
             re_, rs_ = pack_es(u, v, _dtype_code(u))
-            return StagedWinds(self.layout, self.pair_dtype, nlev, raw_a=re_, raw_b=rs_, coef_a=ce_, coef_b=cs_)
+            return StagedWinds(self.layout, self.pair_dtype, nlev, raw_a=re_, raw_b=rs_, coef_a=ce_, coef_b=cs_, round32=round32)
 
     def _to_device(self, a):
         if isinstance(a, torch.Tensor):
@@ -233,7 +247,7 @@ class FtleEngine:
                                   self.d_plat[r0:].data_ptr(), self.d_plon.data_ptr(),
                                   self.d_kx[r0:].data_ptr(), self.d_hx[r0:].data_ptr(), self.ky, self.hy)
             opts = _lib.AdvectOpts(nsteps, self.S, self.order, self.xmode, self.strict,
-                                   nwindows, level0, level_stride, self.arith)
+                                   nwindows, level0, level_stride, self.arith, staged.round32)
             need = self.lib.lcs_advect_workspace_bytes(C.byref(part), C.byref(opts))
             ws = None
             if need:

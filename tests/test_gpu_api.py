@@ -153,6 +153,26 @@ def test_rolling_matches_per_window_calls(cuda_device):
         assert close_fraction(fields[s], ref, FTLE_REL) >= 0.995
 
 
+def test_rolling_inf_in_an_early_chunk_still_raises(cuda_device):
+    """scipy.linalg.norm(check_finite=True) raises on any inf derivative (LCS.py:154).  The rolling driver runs one
+    epilogue per chunk and checks once at the end: an inf met by the FIRST chunk must survive the later launches."""
+    from lagrangiancoherence_b200 import rolling
+    from lagrangiancoherence_b200.engine import FtleEngine
+    lat = np.linspace(-30.0, 10.0, 41)
+    lon = np.linspace(-80.0, -24.0, 57)
+    u, v = S.era5_like_winds(lat, lon, 12)
+    eng = FtleEngine(lat, lon, -21600, SETTLS_order=1, xmode='pointwise', device=cuda_device)
+    dy = eng.dy
+    eng.dy = 0.0                                     # zero metric spacing -> +-inf derivatives (first chunk only)
+
+    def restore(first, fields):
+        eng.dy = dy
+    with pytest.raises(ValueError, match='infs or NaNs'):
+        rolling.rolling_ftle(u, v, lat, lon, 3, -21600, SETTLS_order=1, xclamp='pointwise', engine=eng, chunk=3, on_chunk=restore)
+    out = rolling.rolling_ftle(u, v, lat, lon, 3, -21600, SETTLS_order=1, xclamp='pointwise', engine=eng, chunk=3)   # flag was cleared
+    assert np.isfinite(out).any()
+
+
 def test_bench_line_has_the_contract_keys(cuda_device):
     """`python bench.py` prints ONE JSON line carrying the driver's contract (value, e2e with the copied bytes, kernel
     launch count, clocks, roofline with the live-measured ceiling, cpu_baseline unless skipped)."""

@@ -1,6 +1,6 @@
 """Seeded random sweep of the integrator + epilogue against the oracle: ragged grid shapes (partial tiles, odd sizes),
 both interpolation orders, SETTLS orders 0..5, both signs of the time step, all three x-boundaries, wind strengths from
-"nobody exits" to "most particles exit", single and multiple windows (phased and cluster paths)."""
+"nobody exits" to "most particles exit", single and multiple windows (phased launches and the group-persistent kernel)."""
 import numpy as np
 import pytest
 import torch
@@ -9,6 +9,7 @@ from oracle import lcs_oracle as O
 from lagrangiancoherence_b200 import synthetic as S
 
 pytestmark = pytest.mark.gpu
+OUTLIER_MAX = 1e-6      # bound on the magnitude of flipped-branch outliers (relative to the domain scale); B200 runs show none at all
 
 
 def make_case(seed):
@@ -37,8 +38,10 @@ def test_random_configuration(cuda_device, seed, monkeypatch):
         pytest.skip('degenerate grid')
     eng = FtleEngine(lat, lon, c['dt'], SETTLS_order=c['S'], interp_order=c['order'], xmode=c['xmode'], device=cuda_device)
     st = eng.stage(c['u'], c['v'])
-    if c['nwin'] > 1 and c['xmode'] == 'outer':
-        monkeypatch.setenv('LCS_OUTER_MODE', '2')                      # exercise the persistent cluster kernel too
+    if c['xmode'] == 'outer' and seed % 3 == 0:
+        monkeypatch.setenv('LCS_OUTER_MODE', '1')                      # a third of the outer cases through the phased launches
+    elif c['xmode'] == 'outer' and seed % 3 == 1:
+        monkeypatch.setenv('LCS_OUTER_GROUPS', '1')                    # ... a third with the whole machine on one window at a time
     x, y = eng.advect(st, nsteps=nt - 1, nwindows=c['nwin'])
     sig = eng.epilogue(x, y).cpu().numpy()
     x, y = x.cpu().numpy(), y.cpu().numpy()
@@ -48,7 +51,8 @@ def test_random_configuration(cuda_device, seed, monkeypatch):
                                       interp_order=c['order'], cyclic_xboundary=c['xmode'] == 'cyclic',
                                       xclamp='pointwise' if c['xmode'] == 'pointwise' else 'outer')
         ex, ey = np.abs(x[w] - rx) / sx, np.abs(y[w] - ry) / sy
-        assert (ex > 1e-10).mean() <= 2e-3 and (ey > 1e-10).mean() <= 2e-3, (c['xmode'], c['order'], c['S'], ex.max(), ey.max())
+        from conftest import position_parity
+        position_parity(f"fuzz{seed}.{w} {c['xmode']} p{c['order']} S{c['S']}", ex, ey, 1e-10, 2e-3, OUTLIER_MAX)
         ref = O.spectral_norm_field(O.flowmap_gradient(rx, ry, lat, lon))
         ok = np.abs(sig[w] - ref) <= 1e-5 * np.abs(ref) + 1e-9
         assert ok.mean() >= 0.99, ok.mean()
