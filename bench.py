@@ -36,6 +36,7 @@ METRIC = 'particle-steps/s'
 
 
 DEFAULT_BATCH = {'C2': 1184, 'C4': 1184, 'C3': 8}
+DEFAULT_BATCH_ROWBANDS = {'C2': 8, 'C4': 8, 'C3': 1}
 
 
 def parse():
@@ -55,11 +56,18 @@ def parse():
                     help="'f64' parity path (default, the headline); 'f32' f32 packed winds with f64 tap arithmetic; "
                          "'f32fast' f32 winds and f32 tap arithmetic (tolerance-tested fast path)")
     ap.add_argument('--workload', default='C2', choices=['C2', 'C3', 'C4'])
+    ap.add_argument('--sharding', default='starts', choices=['starts', 'rowbands'],
+                    help="multi-GPU sharding: 'starts' = independent start times per rank (weak scaling, the headline); "
+                         "'rowbands' = every rank integrates a band of particle rows of the SAME windows (strong scaling, BASELINE "
+                         "configs[2]: use with --workload C3)")
+    ap.add_argument('--host-dtype', default='f64', choices=['f64', 'f32'],
+                    help="dtype of the host winds of the end-to-end path; 'f32' (how ERA5 is stored) halves the upload but then the "
+                         "f64 path follows the reference's f32 dtype propagation (round32: two gathers per SETTLS stage)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--chunk', type=int, default=148, help='windows per launch in the pipelined end-to-end path')
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = DEFAULT_BATCH[args.workload]
+        args.batch = (DEFAULT_BATCH_ROWBANDS if args.sharding == 'rowbands' else DEFAULT_BATCH)[args.workload]
     return args
 
 
@@ -76,11 +84,17 @@ def workload(name):
 
 
 def config_dict(args, desc, B, world):
+    if args.sharding == 'rowbands':
+        shard = f'row bands x{world} (2-row recomputed halo, winds replicated' + ('' if world == 1 else ', bands gathered inside the timed region') + ')'
+        what = f'step = {B} field(s), particle rows split over the GPUs'
+    else:
+        shard = f'start-times x{world}' + ('' if world == 1 else ', finished fields gathered on rank 0 inside the timed region ('
+                                                    + os.environ.get('LCS_BENCH_GATHER', 'p2p') + ')')
+        what = f'step = {B} rolling start times per GPU'
     return {'workload': f'{desc}, SETTLS_order={S_ORDER}, interp_order={args.order}, {args.precision} winds, '
-                        f'xclamp={args.xclamp}; step = {B} rolling start times per GPU',
+                        f'xclamp={args.xclamp}; {what}',
             'grid': desc.split(',')[0], 'windows_per_step_per_gpu': B, 'xclamp': args.xclamp,
-            'interp_order': args.order, 'settls_order': S_ORDER, 'sharding': f'start-times x{world}' + ('' if world == 1 else ', finished fields gathered on every rank inside the timed '
-                                                                  'region (' + os.environ.get('LCS_BENCH_GATHER', 'p2p') + ')'),
+            'interp_order': args.order, 'settls_order': S_ORDER, 'sharding': shard,
             'l2': 'flushed between timed steps (256 MiB write)'}
 
 
@@ -197,14 +211,24 @@ def run_reference(args):
 # ----------------------------------------------------------------------------- CUDA arm
 def ncu_traffic(args, B):
     """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
-    `ncu --set full` capture of this very command line (profiles/r01_traffic.json); null for any other config."""
+    `ncu --set full` capture of this very command line (profiles/r02_traffic.json); None for any other config."""
     try:
-        table = json.load(open(os.path.join(ROOT, 'profiles', 'r01_traffic.json')))
+        table = json.load(open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')))
     except OSError:
         return None
-    key = f'{args.workload}:{args.xclamp}:p{args.order}:{args.precision}:B{B}'
+    key = f'{args.workload}:{args.xclamp}:p{args.order}:{args.precision}:B{B}:{args.sharding}'
     entry = table.get(key)
     return entry['dram_bytes_per_launch'] if entry else None
+
+
+def measured_peaks():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except OSError:
+        peaks = {}
+    if 'hbm_gbs' in peaks:
+        return peaks['hbm_gbs'], 'MEASURED_PEAKS.json (measured copy)'
+    return 6650.0, 'fallback 6650 GB/s (B200_PROFILING.md)'
 
 
 def run_b200(args):
@@ -225,42 +249,47 @@ def run_b200(args):
     lib = _lib.load()
     lat, lon, nt, dt, desc = workload(args.workload)
     B = args.batch
+    rowbands = args.sharding == 'rowbands'
     nlev = B + nt - 1
     npts = lat.size * lon.size
-    # rank r owns start times [r*B, (r+1)*B) of one long synthetic series (start-time sharding)
-    u, v = S.era5_like_winds(lat, lon, nlev, t0=rank * B)
-    if args.precision != 'f64':
-        u, v = u.astype(np.float32), v.astype(np.float32)
+    # start-time sharding: rank r owns start times [r*B, (r+1)*B) of one long synthetic series (weak scaling);
+    # row bands: every rank holds the SAME B windows and integrates its band of particle rows (strong scaling)
+    u, v = S.era5_like_winds(lat, lon, nlev, t0=0 if rowbands else rank * B)
+    host_dtype = np.float32 if (args.precision != 'f64' or args.host_dtype == 'f32') else np.float64
+    u, v = u.astype(host_dtype), v.astype(host_dtype)
     h_u = torch.from_numpy(u).pin_memory()
     h_v = torch.from_numpy(v).pin_memory()
     d_u, d_v = h_u.to(dev), h_v.to(dev)
     eng = FtleEngine(lat, lon, dt, SETTLS_order=S_ORDER, interp_order=args.order, xmode=args.xclamp,
                      device=dev, **precision_args(args.precision))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gather_mode = os.environ.get('LCS_BENCH_GATHER', 'p2p')          # 'p2p' (NVLink peer copies) | 'nccl' (all_gather)
-    gathered = peer = None
-    if world > 1 and gather_mode == 'p2p':
-        # symmetric memory needs CUDA VMM handle exchange between the ranks; where the box forbids it every rank
-        # falls back to the NCCL all_gather (agreed through an all_reduce so that no rank is left behind)
-        try:
-            from lagrangiancoherence_b200.peer import PeerFields
-            peer = PeerFields([B] * world, lat.size, lon.size, device=dev)
-        except Exception as exc:                                    # noqa: BLE001
-            sys.stderr.write(f'[bench] rank {rank}: peer gather unavailable ({exc!r}); using NCCL all_gather\n')
-            peer = None
-        agree = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=dev)
-        dist.all_reduce(agree, op=dist.ReduceOp.MIN)
-        if int(agree.item()) == 0:
-            peer, gather_mode = None, 'nccl'
-            os.environ['LCS_BENCH_GATHER'] = 'nccl'
-    if world > 1 and peer is None:
-        gathered = [torch.empty((B, lat.size, lon.size), dtype=torch.float64, device=dev) for _ in range(world)]
-    x = torch.empty((B, lat.size, lon.size), dtype=torch.float64, device=dev)
-    y = torch.empty_like(x)
     ev = lambda: torch.cuda.Event(enable_timing=True)
     adv_ms = []
 
-    def step(timed):
+    # ---- the gather of finished fields onto rank 0 (the only exchange on this path)
+    gather_mode = os.environ.get('LCS_BENCH_GATHER', 'p2p')          # 'p2p' (NVLink peer copies) | 'nccl'
+    peer = None
+    gathered = None
+    if world > 1 and not rowbands:
+        if gather_mode == 'p2p':
+            # symmetric memory needs CUDA VMM handle exchange between the ranks; where the box forbids it every rank
+            # falls back to NCCL (agreed through an all_reduce so that no rank is left behind)
+            try:
+                from lagrangiancoherence_b200.peer import PeerFields
+                peer = PeerFields([B] * world, lat.size, lon.size, device=dev, dst=0)
+            except Exception as exc:                                    # noqa: BLE001
+                sys.stderr.write(f'[bench] rank {rank}: peer gather unavailable ({exc!r}); using NCCL gather\n')
+                peer = None
+            agree = torch.tensor([1 if peer is not None else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+            if int(agree.item()) == 0:
+                peer, gather_mode = None, 'nccl'
+        if peer is None and rank == 0:
+            gathered = torch.empty((world, B, lat.size, lon.size), dtype=torch.float64, device=dev)
+    x = torch.empty((B, lat.size, lon.size), dtype=torch.float64, device=dev)
+    y = torch.empty_like(x)
+
+    def step_starts(timed):
         st = eng.stage(d_u, d_v)
         if world == 1:
             a, b = ev(), ev()
@@ -271,10 +300,9 @@ def run_b200(args):
             if timed:
                 adv_ms.append([(a, b)])
             return sigma
-        # N > 1: the batch goes in parts (whole waves of 296 windows where B allows, else halves), so that the gather
-        # of a finished part's fields (the only exchange on this path: NVLink peer copies, or NCCL all_gather with
-        # LCS_BENCH_GATHER=nccl) runs while the next part is integrated
-        nparts = B // 296 if (B % 296 == 0 and B >= 592) else 2
+        # N > 1: the batch goes in parts (whole waves of 296 windows where B allows, else halves) so that the push of
+        # a finished part's fields to rank 0 (NVLink copy engines, or NCCL gather) runs while the next part is integrated
+        nparts = B // 296 if (B % 296 == 0 and B >= 592) else (2 if B >= 2 else 1)
         bounds = [B * i // nparts for i in range(nparts + 1)]
         works, evs, sig = [], [], []
         for lo, n in ((bounds[i], bounds[i + 1] - bounds[i]) for i in range(nparts)):
@@ -287,7 +315,8 @@ def run_b200(args):
             if peer is not None:
                 peer.push(lo, sig[-1])
             else:
-                works.append(dist.all_gather([g[lo:lo + n] for g in gathered], sig[-1], async_op=True))
+                dst_list = [gathered[r, lo:lo + n] for r in range(world)] if rank == 0 else None
+                works.append(dist.gather(sig[-1], dst_list, dst=0, async_op=True))
         for w in works:
             w.wait()
         if peer is not None:
@@ -295,6 +324,20 @@ def run_b200(args):
         if timed:
             adv_ms.append(evs)
         return sig
+
+    def step_bands(timed):
+        st = eng.stage(d_u, d_v)                                        # replicated: particles of any band roam the whole domain
+        a, b = ev(), ev()
+        a.record()
+        out0, out1, in0, in1 = rolling.shard_rows(lat.size, world, rank)
+        xb, yb = eng.advect(st, nsteps=nt - 1, nwindows=B, rows=(in0, in1))
+        b.record()
+        band = eng.epilogue(xb, yb, in_row0=in0, out_rows=(out0, out1))
+        if timed:
+            adv_ms.append([(a, b)])
+        return rolling.gather_bands(band, lat.size) if world > 1 else band
+
+    step = step_bands if rowbands else step_starts
 
     def barrier():
         if world > 1:
@@ -308,17 +351,19 @@ def run_b200(args):
     launches0 = lib.lcs_kernel_launches()
     t_wall0 = time.time()
     step_ms = []
+    last = None
     for _ in range(args.steps):
         flush.fill_(1)                              # evict L2 between timed iterations
         barrier()
         a, b = ev(), ev()
         a.record()
-        step(True)
+        last = step(True)
         b.record()
         barrier()
         step_ms.append(a.elapsed_time(b))
     t_wall1 = time.time()
     launches_timed = int(lib.lcs_kernel_launches() - launches0)
+    eng.check_finite()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     total_ms = float(np.sum(step_ms))
     if world > 1:
@@ -326,49 +371,98 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     advect_ms = float(np.mean([sum(a.elapsed_time(b) for a, b in evs) for evs in adv_ms]))
-    psteps_step = world * B * npts * (nt - 1)
+    work_ranks = 1 if rowbands else world                           # row bands split ONE batch; start times add batches
+    psteps_step = work_ranks * B * npts * (nt - 1)
     value = psteps_step * args.steps / (total_ms * 1e-3)
 
-    # ---- end to end through the public rolling API: pinned host winds in, host fields out
-    h_out = torch.empty((B, lat.size, lon.size), dtype=torch.float64).pin_memory()
+    # ---- outside the timed region: rank 0 checks what it gathered against its own single-GPU recomputation
+    gather_check = None
+    if world > 1 and rank == 0:
+        if rowbands:
+            full = last
+            st = eng.stage(d_u, d_v)
+            xs, ys = eng.advect(st, nsteps=nt - 1, nwindows=B)
+            ref = eng.epilogue(xs, ys)
+            gather_check = {'what': 'row bands gathered on rank 0 vs the whole field integrated by rank 0 alone',
+                            'fields': int(B), 'bit_identical': bool(torch.equal(full, ref))}
+        else:
+            got = peer.local if peer is not None else gathered
+            ok, checked = True, 0
+            for r in range(world):
+                for s_ in sorted({0, B // 2, B - 1}):
+                    uu, vv = S.era5_like_winds(lat, lon, nt, t0=r * B + s_)
+                    uu, vv = uu.astype(host_dtype), vv.astype(host_dtype)
+                    st = eng.stage(torch.from_numpy(uu).to(dev), torch.from_numpy(vv).to(dev))
+                    xs, ys = eng.advect(st, nsteps=nt - 1, nwindows=1)
+                    ok = ok and bool(torch.equal(eng.epilogue(xs, ys)[0], got[r, s_]))
+                    checked += 1
+            gather_check = {'what': 'fields gathered on rank 0 (%s) vs single-window recomputation on rank 0' % gather_mode,
+                            'windows': checked, 'bit_identical': ok}
+
+    # ---- end to end through the public API: pinned host winds in, host fields out, every step
     e2e_ms = []
-    for i in range(args.warmup + args.steps):
-        flush.fill_(1)
-        barrier()
-        a, b = ev(), ev()
-        a.record()
-        rolling.rolling_ftle(h_u, h_v, lat, lon, nt, dt, SETTLS_order=S_ORDER, interp_order=args.order,
-                             xclamp=args.xclamp, precision=args.precision, device=dev, out=h_out, chunk=args.chunk,
-                             engine=eng)
-        b.record()
-        barrier()
-        if i >= args.warmup:
-            e2e_ms.append(a.elapsed_time(b))
+    if rowbands:
+        h_out = torch.empty((B, lat.size, lon.size), dtype=torch.float64).pin_memory() if rank == 0 else None
+        bu, bv = torch.empty_like(d_u), torch.empty_like(d_v)
+        for i in range(args.warmup + args.steps):
+            flush.fill_(1)
+            barrier()
+            a, b = ev(), ev()
+            a.record()
+            bu.copy_(h_u, non_blocking=True)
+            bv.copy_(h_v, non_blocking=True)
+            full = rolling.ftle_row_bands(eng, bu, bv, nwindows=B) if world > 1 else eng.epilogue(*eng.advect(eng.stage(bu, bv), nsteps=nt - 1, nwindows=B))
+            if rank == 0:
+                h_out.copy_(full, non_blocking=True)
+            b.record()
+            barrier()
+            if i >= args.warmup:
+                e2e_ms.append(a.elapsed_time(b))
+        api = 'lagrangiancoherence_b200.rolling.ftle_row_bands (pinned host winds in on every rank, gathered field out on rank 0)'
+        h2d, d2h = 2 * nlev * npts * u.itemsize, B * npts * 8
+    else:
+        h_out = torch.empty((B, lat.size, lon.size), dtype=torch.float64).pin_memory()
+        for i in range(args.warmup + args.steps):
+            flush.fill_(1)
+            barrier()
+            a, b = ev(), ev()
+            a.record()
+            rolling.rolling_ftle(h_u, h_v, lat, lon, nt, dt, SETTLS_order=S_ORDER, interp_order=args.order,
+                                 xclamp=args.xclamp, precision=args.precision, device=dev, out=h_out, chunk=args.chunk,
+                                 engine=eng)
+            b.record()
+            barrier()
+            if i >= args.warmup:
+                e2e_ms.append(a.elapsed_time(b))
+        api = ('lagrangiancoherence_b200.rolling.rolling_ftle (pinned host winds in, pinned host fields out; every rank keeps '
+               'its own start times -- the consumer is the host, nothing is gathered)')
+        h2d, d2h = 2 * nlev * npts * u.itemsize, B * npts * 8
     e2e_total = float(np.sum(e2e_ms))
     if world > 1:
         t = torch.tensor([e2e_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_total = float(t.item())
     e2e_value = psteps_step * args.steps / (e2e_total * 1e-3)
-    elt = 8 if args.precision == 'f64' else 4
-    h2d = 2 * nlev * npts * elt
-    d2h = B * npts * 8
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel(s): the departure-point integrator.
+    # ---- roofline of the dominant kernel: the departure-point integrator.
     # Bytes per particle-step: the reference formulation gathers (2+4S)(p+1)^2 values of w bytes (SURVEY 8(d):
     # 2304 B at S=4, p=3, f64).  The ES layout pre-combines the SETTLS operand 2f_k - f_{k+1} per grid point, so
     # the kernel gathers (1+S)(p+1)^2 two-value elements = 1280 B.  The roofline uses the bytes the kernel moves
     # through the bounding L1 data pipe and the measured ceiling for exactly that element size; the reference-
-    # formulation figure is reported beside it (it exceeds its own ceiling: that is the algorithmic saving).
+    # formulation figure is reported beside it, informational (it exceeds its own ceiling: the algorithmic saving).
+    elt = 8 if args.precision == 'f64' else 4
     taps = (args.order + 1) ** 2
     survey_bytes_pstep = (2 + 4 * S_ORDER) * taps * elt
     issued_bytes_pstep = (1 + S_ORDER) * taps * 2 * elt
-    psteps_launch = B * npts * (nt - 1)
+    if eng.pair_dtype == _lib.LCS_F64 and host_dtype == np.float32 and eng.f32_propagation:
+        issued_bytes_pstep = (1 + 2 * S_ORDER) * taps * 2 * elt      # round32: levels k and k+1 sampled separately
+    rows_rank = lat.size if not rowbands else (lambda r: r[3] - r[2])(rolling.shard_rows(lat.size, world, rank))
+    psteps_launch = B * rows_rank * lon.size * (nt - 1)
     achieved = psteps_launch * issued_bytes_pstep / (advect_ms * 1e-3) / 1e9
     achieved_survey = psteps_launch * survey_bytes_pstep / (advect_ms * 1e-3) / 1e9
     # measured ceiling: lcs_gather_peak = same taps x taps pattern and thread tiling, coherent positions, integer
@@ -376,10 +470,11 @@ def run_b200(args):
     sink = torch.zeros(1, dtype=torch.float64, device=dev)
     iters = 40
     buf = torch.zeros((lat.size * lon.size + 8) * 4 * elt, dtype=torch.uint8, device=dev)
+    Bp = max(B, 296)                                                    # enough windows to fill the machine
 
     def measure_peak(vec):
         gp = lambda: _lib.check(lib.lcs_gather_peak(_ptr(buf), eng.pair_dtype, vec, lat.size, lon.size, lat.size, lon.size,
-                                                    B, args.order + 1, 0.0, iters, _ptr(sink), _stream(dev)), 'lcs_gather_peak')
+                                                    Bp, args.order + 1, 0.0, iters, _ptr(sink), _stream(dev)), 'lcs_gather_peak')
         for _ in range(3):
             gp()
         torch.cuda.synchronize(dev)
@@ -389,61 +484,62 @@ def run_b200(args):
             a.record(); gp(); b.record()
             torch.cuda.synchronize(dev)
             best = min(best, a.elapsed_time(b))
-        return B * npts * iters * taps * vec * elt / (best * 1e-3) / 1e9
+        return Bp * npts * iters * taps * vec * elt / (best * 1e-3) / 1e9
     gather_peak_es = measure_peak(2)         # 2-value elements: what the ES kernel issues
     gather_peak = measure_peak(4)            # 4-value elements: the reference formulation's taps
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-    except OSError:
-        pass
-    hbm_peak = peaks.get('hbm_gbs', 6650.0)
-    hbm_src = 'MEASURED_PEAKS.json (measured copy)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
-    # compulsory HBM traffic of the integrator: every packed pair level read once, final positions written once
-    hbm_bytes = (nlev - 1) * npts * 4 * elt + B * 2 * npts * 8
-    clustered = args.xclamp == 'outer' and B >= 19
-    kernel_name = ('advect_outer_cluster_kernel (one persistent cluster per window, one launch per step)' if clustered else
-                   'advect_phase_move x%d + advect_phase_gtpass (launch pair per sub-step)' % ((nt - 1) * (1 + S_ORDER))
-                   if args.xclamp == 'outer' else 'advect_fused_kernel (one launch per step)')
+    hbm_peak, hbm_src = measured_peaks()
+    # compulsory HBM traffic of the integrator: every staged level read once, final positions written once
+    hbm_bytes = (nlev * 2 - 1) * npts * 2 * elt + B * 2 * rows_rank * lon.size * 8
+    traffic = ncu_traffic(args, B)
+    outer = args.xclamp == 'outer'
+    kernel_name = ('advect_outer_group_kernel (one cooperative launch per step: resident CTA groups draw windows, group '
+                   'barriers per sub-step)' if outer else 'advect_fused_kernel (one launch per step)')
+    hbm = {'peak': hbm_peak, 'unit': 'GB/s', 'peak_source': hbm_src, 'compulsory_bytes': hbm_bytes,
+           'compulsory_frac': hbm_bytes / (advect_ms * 1e-3) / 1e9 / hbm_peak}
+    if traffic is not None:
+        hbm.update({'measured_bytes': traffic, 'achieved': traffic / (advect_ms * 1e-3) / 1e9,
+                    'frac': traffic / (advect_ms * 1e-3) / 1e9 / hbm_peak,
+                    'source': 'dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full capture of this '
+                              'command, profiles/r02_traffic.json) over the live CUDA-event time'})
+    note = ('L1/L2 -> SM gather throughput (SURVEY 8(d)); not tensor: nothing on this path is a dense contraction.  HBM: '
+            + ('the outer-clamp kernel also streams its position / Euler-sample state (48 B per particle sub-step) through DRAM -- '
+               'see roofline.hbm.frac for the measured share of the copy bandwidth; shrinking the windows in flight until that '
+               'state is L2-resident was measured and is slower (DESIGN.md 4), the kernel is bound by L1 wavefronts and issue '
+               'slots' if outer else 'compulsory traffic only (levels read once, positions written once), see roofline.hbm'))
     line = {
         'metric': METRIC, 'value': value, 'unit': 'particle-steps/s', 'n_gpus': world, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+        'scaling': 'strong' if rowbands else 'weak',
         'vs_baseline': None, 'dtype': {'f64': 'f64', 'f32': 'f32 winds / f64 tap arithmetic and positions',
                                        'f32fast': 'f32 winds and tap arithmetic / f64 index map and positions'}[args.precision],
         'data': 'synthetic', 'config': config_dict(args, desc, B, world),
-        'fields_per_s': world * B * args.steps / (total_ms * 1e-3),
+        'fields_per_s': work_ranks * B * args.steps / (total_ms * 1e-3),
         'interpolations_per_s': value * (2 + 4 * S_ORDER),
         'e2e': {'value': e2e_value, 'unit': 'particle-steps/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'ms_per_step': e2e_total / args.steps, 'fields_per_s': world * B * args.steps / (e2e_total * 1e-3),
-                'api': 'lagrangiancoherence_b200.rolling.rolling_ftle (pinned host winds in, pinned host fields out)'},
+                'ms_per_step': e2e_total / args.steps, 'fields_per_s': work_ranks * B * args.steps / (e2e_total * 1e-3),
+                'api': api},
         'gpu_launches': launches_timed,
         'gpu_launches_per_step': launches_timed / args.steps,
         'clocks': clocks,
         'host_binding': numa,
+        'gather_check': gather_check,
         'roofline': {
             'bound': 'l1-gather',
-            'bound_note': 'L1/L2 -> SM gather throughput (SURVEY 8(d)); not hbm (see roofline.hbm: <2 % of the measured copy '
-                          'bandwidth), not tensor: nothing on this path is a dense contraction',
+            'bound_note': note,
             'kernel': kernel_name,
             'achieved': achieved, 'peak': gather_peak_es, 'unit': 'GB/s', 'frac': achieved / gather_peak_es,
             'bytes_per_particle_step': issued_bytes_pstep,
-            # SURVEY 8(d) / BASELINE.md figure beside it: the reference formulation's (2+4S)(p+1)^2 w bytes per particle-step
-            # over the same kernel time, against the measured ceiling for 4-value taps (details in reference_formulation)
-            'algorithmic_bytes_per_particle_step': survey_bytes_pstep,
-            'achieved_algorithmic': achieved_survey, 'frac_algorithmic': achieved_survey / gather_peak,
             'peak_source': 'lcs_gather_peak measured in this run: %dx%d-tap gathers of %d-B elements (what the ES kernel '
                            'issues) on an L2-resident level, same thread tiling, coherent positions, no dependent arithmetic'
                            % (args.order + 1, args.order + 1, 2 * elt),
-            'reference_formulation': {
-                'bytes_per_particle_step': survey_bytes_pstep, 'achieved': achieved_survey, 'peak': gather_peak,
-                'unit': 'GB/s', 'frac': achieved_survey / gather_peak,
-                'note': 'SURVEY 8(d) figure: (2+4S)(p+1)^2 w bytes per particle-step against the ceiling for %d-B (4-value) taps; '
-                        'above 1 because the ES layout needs 2 values per tap, not 4' % (4 * elt)},
+            # informational: SURVEY 8(d)'s (2+4S)(p+1)^2 w bytes per particle-step over the same kernel time, against the
+            # ceiling for 4-value taps; above 1 because the ES layout needs 2 values per tap, not 4
+            'reference_formulation': {'bytes_per_particle_step': survey_bytes_pstep, 'achieved': achieved_survey,
+                                      'peak': gather_peak, 'unit': 'GB/s', 'frac': achieved_survey / gather_peak,
+                                      'note': 'informational only'},
             'advect_ms_per_step': advect_ms,
-            'traffic': ncu_traffic(args, B),
-            'hbm': {'achieved': hbm_bytes / (advect_ms * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-                    'frac': hbm_bytes / (advect_ms * 1e-3) / 1e9 / hbm_peak, 'peak_source': hbm_src,
-                    'compulsory_bytes': hbm_bytes},
+            'traffic': traffic,
+            'hbm': hbm,
         },
     }
     if not args.no_cpu_baseline:

@@ -72,6 +72,25 @@ typedef struct lcs_particles {
     double ky, hy;               /* timestep * conversion_y ; 0.5 * timestep * conversion_y     */
 } lcs_particles;
 
+/* Row-band sharding across GPUs under LCS_X_CLAMP_OUTER: the as-executed clamp sets every (row, column)
+ * with the row AND the column holding an exit (trajectory.py:96-97).  Rows are whole inside a band, so the row flags are
+ * local; the column flags are the OR over all bands.  With `xrank` set, the integrator of every rank posts its band's
+ * column flags after each sub-step into every rank's mailbox over NVLink (plain stores into peer-mapped memory, then a
+ * release flag), waits for the others inside the persistent kernel, and continues with the OR -- twice per sub-step
+ * when particles also left through x_max.  All ranks must call lcs_advect with the same windows, sub-steps and ngroups.
+ *   mailboxes : DEVICE pointer to an array[world] of device pointers, entry d = rank d's mailbox buffer as mapped into
+ *               this process (e.g. torch symmetric memory: buffer_ptrs_dev).  The buffers must be zero before the first
+ *               call and are reused by later calls (they carry a running exchange number); mailbox_bytes >=
+ *               lcs_xrank_mailbox_bytes(world, ngroups, ncol) each.
+ *   ngroups   : windows in flight (1 = the whole GPU on one window at a time), identical on every rank. */
+typedef struct lcs_xrank {
+    int32_t world, rank;
+    int32_t ngroups, reserved;
+    const void* mailboxes;
+    size_t mailbox_bytes;
+} lcs_xrank;
+size_t lcs_xrank_mailbox_bytes(int world, int ngroups, int ncol);
+
 typedef struct lcs_advect_opts {
     int32_t nsteps;         /* wind intervals to cross = nt-1 (trajectory.py:80)                 */
     int32_t settls_order;   /* accumulating sub-iterations per interval (trajectory.py:100)      */
@@ -90,6 +109,7 @@ typedef struct lcs_advect_opts {
                                (timestep is a numpy f64 scalar, e.g. after resample=).  Needs LCS_LAYOUT_ES of f64
                                coefficients computed from the f32 winds; levels k and k+1 are then sampled
                                separately, so a SETTLS stage costs two gathers                                  */
+    const lcs_xrank* xrank; /* NULL, or the cross-rank exchange of the outer clamp for row-band sharding (above)      */
 } lcs_advect_opts;
 
 /* Staged winds handed to the integrator.

@@ -31,11 +31,16 @@ class Particles(C.Structure):
                 ('ky', c_double), ('hy', c_double)]
 
 
+class XRank(C.Structure):
+    _fields_ = [('world', C.c_int32), ('rank', C.c_int32), ('ngroups', C.c_int32), ('reserved', C.c_int32),
+                ('mailboxes', c_void_p), ('mailbox_bytes', c_size_t)]
+
+
 class AdvectOpts(C.Structure):
     _fields_ = [('nsteps', C.c_int32), ('settls_order', C.c_int32), ('interp_order', C.c_int32),
                 ('xmode', C.c_int32), ('strict', C.c_int32),
                 ('nwindows', C.c_int32), ('level0', C.c_int32), ('level_stride', C.c_int32), ('arith', C.c_int32),
-                ('round32', C.c_int32)]
+                ('round32', C.c_int32), ('xrank', C.POINTER(XRank))]
 
 
 class Winds(C.Structure):
@@ -58,6 +63,7 @@ SIGNATURES = {
     'lcs_gaussian_filter2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     'lcs_advect_workspace_bytes': (c_size_t, [C.POINTER(Particles), C.POINTER(AdvectOpts)]),
     'lcs_advect_check': (c_int, [c_void_p, c_void_p]),
+    'lcs_xrank_mailbox_bytes': (c_size_t, [c_int, c_int, c_int]),
     'lcs_pack_es': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'lcs_advect': (c_int, [C.POINTER(Grid), C.POINTER(Particles), C.POINTER(AdvectOpts), C.POINTER(Winds),
                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

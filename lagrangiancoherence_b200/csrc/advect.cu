@@ -40,8 +40,14 @@ extern "C" size_t lcs_advect_workspace_bytes(const lcs_particles* p, const lcs_a
     const size_t nsub = (size_t)o->nsteps * (1 + o->settls_order);
     if (nsub == 0) return 0;
     if (lcs_outer_mode() != 0) return ws_layout(p, o).total;       // phased launches / hardware clusters: state per window
-    const GroupLayout L = group_layout(p->nrow, p->ncol, (int)lcs_slots_per_window(p->nrow, p->ncol), (int)nsub, o->nwindows);
+    const int xg = (o->xrank && o->xrank->world > 1) ? o->xrank->ngroups : 0;
+    const GroupLayout L = group_layout(p->nrow, p->ncol, (int)lcs_slots_per_window(p->nrow, p->ncol), (int)nsub, o->nwindows, xg);
     return L.total;
+}
+
+extern "C" size_t lcs_xrank_mailbox_bytes(int world, int ngroups, int ncol) {
+    if (world < 1 || ngroups < 1 || ncol < 1) return 0;
+    return kXrHdrBytes + (size_t)ngroups * 2 * (size_t)world * xr_msg_stride(ncol);
 }
 
 extern "C" int lcs_advect_check(const void* workspace, void* stream) {
@@ -81,6 +87,15 @@ extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_a
     if (o->round32 < 0 || o->round32 > 2) return lcs_fail(LCS_E_INVALID, "lcs_advect: round32 must be 0, 1 or 2");
     if (o->round32 && (w->layout != LCS_LAYOUT_ES || w->dtype != LCS_F64 || o->strict || o->arith != LCS_ARITH_F64))
         return lcs_fail(LCS_E_UNSUPPORTED, "lcs_advect: round32 (f32 dtype propagation) needs f64 ES levels, strict 0, f64 arithmetic");
+    if (o->xrank && o->xrank->world > 1) {
+        const lcs_xrank* xr = o->xrank;
+        if (o->xmode != LCS_X_CLAMP_OUTER) return lcs_fail(LCS_E_INVALID, "lcs_advect: xrank is for LCS_X_CLAMP_OUTER (the other x-boundaries need no exchange)");
+        if (lcs_outer_mode() != 0) return lcs_fail(LCS_E_UNSUPPORTED, "lcs_advect: xrank needs the group-persistent kernel (LCS_OUTER_MODE=0)");
+        if (xr->rank < 0 || xr->rank >= xr->world || xr->world > kGroupThreads || xr->ngroups < 1 || xr->ngroups > 256 || xr->ngroups > o->nwindows || !xr->mailboxes)
+            return lcs_fail(LCS_E_INVALID, "lcs_advect: bad xrank (need 0 <= rank < world, 1 <= ngroups <= min(nwindows, 256), mailboxes)");
+        if (xr->mailbox_bytes < lcs_xrank_mailbox_bytes(xr->world, xr->ngroups, p->ncol))
+            return lcs_fail(LCS_E_WORKSPACE, "lcs_advect: xrank mailboxes too small (lcs_xrank_mailbox_bytes)");
+    }
     if (g->nlat < 4 || g->nlon < 4) return lcs_fail(LCS_E_INVALID, "lcs_advect: grid must be at least 4x4");
     if (p->nrow < 1 || p->ncol < 1 || o->nwindows < 1 || o->nsteps < 0 || o->settls_order < 0)
         return lcs_fail(LCS_E_INVALID, "lcs_advect: bad sizes");
@@ -116,6 +131,7 @@ extern "C" int lcs_advect(const lcs_grid* g, const lcs_particles* p, const lcs_a
     if ((P.nrow + P.band - 1) / P.band > 65535) return lcs_fail(LCS_E_INVALID, "lcs_advect: too many row bands");
     P.x_out = x_out; P.y_out = y_out; P.x_traj = x_traj; P.y_traj = y_traj;
     P.nsub = o->nsteps * (1 + o->settls_order);
+    P.xr_host = (o->xrank && o->xrank->world > 1) ? o->xrank : nullptr;
     {   // persistent-kernel slot enumeration; tile / ntc for 0 <= tile < 2^31 as a multiply-high:
         // k = floor(log2 ntc), magic = ceil(2^(32+k) / ntc) < 2^32; the rounding error stays below 1/ntc
         P.ntc = (P.ncol + 15) / 16;

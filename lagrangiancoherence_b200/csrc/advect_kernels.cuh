@@ -63,6 +63,7 @@ struct AdvectParams {
     int* cand_count;              // [nwindows][nsub]
     unsigned char* flags;         // [nwindows][nsub][2][nrow+ncol]
     int nsub;
+    const lcs_xrank* xr_host;              // host pointer (launcher only): cross-rank exchange of the outer clamp, or NULL
     int nslots, ntc;                       // persistent kernel: slots per window (tiles of 2x16), tile columns
     unsigned ntc_magic; int ntc_shift;     // tile / ntc as a multiply-high, see slot_rc
 };
@@ -408,7 +409,10 @@ __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefe
 // list itself.  A group of one CTA degenerates to the per-CTA kernel; a single window is integrated by the
 // whole machine (one group), which is the low-latency single-field path.
 struct GroupHdr { unsigned next_window; unsigned error; unsigned pad[30]; };           // 128 B
-struct GroupCtl { unsigned bar; int window; unsigned pad[30]; };                       // 128 B apart: own L2 line each
+struct GroupCtl {                                     // 256 B per group: the arrival counter and the words the pollers read sit in different L2 lines
+    unsigned bar; unsigned pad0[31];
+    unsigned released; int window; unsigned pad1[30];
+};
 struct GroupParams {
     GroupHdr* hdr;
     GroupCtl* ctl;                // [ngroups]
@@ -416,10 +420,21 @@ struct GroupParams {
     double2* wind;                // [ngroups][nslots]  Euler-stage samples of the current interval
     int* cand;                    // [ngroups][2][nslots]  slots with x > lon_max after sub-step q: buffer q & 1 (a fast CTA appends
                                   //                       those of q+1 while a slow one still scans those of q)
-    unsigned char* wbase;         // [ngroups][2 window parities][wstride]: { int count[nsub] | u8 flags[nsub][2][nflag_pad] }
+    unsigned char* wbase;         // [ngroups][2 window parities][wstride]: { int count[2][nsub] | u8 flags[nsub][2][nflag_pad] }
     size_t wstride, flags_off;
     int ngroups, ncta, nwindows, nflag_pad, sflag_bytes, redundant_max, prefetch, per_sm;
+    // Row-band sharding across GPUs under the outer clamp: the row flags of a band are local (rows are whole), the column
+    // flags are the OR over all bands.  xr_world > 1: after the local barrier of a sub-step the group's first CTA posts
+    // its band's column flags (and candidate count) into every rank's mailbox over NVLink, waits for everybody's, and
+    // writes the OR back into the local flag page (include/lcs_b200.h: lcs_xrank).
+    int xr_world, xr_rank;
+    unsigned char* const* xr_mail;        // [world] mailbox base of every rank as mapped into this process
+    size_t xr_group_stride, xr_msg_stride, xr_hdr_bytes;
 };
+
+struct XrMsg { unsigned seq, ncand, pad0, pad1; };         // followed by the column flags (bytes)
+constexpr size_t kXrHdrBytes = 1024;                      // unsigned seq[ngroups <= 256]: running exchange number per group
+
 
 #ifndef LCS_GROUP_THREADS
 #define LCS_GROUP_THREADS 512
@@ -437,17 +452,25 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
 }
 
 // Barrier over the CTAs of one group (all resident: cooperative launch).  `target` = arrivals expected since launch.
-// The same fence / atomic / spin / fence sequence cooperative_groups uses for grid.sync().
-__device__ __forceinline__ void group_barrier(unsigned* bar, unsigned target, unsigned* err) {
+// One thread per CTA: acq_rel fence (this CTA's writes, ordered before it by bar.sync, become visible at gpu scope),
+// arrive on the group's counter, then poll a SEPARATE release word that the last arriver bumps to `target` -- the
+// pollers then read a line nobody is hammering with atomics -- and a second acq_rel fence before the CTA goes on.
+// Data written by other CTAs is read with ld.cg afterwards (L2), the read-only wind levels may stay in L1.
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void group_barrier(GroupCtl* ctl, unsigned target, unsigned* err) {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1u);
-        unsigned spins = 0;
-        while ((int)(ld_volatile_u32(bar) - target) < 0) {
-            if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_volatile_u32(err))) { atomicExch(err, 1u); break; }
+        fence_acq_rel_gpu();
+        if (atomicAdd(&ctl->bar, 1u) + 1u == target) {
+            fence_acq_rel_gpu();          // acquire the other CTAs' arrivals before releasing everybody (cumulativity)
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(&ctl->released), "r"(target) : "memory");
+        } else {
+            unsigned spins = 0;
+            while ((int)(ld_volatile_u32(&ctl->released) - target) < 0) {
+                if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_volatile_u32(err))) { atomicExch(err, 1u); break; }
+            }
         }
-        __threadfence();
+        fence_acq_rel_gpu();
     }
     __syncthreads();
 }
@@ -532,6 +555,52 @@ __device__ __forceinline__ void group_phase_a(const AdvectParams& P, const Group
     }
 }
 
+__device__ __forceinline__ void fence_acq_rel_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
+// Exchange number `seq` of group g, run by every thread of the group's first CTA: OR the `ncol` column-flag bytes at
+// `cols` (local global memory, complete: the group barrier ran) over all ranks, in place, and return the sum of
+// `my_ncand`.  Messages are double-buffered by seq & 1: a rank posts exchange e+2 only after it finished e+1, which
+// every rank posted only after reading all of e.
+__device__ __forceinline__ unsigned xr_exchange(const GroupParams& G, int g, unsigned seq, unsigned char* cols, int ncol,
+                                                unsigned my_ncand, unsigned* err, unsigned* s_total) {
+    const size_t slot = (size_t)g * G.xr_group_stride + (size_t)(seq & 1u) * G.xr_world * G.xr_msg_stride;
+    const size_t mine = G.xr_hdr_bytes + slot + (size_t)G.xr_rank * G.xr_msg_stride;
+    for (int d = 0; d < G.xr_world; ++d) {                                   // post: plain stores into peer memory
+        unsigned char* m = G.xr_mail[d] + mine + sizeof(XrMsg);
+        for (int i = threadIdx.x; i < ncol; i += kGroupThreads) m[i] = __ldcg(cols + i);
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < G.xr_world) {
+        fence_acq_rel_sys();                                                 // the CTA's stores (ordered by bar.sync) before the flag
+        XrMsg* m = reinterpret_cast<XrMsg*>(G.xr_mail[threadIdx.x] + mine);
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" :: "l"(&m->ncand), "r"(my_ncand) : "memory");
+        asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(&m->seq), "r"(seq) : "memory");
+        // wait for the message of rank threadIdx.x in the local mailbox
+        const XrMsg* in = reinterpret_cast<const XrMsg*>(G.xr_mail[G.xr_rank] + G.xr_hdr_bytes + slot + (size_t)threadIdx.x * G.xr_msg_stride);
+        unsigned spins = 0, v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&in->seq) : "memory");
+            if (v == seq) break;
+            if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_volatile_u32(err))) { atomicExch(err, 1u); break; }
+        }
+        unsigned nc;
+        asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(nc) : "l"(&in->ncand) : "memory");
+        atomicAdd(s_total, nc);
+        fence_acq_rel_sys();
+    }
+    __syncthreads();
+    const unsigned char* base = G.xr_mail[G.xr_rank] + G.xr_hdr_bytes + slot + sizeof(XrMsg);
+    for (int i = threadIdx.x; i < ncol; i += kGroupThreads) {
+        unsigned char o = 0;
+        for (int r = 0; r < G.xr_world; ++r) o |= __ldcg(base + (size_t)r * G.xr_msg_stride + i);
+        __stcg(cols + i, o);
+    }
+    const unsigned total = *s_total;
+    __syncthreads();
+    if (threadIdx.x == 0) *s_total = 0;
+    return total;
+}
+
 template <typename T, bool STRICT, int ORDER, int LAYOUT, int STATE, bool R32 = false>
 __global__ void __launch_bounds__(kGroupThreads, LCS_GROUP_MINBLOCKS)
 advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
@@ -550,13 +619,23 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
     // slots of this CTA: a contiguous block (whole 2x16 tiles), swept in order -- consecutive iterations of a warp then
     // touch neighbouring particle rows, whose 4x4 stencils share three of five coefficient rows in L1 (a group-strided
     // assignment lost that: ncu showed the L1 hit rate falling from 64 % to 59 % between groups of 1 and 8 CTAs)
-    const int chunk = (P.nslots + nthr_w - 1) / nthr_w * kGroupThreads;
+    const int chunk = ((P.nslots >> 5) + gsize - 1) / gsize * 32;      // whole 2x16 tiles, the same number for every CTA of the group
     const int e_begin = (bid - c0) * chunk + threadIdx.x;
     const int e_end = min((bid - c0 + 1) * chunk, P.nslots);
     GroupCtl* const ctl = G.ctl + g;
     unsigned* const err = &G.hdr->error;
     unsigned arrivals = 0;                                // arrivals of this group expected at its next barrier
     int parity = 0;
+    const bool xr = G.xr_world > 1;
+    const bool leader = bid == c0;                        // the group's first CTA runs the cross-rank exchanges
+    __shared__ unsigned s_xr_total;
+    unsigned xr_seq = 0;                                  // running exchange number of this group (persists across calls)
+    if (xr && leader) {
+        if (threadIdx.x == 0) s_xr_total = 0;
+        xr_seq = __ldcg(reinterpret_cast<const unsigned*>(G.xr_mail[G.xr_rank]) + g);
+        __syncthreads();
+    }
+    int wstatic = g;                                      // cross-rank mode: window -> group assignment must agree on all ranks
     for (;;) {
         unsigned char* const wb = G.wbase + ((size_t)g * 2 + parity) * G.wstride;
         {   // this window's candidate counters and exit flags start cleared (the other parity may still be read)
@@ -564,8 +643,9 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
             const int n16 = (int)(G.wstride >> 4);
             for (int i = tid_w; i < n16; i += nthr_w) __stcg(c + i, make_uint4(0u, 0u, 0u, 0u));
         }
-        if (tid_w == 0) ctl->window = (int)atomicAdd(&G.hdr->next_window, 1u);
-        group_barrier(&ctl->bar, arrivals += gsize, err);
+        if (tid_w == 0) { ctl->window = xr ? wstatic : (int)atomicAdd(&G.hdr->next_window, 1u); }
+        wstatic += G.ngroups;
+        group_barrier(ctl, arrivals += gsize, err);
         const int w = __ldcg(&ctl->window);
         if (w >= G.nwindows) break;
         int q = 0;
@@ -574,16 +654,27 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
                 // ---- phase A: pending clamps of q-1 (mirrored in smem), stage, y clamp, raise "< x_min" flags
                 if (k == 0) group_phase_a<T, STRICT, ORDER, LAYOUT, true, STATE, R32>(P, G, g, w, q, t, e_begin, e_end, s_f, s_pos, 2 * g + parity);
                 else group_phase_a<T, STRICT, ORDER, LAYOUT, false, STATE, R32>(P, G, g, w, q, t, e_begin, e_end, s_f, s_pos, 2 * g + parity);
-                group_barrier(&ctl->bar, arrivals += gsize, err);
+                group_barrier(ctl, arrivals += gsize, err);
+                unsigned char* const lt_page = wb + G.flags_off + (size_t)(2 * q) * G.nflag_pad;
+                int* const counts = reinterpret_cast<int*>(wb);
+                if (xr) {
+                    // ---- cross-rank: OR the "< x_min" column flags of all bands, sum the candidate counts
+                    if (leader) {
+                        const unsigned total = xr_exchange(G, g, ++xr_seq, lt_page + P.nrow, P.ncol, (unsigned)__ldcg(counts + q), err, &s_xr_total);
+                        if (threadIdx.x == 0) __stcg(counts + P.nsub + q, (int)total);
+                    }
+                    group_barrier(ctl, arrivals += gsize, err);
+                }
                 // ---- phase B: mirror the "< x_min" flags; candidates that survive that pass raise the "> x_max" flags
-                const unsigned* g_lt = reinterpret_cast<const unsigned*>(wb + G.flags_off + (size_t)(2 * q) * G.nflag_pad);
+                const unsigned* g_lt = reinterpret_cast<const unsigned*>(lt_page);
                 unsigned* const s_f32 = reinterpret_cast<unsigned*>(s_f);
+                const int ncand = __ldcg(counts + q);                                                              // in flight with the mirror loads
+                const int ncand_all = xr ? __ldcg(counts + P.nsub + q) : ncand;                                    // over all ranks
                 for (int i = threadIdx.x; i < (G.nflag_pad >> 2); i += kGroupThreads) s_f32[i] = __ldcg(g_lt + i);   // bytes 0 / 1
                 __syncthreads();
-                const int ncand = __ldcg(reinterpret_cast<const int*>(wb) + q);
-                if (ncand > 0) {                                     // uniform over the group
+                if (ncand_all > 0) {                                 // uniform over the group (and over the ranks)
                     const int* cand = G.cand + (size_t)(2 * g + (q & 1)) * P.nslots;
-                    if (ncand <= G.redundant_max) {
+                    if (!xr && ncand <= G.redundant_max) {
                         // few candidates: every CTA scans them all and sets the "> x_max" bits itself -- no second barrier
                         for (int i = threadIdx.x; i < ncand; i += kGroupThreads) {
                             int row, col;
@@ -593,13 +684,17 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
                         }
                         __syncthreads();
                     } else {
-                        unsigned char* g_gt = wb + G.flags_off + (size_t)(2 * q + 1) * G.nflag_pad;
+                        unsigned char* g_gt = lt_page + G.nflag_pad;
                         for (int i = tid_w; i < ncand; i += nthr_w) {
                             int row, col;
                             slot_rc(P, __ldcg(cand + i), row, col);
                             if (!(s_f[row] & s_f[P.nrow + col] & 1)) { g_gt[row] = 1; g_gt[P.nrow + col] = 1; }
                         }
-                        group_barrier(&ctl->bar, arrivals += gsize, err);
+                        group_barrier(ctl, arrivals += gsize, err);
+                        if (xr) {
+                            if (leader) xr_exchange(G, g, ++xr_seq, g_gt + P.nrow, P.ncol, 0u, err, &s_xr_total);
+                            group_barrier(ctl, arrivals += gsize, err);
+                        }
                         const unsigned* g_gt32 = reinterpret_cast<const unsigned*>(g_gt);
                         for (int i = threadIdx.x; i < (G.nflag_pad >> 2); i += kGroupThreads) s_f32[i] |= __ldcg(g_gt32 + i) << 1;
                         __syncthreads();
@@ -627,6 +722,7 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
         }
         parity ^= 1;
     }
+    if (xr && leader && threadIdx.x == 0) __stcg(reinterpret_cast<unsigned*>(G.xr_mail[G.xr_rank]) + g, xr_seq);
 }
 
 // Occupancy of a kernel on the current device, cached per (device, kernel, block, shared memory); thread-safe.
@@ -658,7 +754,9 @@ struct GroupLayout {
     size_t hdr, ctl, pos, wind, cand, wbase, head_bytes, total;
 };
 static size_t lcs_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-static GroupLayout group_layout(int nrow, int ncol, int nslots, int nsub, int nwindows) {
+static size_t xr_msg_stride(int ncol) { return lcs_align_up(sizeof(XrMsg) + (size_t)ncol, 16); }
+
+static GroupLayout group_layout(int nrow, int ncol, int nslots, int nsub, int nwindows, int xr_groups = 0) {
     GroupLayout L;
     // Windows in flight.  Measured (C2, 1184 windows, B200): one CTA per window is fastest -- 71.8 ms against 74.6 / 79.9 ms
     // with 2 / 8 CTAs per window, although the latter keep the state of the windows in flight inside L2: the kernel is
@@ -670,12 +768,13 @@ static GroupLayout group_layout(int nrow, int ncol, int nslots, int nsub, int nw
     if (l2mb > 0) n = ((long long)l2mb << 20) / ((long long)nslots * 32);
     const int forced = lcs_env_int("LCS_OUTER_GROUPS", 0);
     if (forced > 0) n = forced;
+    if (xr_groups > 0) n = xr_groups;                    // cross-rank mode: the caller fixes the windows in flight for all ranks
     if (n < 1) n = 1;
     if (n > nwindows) n = nwindows;
     if (n > 4 * lcs_sm_count()) n = 4 * lcs_sm_count();
     L.ngroups_max = (int)n;
     L.nflag_pad = (int)lcs_align_up((size_t)(nrow + ncol), 16);
-    L.flags_off = lcs_align_up((size_t)nsub * sizeof(int), 16);
+    L.flags_off = lcs_align_up((size_t)nsub * 2 * sizeof(int), 16);      // candidate counts: local, and summed over the ranks
     L.wstride = L.flags_off + (size_t)nsub * 2 * L.nflag_pad;
     L.hdr = 0;
     L.ctl = L.hdr + sizeof(GroupHdr);
@@ -691,7 +790,8 @@ static GroupLayout group_layout(int nrow, int ncol, int nslots, int nsub, int nw
 template <typename T, bool STRICT, int ORDER, int LAYOUT, bool R32>
 static cudaError_t launch_outer_group(const AdvectParams& P, int nwindows, void* workspace, cudaStream_t st, bool* launched) {
     *launched = false;
-    const GroupLayout L = group_layout(P.nrow, P.ncol, P.nslots, P.nsub, nwindows);
+    const lcs_xrank* xr = (P.xr_host && P.xr_host->world > 1) ? P.xr_host : nullptr;
+    const GroupLayout L = group_layout(P.nrow, P.ncol, P.nslots, P.nsub, nwindows, xr ? xr->ngroups : 0);
     int state = lcs_env_int("LCS_OUTER_STATE", 0);               // 0: positions in global memory (L2), 1: in shared memory
     const int nsm = lcs_sm_count();
     const int sflag = (int)lcs_align_up((size_t)L.nflag_pad, 16);
@@ -716,7 +816,8 @@ static cudaError_t launch_outer_group(const AdvectParams& P, int nwindows, void*
                 if (cap > 0 && cap < c) c = cap;
                 const int n = L.ngroups_max < c ? L.ngroups_max : c;
                 const int gmin = c / n;                               // smallest group
-                const int iters = (P.nslots + gmin * kGroupThreads - 1) / (gmin * kGroupThreads);
+                const int chunk = ((P.nslots >> 5) + gmin - 1) / gmin * 32;
+                const int iters = (chunk + kGroupThreads - 1) / kGroupThreads;
                 smem = (size_t)sflag + (size_t)iters * kGroupThreads * sizeof(double2);
                 if (smem > 200 * 1024) continue;
                 if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) continue;
@@ -729,6 +830,7 @@ static cudaError_t launch_outer_group(const AdvectParams& P, int nwindows, void*
     }
     if (ncta < 1) return cudaSuccess;                                 // caller reports the failure
     ngroups = L.ngroups_max < ncta ? L.ngroups_max : ncta;
+    if (xr && ngroups != xr->ngroups) return cudaErrorInvalidValue;    // every rank must run the same groups
     if ((unsigned long long)ngroups * (unsigned long long)P.nslots >= (1ULL << 32)) return cudaSuccess;
     char* wsb = static_cast<char*>(workspace);
     GroupParams G{};
@@ -743,6 +845,13 @@ static cudaError_t launch_outer_group(const AdvectParams& P, int nwindows, void*
     G.redundant_max = lcs_env_int("LCS_OUTER_REDUNDANT", 2048);
     G.prefetch = lcs_env_int("LCS_OUTER_PREFETCH", 1);
     G.per_sm = lcs_env_int("LCS_OUTER_SAMESM", 0) ? per_sm_used : 1;
+    if (xr) {
+        G.xr_world = xr->world; G.xr_rank = xr->rank;
+        G.xr_mail = static_cast<unsigned char* const*>(xr->mailboxes);
+        G.xr_msg_stride = xr_msg_stride(P.ncol);
+        G.xr_group_stride = 2 * (size_t)xr->world * G.xr_msg_stride;
+        G.xr_hdr_bytes = kXrHdrBytes;
+    }
     cudaError_t e = cudaMemsetAsync(wsb, 0, L.head_bytes, st);        // window counter, error word, barrier counters
     if (e != cudaSuccess) return e;
     if (lcs_env_int("LCS_DEBUG_CLUSTER", 0))

@@ -221,8 +221,9 @@ class FtleEngine:
 
     # ------------------------------------------------------------------ integrator
     def advect(self, staged, nsteps=None, nwindows=1, level0=0, level_stride=1, return_traj=False,
-               rows=None, out=None):
-        """Run lcs_advect.  ``rows=(r0, r1)`` restricts to a band of particle rows (global indices).
+               rows=None, out=None, xrank=None):
+        """Run lcs_advect.  ``rows=(r0, r1)`` restricts to a band of particle rows (global indices); ``xrank`` = a
+        ``peer.ColumnFlagMail`` when the bands of an outer-clamp integration are spread over several GPUs.
 
         Returns ``(x, y)`` shaped ``[nwindows, nrow, ncol]`` (+ ``(x_traj, y_traj)`` shaped
         ``[nwindows, nsteps+1, nrow, ncol]`` with ``return_traj``).
@@ -247,7 +248,8 @@ class FtleEngine:
                                   self.d_plat[r0:].data_ptr(), self.d_plon.data_ptr(),
                                   self.d_kx[r0:].data_ptr(), self.d_hx[r0:].data_ptr(), self.ky, self.hy)
             opts = _lib.AdvectOpts(nsteps, self.S, self.order, self.xmode, self.strict,
-                                   nwindows, level0, level_stride, self.arith, staged.round32)
+                                   nwindows, level0, level_stride, self.arith, staged.round32,
+                                   C.pointer(xrank.struct) if xrank is not None else None)
             need = self.lib.lcs_advect_workspace_bytes(C.byref(part), C.byref(opts))
             ws = None
             if need:

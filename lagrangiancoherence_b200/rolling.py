@@ -9,8 +9,9 @@ Sharding, one process per GPU, no data-path collective:
   * start times  -- rank r owns a contiguous block of windows (``shard_starts``);
   * row bands    -- rank r integrates particle rows [r0-2, r1+2) (2-row recomputed halo for the
                     +-2 y-stencil, tools.py:204-207) and writes rows [r0, r1) (``shard_rows``);
-                    valid for the cyclic / pointwise x-boundary only: the as-executed outer-product
-                    clamp (quirk Q6) couples rows through the per-sub-step column flags.
+                    Under the as-executed outer-product clamp (quirk Q6) the bands are coupled through
+                    the per-sub-step column exit flags: those are OR-ed across the ranks inside the
+                    persistent kernel over NVLink mailboxes (peer.ColumnFlagMail), rows stay local.
 NCCL is used only to gather the finished fields (``gather_fields`` / ``gather_bands``).
 """
 from __future__ import annotations
@@ -191,15 +192,27 @@ def gather_bands(local_band, nrows, group=None):
     return full.movedim(0, -2).contiguous()
 
 
-def band_ftle(engine, staged, world_size, rank, nsteps=None, nwindows=1, level0=0, log_scale=False):
+XRANK_MAX_GROUPS = 16        # windows in flight per rank in the cross-rank outer-clamp mode (same on every rank)
+
+
+def band_ftle(engine, staged, world_size, rank, nsteps=None, nwindows=1, level0=0, log_scale=False, group=None):
     """Row-band shard of one (or several) fields: integrate own rows + 2-row halo, run the epilogue
-    on own rows.  Returns ``(sigma_band [nwindows, rows, nlon], (out0, out1))``."""
+    on own rows.  Returns ``(sigma_band [nwindows, rows, nlon], (out0, out1))``.
+
+    Cyclic / pointwise x-boundary: particles are independent, no exchange.  As-executed outer-product clamp (quirk Q6):
+    the row flags of a band are local, the column flags are OR-ed over all bands after every sub-step through NVLink
+    mailboxes inside the persistent kernel (``peer.ColumnFlagMail``; needs a process group on CUDA devices)."""
     from . import _lib
-    if engine.xmode == _lib.LCS_X_CLAMP_OUTER and world_size > 1:
-        raise ValueError("row-band sharding needs xmode 'cyclic' or 'pointwise': the as-executed outer-product "
-                         'x-clamp couples all rows each sub-step (use start-time sharding instead)')
     out0, out1, in0, in1 = shard_rows(engine.nlat, world_size, rank)
-    x, y = engine.advect(staged, nsteps=nsteps, nwindows=nwindows, level0=level0, rows=(in0, in1))
+    xrank = None
+    if engine.xmode == _lib.LCS_X_CLAMP_OUTER and world_size > 1:
+        ngroups = min(nwindows, XRANK_MAX_GROUPS)
+        cache = getattr(engine, '_xrank', None)
+        if cache is None or cache.ngroups != ngroups or cache.world != world_size:
+            from .peer import ColumnFlagMail
+            cache = engine._xrank = ColumnFlagMail(engine.part_lon.size, ngroups, group=group, device=engine.device)
+        xrank = cache
+    x, y = engine.advect(staged, nsteps=nsteps, nwindows=nwindows, level0=level0, rows=(in0, in1), xrank=xrank)
     sigma = engine.epilogue(x, y, log_scale=log_scale, in_row0=in0, out_rows=(out0, out1))
     return sigma, (out0, out1)
 
@@ -222,21 +235,26 @@ def rolling_ftle_sharded(u, v, lat, lon, window_levels, timestep, group=None, ds
         from .peer import PeerFields
         engine = kw.get('engine')
         device = engine.device if engine is not None else kw.get('device', 'cuda:0')
-        peer = PeerFields(counts, len(lat), len(lon), group=group, device=device)
+        peer = PeerFields(counts, len(lat), len(lon), group=group, device=device, dst=dst)
         rolling_ftle(u, v, lat, lon, window_levels, timestep, starts=(first, count), return_device=True,
                      on_chunk=peer.push, **kw)
         peer.finish()
-        return peer.result()
+        return peer.result() if dst is None or rank == dst else None
     if gather != 'nccl':
         raise ValueError("gather must be 'nccl' or 'p2p'")
     mine = rolling_ftle(u, v, lat, lon, window_levels, timestep, starts=(first, count), return_device=True, **kw)
     return gather_fields(mine, counts, group=group, dst=dst)
 
 
-def ftle_row_bands(engine, u, v, group=None, log_scale=False):
-    """Row-band sharding of ONE field over the ranks of ``group`` (winds replicated, 2-row recomputed halo,
-    cyclic / pointwise x-boundary only).  Returns the full ``[nlat, nlon]`` field on every rank."""
+def ftle_row_bands(engine, u, v, group=None, log_scale=False, nwindows=None):
+    """Row-band sharding of ONE field (or, ``nwindows=n``, of the ``n`` rolling windows of the series) over the ranks
+    of ``group``: winds replicated, 2-row recomputed halo; under the outer-product clamp the column exit flags are
+    exchanged between the ranks after every sub-step (``band_ftle``).  Returns the full ``[nlat, nlon]`` field
+    (``[n, nlat, nlon]`` with ``nwindows``) on every rank."""
     import torch.distributed as dist
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    band, _ = band_ftle(engine, engine.stage(u, v), world, rank, log_scale=log_scale)
-    return gather_bands(band, engine.nlat, group=group)[0]
+    n = 1 if nwindows is None else int(nwindows)
+    staged = engine.stage(u, v)
+    band, _ = band_ftle(engine, staged, world, rank, nsteps=staged.nlev - n, nwindows=n, log_scale=log_scale, group=group)
+    full = gather_bands(band, engine.nlat, group=group)
+    return full[0] if nwindows is None else full

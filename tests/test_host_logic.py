@@ -35,7 +35,7 @@ def test_ctypes_structs_match_the_header_layout(lib_path):
     from lagrangiancoherence_b200 import _lib
     assert ctypes.sizeof(_lib.Grid) == 8 + 4 * 8
     assert ctypes.sizeof(_lib.Particles) == 16 + 4 * 8 + 2 * 8
-    assert ctypes.sizeof(_lib.AdvectOpts) == 10 * 4
+    assert ctypes.sizeof(_lib.AdvectOpts) == 10 * 4 + 8 and ctypes.sizeof(_lib.XRank) == 16 + 8 + 8
     assert ctypes.sizeof(_lib.Winds) == 8 + 4 * 8 + 8
 
 
