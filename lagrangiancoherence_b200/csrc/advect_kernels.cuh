@@ -394,6 +394,9 @@ __device__ __forceinline__ bool slot_rc(const AdvectParams& P, int e, int& row, 
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) {     // p 16-B aligned, bytes a multiple of 16
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(p), "r"(bytes) : "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 // Outer-product clamp, group-persistent form (the default).  The cluster kernel above keeps one window per CTA
@@ -504,7 +507,14 @@ __device__ __forceinline__ void group_phase_a(const AdvectParams& P, const Group
     for (int e = e_begin; e < e_end; e += nthr_w, ++it) {
         double2* const ps = (STATE == 1) ? s_pos + (it * kGroupThreads + threadIdx.x) : G.pos + (sbase + (unsigned)e);
         double2* const pw = G.wind + (sbase + (unsigned)e);
-        if (G.prefetch && e + nthr_w < e_end) {                      // next slot's state: on its way by the time it is needed
+        if (G.prefetch == 3) {
+            // one bulk L2 prefetch per CTA and iteration (TMA unit: no LSU wavefronts, unlike 2 x 16 prefetch instructions)
+            if (threadIdx.x == 0 && e + nthr_w < e_end) {
+                const unsigned bytes = (unsigned)min(nthr_w, e_end - (e + nthr_w)) * (unsigned)sizeof(double2);
+                if (STATE == 0 && q != 0) bulk_prefetch_l2(ps + nthr_w, bytes);
+                if (!EULER) bulk_prefetch_l2(pw + nthr_w, bytes);
+            }
+        } else if (G.prefetch && e + nthr_w < e_end) {               // next slot's state: on its way by the time it is needed
             if (G.prefetch == 1) {
                 if (STATE == 0 && q != 0) prefetch_l1(ps + nthr_w);
                 if (!EULER) prefetch_l1(pw + nthr_w);
