@@ -184,6 +184,20 @@ int lcs_regrid_linear_nearest(const void* in, int in_dtype, int nlev, int nlat_s
                               const uint8_t* lon_valid, const int32_t* lon_nearest,
                               int nlat_dst, int nlon_dst, double* out, void* stream);
 
+/* lcs_spectral_truncate: the triangular spectral truncation of the global path, LCS.py:115-118:
+ * `VectorWind(u, v).truncate(field, truncation=T)` = windspharm -> pyspharm grdtospec / spectogrd -> SPHEREPACK shaes /
+ * shses on the "regular" grid (rows at colatitudes i*pi/(nlat-1), columns at 2*pi*j/nlon).  The operation is linear
+ * and separable; the host builds its tables (lagrangiancoherence_b200/spectral.py): At [T+1][nlat][nlat] = the
+ * colatitude operator of every zonal wavenumber, TRANSPOSED (At[m][k][i] = A_m[i][k]); Fc [nlon][2T+1] and
+ * Fi [2T+1][nlon] = the forward / inverse longitude transform (columns: mean, cos 1, sin 1, ..., cos T, sin T).
+ * in: device [nfields][nlat][nlon] of in_dtype; out: device f64, same shape, not aliasing in; scratch: device,
+ * lcs_spectral_truncate_scratch_bytes().  Parity against the reference is UNPINNED for this step (SPHEREPACK is not
+ * available in this image); the kernel is tested against the CPU restatement oracle/spectral_oracle.py. */
+size_t lcs_spectral_truncate_scratch_bytes(int nfields, int nlat, int ntrunc);
+int lcs_spectral_truncate(const void* in, int in_dtype, int nfields, int nlat, int nlon, int ntrunc,
+                          const double* At, const double* Fc, const double* Fi,
+                          void* scratch, size_t scratch_bytes, double* out, void* stream);
+
 /* ---------------------------------------------------------------- integrator
  * lcs_advect replaces parcel_propagation's loop, trajectory.py:80-126, together with the
  * xr_map_coordinates calls inside it (tools.py:11-41).

@@ -70,13 +70,10 @@ class LCS:
         assert set(u.dims) == {'latitude', 'longitude', timedim}, \
             'array dims should be latitude and longitude only'                               # LCS.py:96
         if isglobal:                                                 # LCS.py:105-120
-            if truncation is not None:
-                raise NotImplementedError(
-                    'isglobal=True with truncation needs a spherical-harmonic truncation of the winds (windspharm / '
-                    'SPHEREPACK upstream, LCS.py:115-118), which has no counterpart here; pass truncation=None '
-                    '(the 360x721 regrid of interp_to_common_grid=True is supported)')
             if interp_to_common_grid:                                # LCS.py:106-114
                 u, v = (_to_common_grid(a, timedim, device) for a in (u, v))
+            if truncation is not None:                               # LCS.py:115-118: VectorWind(u, v).truncate(., truncation)
+                u, v = (_truncate(a, timedim, truncation, device) for a in (u, v))
             cyclic_xboundary = True
             self.subdomain = None
         else:
@@ -150,6 +147,20 @@ def _to_common_grid(da, timedim, device):
     lats, lons = common_grid()
     out = regrid_device(d.values, coord_values(d, 'latitude'), coord_values(d, 'longitude'), lats, lons, device=device)
     coords = {timedim: coord_values(d, timedim), 'latitude': lats, 'longitude': lons}
+    return make_like(da, out.cpu().numpy(), (timedim, 'latitude', 'longitude'), coords)
+
+
+def _truncate(da, timedim, truncation, device):
+    """LCS.py:115-118 for one component: windspharm's triangular truncation (pyspharm / SPHEREPACK regular grid) as
+    one device operator (engine.spectral_truncate_device; spectral.py describes it and why its parity is unpinned).
+    windspharm refuses grids that are not global and equally spaced with a ValueError; so does this."""
+    from ..engine import spectral_truncate_device
+    from ..spectral import check_regular_global_grid
+    d = da.sortby('latitude').sortby('longitude').transpose(timedim, 'latitude', 'longitude')
+    lat, lon = coord_values(d, 'latitude'), coord_values(d, 'longitude')
+    check_regular_global_grid(lat, lon)
+    out = spectral_truncate_device(d.values, int(truncation), device=device)
+    coords = {timedim: coord_values(d, timedim), 'latitude': lat, 'longitude': lon}
     return make_like(da, out.cpu().numpy(), (timedim, 'latitude', 'longitude'), coords)
 
 

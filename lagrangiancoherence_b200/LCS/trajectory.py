@@ -19,6 +19,23 @@ def _sorted_winds(U, V, propdim):
     return U.transpose(propdim, 'latitude', 'longitude'), V.transpose(propdim, 'latitude', 'longitude')
 
 
+_ENGINES = {}          # a handful of engines keyed by grid + recipe: repeated calls on the same grid (a rolling series driven
+_ENGINES_MAX = 4       # through the reference-shaped API) reuse the device tables, workspaces and streams
+
+
+def _cached_engine(lat, lon, timestep, SETTLS_order, interp_order, xmode, device, precision):
+    key = (lat.tobytes(), lon.tobytes(), str(lat.dtype), str(lon.dtype), repr(timestep), type(timestep).__name__,
+           int(SETTLS_order), int(interp_order), xmode, str(device), precision)
+    eng = _ENGINES.pop(key, None)
+    if eng is None:
+        eng = FtleEngine(lat, lon, timestep, SETTLS_order=SETTLS_order, interp_order=interp_order,
+                         xmode=xmode, device=device, **precision_args(precision))
+        while len(_ENGINES) >= _ENGINES_MAX:
+            _ENGINES.pop(next(iter(_ENGINES)))
+    _ENGINES[key] = eng                                 # most recently used last
+    return eng
+
+
 def propagate(U, V, timestep, propdim, return_traj, SETTLS_order, interp_order, cyclic_xboundary,
               xclamp=XCLAMP_DEFAULT, device='cuda:0', precision='f64', engine=None, resample=None):
     """Shared by parcel_propagation and LCS.__call__: returns device tensors plus the metadata the
@@ -32,8 +49,7 @@ def propagate(U, V, timestep, propdim, return_traj, SETTLS_order, interp_order, 
         times.reverse()                                            # labels only (quirk Q2), :59-60
     xmode = 'cyclic' if cyclic_xboundary else xclamp
     if engine is None:
-        engine = FtleEngine(lat, lon, timestep, SETTLS_order=SETTLS_order, interp_order=interp_order,
-                            xmode=xmode, device=device, **precision_args(precision))
+        engine = _cached_engine(lat, lon, timestep, SETTLS_order, interp_order, xmode, device, precision)
     uu, vv = np.asarray(U.values), np.asarray(V.values)
     if resample is not None:                                       # LCS.py:88-90, evaluated on the device
         _, lo, w_hi, w_lo = resample

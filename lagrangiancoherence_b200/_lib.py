@@ -60,6 +60,9 @@ SIGNATURES = {
     'lcs_pack_pairs': (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     'lcs_time_lerp': (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_void_p, c_void_p]),
     'lcs_regrid_linear_nearest': (c_int, [c_void_p, c_int, c_int, c_int, c_int] + [c_void_p] * 10 + [c_int, c_int, c_void_p, c_void_p]),
+    'lcs_spectral_truncate_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'lcs_spectral_truncate': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                      c_void_p, c_void_p]),
     'lcs_gaussian_filter2d': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     'lcs_advect_workspace_bytes': (c_size_t, [C.POINTER(Particles), C.POINTER(AdvectOpts)]),
     'lcs_advect_check': (c_int, [c_void_p, c_void_p]),

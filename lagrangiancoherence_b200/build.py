@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'liblcs_b200.so')
 SOURCES = ['advect.cu', 'advect_inst_es3.cu', 'advect_inst_f64.cu', 'advect_inst_orders.cu', 'advect_inst_f32.cu', 'advect_inst_r32.cu',
-           'prefilter.cu', 'epilogue.cu', 'filters.cu', 'seams.cu']
+           'prefilter.cu', 'epilogue.cu', 'filters.cu', 'spectral.cu', 'seams.cu']
 HEADERS = ['lcs_device.cuh', 'lcs_internal.h', 'advect_kernels.cuh', os.path.join('..', '..', 'include', 'lcs_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']

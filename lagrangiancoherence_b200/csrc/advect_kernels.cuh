@@ -1,23 +1,24 @@
 // Departure-point integrator: parcel_propagation's loop (trajectory.py:80-126) with the
 // xr_map_coordinates calls inside it (tools.py:11-41) as CUDA kernels for sm_100a.
 //
-// Two launch shapes share the same stage functions:
-//  * advect_fused_kernel  -- one thread per particle carries it across every wind interval and
-//    SETTLS sub-iteration (cyclic / pointwise x-boundary, where particles are independent);
-//  * advect_phase_*       -- the as-executed outer-product x-clamp (quirk Q6) couples all
-//    particles of a window after every sub-step, so each sub-step is a pair of launches that
-//    meet through per-substep row/column exit flags.
+// Launch shapes, all built from the same stage functions (stage_euler / stage_settls):
+//  * advect_fused_kernel        -- one thread per particle carries it across every wind interval and SETTLS
+//    sub-iteration in registers (cyclic / pointwise x-boundary, where particles are independent);
+//  * advect_outer_group_kernel  -- the as-executed outer-product x-clamp (quirk Q6) couples all particles of a
+//    window after every sub-step: one cooperative grid of resident CTAs in groups, a group per window in flight,
+//    group barriers in global memory between the sub-steps, optional exchange of the column flags with other GPUs;
+//  * advect_phase_*             -- the same clamp with one launch pair per sub-step (kernel boundaries as barriers):
+//    the independent implementation the tests compare the persistent kernel with.
 //
 // Data, two layouts (include/lcs_b200.h):
-//  * PAIR4: pairs[k][lat][lon] = (u_k, v_k, u_{k+1}, v_{k+1}); one 32-B (f64) vector load per tap
-//    feeds the four operands of a SETTLS stage, which are combined in the reference's order
-//    (bit-faithful `strict` evaluation is only offered here);
-//  * ES   : E[k] = (u_k, v_k) and S[k] = (2u_k - u_{k+1}, 2v_k - v_{k+1}); a SETTLS stage needs one
-//    16-B load per tap -- the kernel is bound by L1 data-pipe wavefronts (ncu: 79 % of peak with
-//    PAIR4), so halving the bytes per tap is the lever that matters.
-// Positions stay in registers in the fused kernel.  Gathers go through the read-only L1 path (L1
-// hit rate 91 %, L2 throughput 5 % in ncu: staging tiles through shared memory/TMA would move the
-// same bytes through the same 128 B/clk port and was not pursued).
+//  * PAIR4: pairs[k][lat][lon] = (u_k, v_k, u_{k+1}, v_{k+1}); one 32-B (f64) vector load per tap feeds the four
+//    operands of a SETTLS stage, combined in the reference's order (bit-faithful `strict` evaluation);
+//  * ES   : E[k] = (u_k, v_k) and S[k] = (2u_k - u_{k+1}, 2v_k - v_{k+1}), every level with a mirror-filled halo; a
+//    SETTLS stage needs one 16-B load per tap and no gather ever reflects a tap index.
+// The kernels are bound by L1 data-pipe wavefronts (ncu, round 2: 82-85 % of peak, issue slots 48 %, DRAM 41 % for
+// the outer-clamp kernel): gathers go through the read-only L1 path, 16 B per tap.  A block-level shared-memory /
+// TMA tile of the taps was built in round 1 and lost to its barriers; what paid in round 2 was
+// removing instructions and wavefronts around the gathers (halo layout, fold fast path, row-sum taps).
 #pragma once
 #include <stdio.h>
 #include <mutex>

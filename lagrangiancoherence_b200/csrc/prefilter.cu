@@ -1,84 +1,34 @@
-// Wind staging: cubic B-spline prefilter (once per level) and packing into the gather layout.
+// Wind staging: B-spline prefilter (once per level) and packing into the gather layout.
 //
-// scipy.ndimage.map_coordinates(order=3, mode='wrap') re-runs spline_filter over the whole field
-// inside every call (tools.py:26-30: 18 calls per wind interval at SETTLS_order=4).  The
-// coefficients depend only on the level, so here they are computed once per level.
+// scipy.ndimage.map_coordinates(order >= 2, mode='wrap') re-runs spline_filter over the whole field inside every
+// call (tools.py:26-30: 18 calls per wind interval at SETTLS_order=4).  The coefficients depend only on the level,
+// so here they are computed once per level.
 //
-// scipy's filter is, per axis, gain (1-z)(1-1/z) times a causal and an anticausal one-pole
-// recursion (z = sqrt(3)-2) with the *exact* initialisation for the mirror extension.  That
-// recursion is sequential along a line; its closed form is a symmetric two-sided exponential
-//      c[i] = sum_k  sqrt(3) * z^|k| * s[mirror(i + k)]
-// over the mirror-extended signal (d c b | a b c d | c b a).  |z| = 0.268, so truncating at
-// |k| <= 32 leaves a relative remainder < 1e-18, far below one f64 ulp: every output is
-// independent and the filter becomes a 65-tap FIR.  Each thread slides a register window down
-// KR consecutive outputs (65+KR-1 loads for KR*65 FMAs); both passes filter along axis 0 of their
-// input with threads along axis 1 (coalesced) and write their result transposed, so two
-// applications filter axis 0 (lat) then axis 1 (lon) -- scipy's order -- and restore the layout.
-// Agreement with scipy.ndimage.spline_filter is ~1e-15 of the field magnitude
-// (tests/test_gpu_engine.py), not bitwise: the summation order differs from the recursion.
+// scipy's filter is, per axis and per pole z, the gain (1-z)(1-1/z) times a causal and an anticausal one-pole
+// recursion with the *exact* initialisation for the mirror extension (d c b | a b c d | c b a).  The recursion is
+// sequential along a line; its closed form is a symmetric two-sided exponential
+//      c[i] = sum_k  h0 * z^|k| * s[mirror(i + k)],
+// and |z| <= 0.43, so truncating at |k| <= log(1e-18)/log|z| leaves a remainder far below one f64 ulp: every run of
+// outputs can start from truncated end sums.  iir_axis0_transpose_kernel gives each thread a run of KQ consecutive
+// outputs: the two one-sided sums at the run's ends by Horner over the mirror extension, the same one-pole
+// recursions scipy uses inside the run.  Both passes filter along axis 0 of their input with threads along axis 1
+// (coalesced) and write their result transposed, so two applications filter axis 0 (lat) then axis 1 (lon) --
+// scipy's order -- and restore the layout.  Agreement with scipy.ndimage.spline_filter is ~1e-15 of the field
+// magnitude (tests/test_gpu_engine.py), not bitwise: the summation order differs from the whole-line recursion.
 #include <math.h>
 #include "lcs_internal.h"
 #include "lcs_device.cuh"
 
 namespace lcs {
 
-constexpr int KH = 32;    // half width of the truncated impulse response
-constexpr int KR = 8;     // consecutive outputs per thread
-
-struct FirTaps { double h[KH + 1]; };
-
-// in : [plane][n0][n1]  (plane p of the first pass: level p>>1, component p&1 -> u or v)
-// out: [plane][n1][n0]  filtered along n0, transposed
-template <typename Tin>
-__global__ void __launch_bounds__(128)
-fir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b, int interleaved_planes,
-                           double* __restrict__ out_a, double* __restrict__ out_b, int split_out,
-                           int n0, int n1, const FirTaps taps) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n1) return;
-    const int r0 = blockIdx.y * KR;
-    const int p = blockIdx.z;
-    const size_t plane = (size_t)n0 * n1;
-    // first pass reads planes alternately from u and v; second pass reads one contiguous scratch
-    const Tin* src = interleaved_planes ? ((p & 1) ? in_b : in_a) + (size_t)(p >> 1) * plane + c
-                                        : in_a + (size_t)p * plane + c;
-    double* dst = split_out ? ((p & 1) ? out_b : out_a) + (size_t)(p >> 1) * plane
-                            : out_a + (size_t)p * plane;
-    // mirror-reflected start index, then walk with direction flips at the two ends
-    const int period = 2 * n0 - 2;
-    int ii = (r0 - KH) % period;
-    if (ii < 0) ii += period;
-    int dir = 1;
-    if (ii >= n0) { ii = period - ii; dir = -1; }
-    if (ii == n0 - 1) dir = -1;
-    if (ii == 0) dir = 1;
-    double acc[KR];
-#pragma unroll
-    for (int j = 0; j < KR; ++j) acc[j] = 0.0;
-#pragma unroll
-    for (int m = 0; m < KR + 2 * KH; ++m) {
-        const double s = (double)__ldg(src + (size_t)ii * n1);
-#pragma unroll
-        for (int j = 0; j < KR; ++j) {
-            const int k = m - KH - j;                      // source index minus output index
-            if (k >= -KH && k <= KH) acc[j] = fma(taps.h[k < 0 ? -k : k], s, acc[j]);
-        }
-        ii += dir;
-        if (ii == n0 - 1) dir = -1;
-        else if (ii == 0) dir = 1;
-    }
-    double* o = dst + (size_t)c * n0 + r0;
-#pragma unroll
-    for (int j = 0; j < KR; ++j)
-        if (r0 + j < n0) o[j] = acc[j];
-}
-
-// Same filter, same interface, ~10x fewer FMAs: inside a thread's run of KQ consecutive outputs the two one-sided
-// sums obey the one-pole recursions that scipy runs along the whole line,
+// Inside a thread's run of KQ consecutive outputs the two one-sided sums obey the one-pole recursions that scipy runs
+// along the whole line,
 //      a[i] = s[i] + z a[i-1]   (causal),      m[i] = s[i] + z m[i+1]   (anticausal),      c[i] = sqrt(3) (a[i] + z m[i+1]),
-// and only their values at the ends of the run need the truncated (|k| <= KH, remainder < 1e-18) mirror sums.  Per run:
-// 2*(KH+1) Horner steps for the two ends + 2*KQ recursion steps, instead of KQ*65 FMAs -- the filter becomes a
-// streaming kernel (ncu: the FIR form ran the FP64 pipe at ~45 %).  Agreement with scipy stays ~1e-15 of the field.
+// and only their values at the ends of the run need the truncated (|k| <= kh, remainder < 1e-18) mirror sums.  Per run:
+// 2*(kh+1) Horner steps for the two ends + 2*KQ recursion steps (the first version of this file was a 65-tap FIR per
+// output: 3.5 ms against 1.4 ms per pass on the bench step).  ncu, round 2 (profiles/r02_prof_staging_B1184*): 1.45 ms
+// per pass over 2 x 1192 C2 levels = 2.35 TB/s of DRAM traffic (36 % of the copy bandwidth), L1 pipe 62 %, 27 % of the
+// warp slots at 96 registers -- bound by the latency of the two dependent recursions, not by HBM.
 #ifndef LCS_PREFILTER_RUN
 #define LCS_PREFILTER_RUN 32        // ncu launch lists, 1192 C2 levels x 2 components, lat + lon pass: runs of 32 at 96 registers
                                     // 1.31 + 1.37 / 1.45 + 1.50 ms on two boxes; runs of 24 capped at 64 registers 1.40 + 1.45 ms
@@ -195,14 +145,6 @@ pack_es_kernel(const Tin* __restrict__ u, const Tin* __restrict__ v,
 
 using namespace lcs;
 
-static FirTaps make_taps() {
-    FirTaps t;
-    const double z = sqrt(3.0) - 2.0;
-    const double h0 = (1.0 - z) * (1.0 - 1.0 / z) * (-z) / (1.0 - z * z);   // = sqrt(3)
-    for (int k = 0; k <= KH; ++k) t.h[k] = h0 * pow(z, k);
-    return t;
-}
-
 extern "C" size_t lcs_prefilter_scratch_bytes(int nlev, int nlat, int nlon) {
     if (nlev < 1 || nlat < 1 || nlon < 1) return 0;
     return (size_t)2 * nlev * nlat * nlon * sizeof(double);
@@ -235,10 +177,7 @@ extern "C" int lcs_prefilter(const void* u, const void* v, int in_dtype, double*
     if (npoles == 0) return lcs_fail(LCS_E_UNSUPPORTED, "lcs_prefilter: order must be 2..5 (order 1 needs no prefilter)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     double* tmp = static_cast<double*>(scratch);
-    const bool fir = order == 3 && lcs_env_int("LCS_PREFILTER_FIR", 0) != 0;    // the first (65-tap FIR) form, kept for A/B runs
-    const FirTaps taps = make_taps();
     const dim3 q1((nlon + 127) / 128, (nlat + KQ - 1) / KQ, 2 * nlev), q2((nlat + 127) / 128, (nlon + KQ - 1) / KQ, 2 * nlev);
-    const dim3 g1((nlon + 127) / 128, (nlat + KR - 1) / KR, 2 * nlev), g2((nlat + 127) / 128, (nlon + KR - 1) / KR, 2 * nlev);
     // One pole = one symmetric two-sided exponential h0 z^|k| with unit DC gain.  Per pole: a pass along latitude
     // ([plane][lat][lon] -> scratch [plane][lon][lat]) and a pass along longitude (scratch -> coef [lat][lon]); the
     // second pole of orders 4 and 5 re-reads the coefficient planes.  scipy runs all poles along an axis before the
@@ -251,12 +190,7 @@ extern "C" int lcs_prefilter(const void* u, const void* v, int in_dtype, double*
         const void* src_u = ip == 0 ? u : (const void*)coef_u;
         const void* src_v = ip == 0 ? v : (const void*)coef_v;
         const int src_dtype = ip == 0 ? in_dtype : LCS_F64;
-        if (fir) {
-            if (src_dtype == LCS_F64)
-                fir_axis0_transpose_kernel<double><<<g1, 128, 0, st>>>((const double*)src_u, (const double*)src_v, 1, tmp, nullptr, 0, nlat, nlon, taps);
-            else
-                fir_axis0_transpose_kernel<float><<<g1, 128, 0, st>>>((const float*)src_u, (const float*)src_v, 1, tmp, nullptr, 0, nlat, nlon, taps);
-        } else if (src_dtype == LCS_F64) {
+        if (src_dtype == LCS_F64) {
             iir_axis0_transpose_kernel<double><<<q1, 128, 0, st>>>((const double*)src_u, (const double*)src_v, 1, tmp, nullptr, 0,
                                                                    nlat, nlon, z, h0, kh);
         } else {
@@ -265,8 +199,7 @@ extern "C" int lcs_prefilter(const void* u, const void* v, int in_dtype, double*
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_prefilter(lat pass)");
-        if (fir) fir_axis0_transpose_kernel<double><<<g2, 128, 0, st>>>(tmp, nullptr, 0, coef_u, coef_v, 1, nlon, nlat, taps);
-        else iir_axis0_transpose_kernel<double><<<q2, 128, 0, st>>>(tmp, nullptr, 0, coef_u, coef_v, 1, nlon, nlat, z, h0, kh);
+        iir_axis0_transpose_kernel<double><<<q2, 128, 0, st>>>(tmp, nullptr, 0, coef_u, coef_v, 1, nlon, nlat, z, h0, kh);
         e = cudaGetLastError();
         if (e != cudaSuccess) return lcs_fail_cuda(e, "lcs_prefilter(lon pass)");
         lcs_count_launches(2);

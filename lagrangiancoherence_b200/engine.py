@@ -385,6 +385,35 @@ def regrid_device(series, lat, lon, new_lat, new_lon, device='cuda:0'):
     return out
 
 
+_SPECTRAL_TABLES = {}
+
+
+def spectral_truncate_device(series, ntrunc, device='cuda:0'):
+    """LCS.py:115-118 for one component: triangular truncation at ``ntrunc`` of every level of ``[nlev, nlat, nlon]``
+    (SPHEREPACK's regular-grid analysis + synthesis, see spectral.py).  Returns an f64 tensor on the device."""
+    from .spectral import truncation_tables
+    lib = _lib.load()
+    device = torch.device(device)
+    a = np.asarray(series)
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)
+    nlev, nlat, nlon = a.shape
+    key = (nlat, nlon, int(ntrunc), str(device))
+    with torch.cuda.device(device):
+        if key not in _SPECTRAL_TABLES:
+            A, Fc, Fi = truncation_tables(nlat, nlon, int(ntrunc))
+            dev = lambda m: torch.from_numpy(np.ascontiguousarray(m)).to(device)
+            _SPECTRAL_TABLES[key] = (dev(A.transpose(0, 2, 1)), dev(Fc), dev(Fi))
+        At, Fc, Fi = _SPECTRAL_TABLES[key]
+        t = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        out = torch.empty((nlev, nlat, nlon), dtype=torch.float64, device=device)
+        nbytes = int(lib.lcs_spectral_truncate_scratch_bytes(nlev, nlat, int(ntrunc)))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _lib.check(lib.lcs_spectral_truncate(_ptr(t), _dtype_code(t), nlev, nlat, nlon, int(ntrunc), _ptr(At), _ptr(Fc), _ptr(Fi),
+                                             _ptr(scratch), nbytes, _ptr(out), _stream(device)), 'lcs_spectral_truncate')
+    return out
+
+
 def prefilter_device(u, v, device='cuda:0', order=3):
     """B-spline coefficients (order 2..5) of ``[nlev, nlat, nlon]`` series (f64 tensors on the device)."""
     lib = _lib.load()
