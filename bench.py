@@ -330,7 +330,7 @@ def run_b200(args):
         a, b = ev(), ev()
         a.record()
         out0, out1, in0, in1 = rolling.shard_rows(lat.size, world, rank)
-        xb, yb = eng.advect(st, nsteps=nt - 1, nwindows=B, rows=(in0, in1))
+        xb, yb = eng.advect(st, nsteps=nt - 1, nwindows=B, rows=(in0, in1), xrank=rolling.band_xrank(eng, world, B))
         b.record()
         band = eng.epilogue(xb, yb, in_row0=in0, out_rows=(out0, out1))
         if timed:

@@ -2,9 +2,9 @@
 """The reference's idealised-vortex example (examples/ideal_vortex.py:211-288) on the B200 engine:
 departure points backward (S=4) and forward (S=2) on the cyclic 2-degree grid, then the attracting and
 repelling FTLE fields on the 360x721 common grid of the global path, `0.5*log(sigma)` applied by the caller exactly
-as upstream does.  No plotting: prints summary statistics of what the reference's figures show.  (Upstream's figures
-come from winds that were additionally truncated to T20 by windspharm, which smooths the vortex; that step has no
-counterpart here)
+as upstream does -- with upstream's defaults: the regrid to the common grid and the T20 spectral truncation of the winds
+(windspharm upstream; lcs_spectral_truncate here, see lagrangiancoherence_b200/spectral.py for what is and is not pinned
+about that step).  No plotting: prints summary statistics of what the reference's figures show.
 
     python examples/ideal_vortex.py            # needs a B200 and the built liblcs_b200.so
 """
@@ -31,12 +31,12 @@ def main():
                                                  copy=True, return_traj=True, cyclic_xboundary=True, verbose=False)
     x, y = trajectory.parcel_propagation(ds.u, ds.v, timestep=6 * 3600, propdim='time', SETTLS_order=2,
                                          copy=True, return_traj=True, cyclic_xboundary=True, verbose=False)
-    # upstream calls isglobal=True with its defaults: the 360x721 regrid (done here, on the device) followed by a T20
-    # spherical-harmonic truncation of the winds through windspharm (not available here: truncation=None)
+    # upstream calls isglobal=True with its defaults (examples/ideal_vortex.py:280-287): the 360x721 regrid followed by
+    # a T20 spherical-harmonic truncation of the winds, both on the device here
     rcs = LCS.LCS(timestep=6 * 3600, timedim='time', SETTLS_order=4)
-    ftle_r = np.log(rcs(ds.copy(), isglobal=True, truncation=None, verbose=False)) / 2
+    ftle_r = np.log(rcs(ds.copy(), isglobal=True, verbose=False)) / 2
     acs = LCS.LCS(timestep=-6 * 3600, timedim='time', SETTLS_order=4)
-    ftle_a = np.log(acs(ds.copy(), isglobal=True, truncation=None, verbose=False)) / 2
+    ftle_a = np.log(acs(ds.copy(), isglobal=True, verbose=False)) / 2
     dt = time.perf_counter() - t0
     lat, lon = ftle_a.coords['latitude'], ftle_a.coords['longitude']           # the common grid now
 

@@ -51,10 +51,9 @@ def propagate(U, V, timestep, propdim, return_traj, SETTLS_order, interp_order, 
     if engine is None:
         engine = _cached_engine(lat, lon, timestep, SETTLS_order, interp_order, xmode, device, precision)
     uu, vv = np.asarray(U.values), np.asarray(V.values)
-    if resample is not None:                                       # LCS.py:88-90, evaluated on the device
-        _, lo, w_hi, w_lo = resample
-        uu, vv = engine.time_lerp(uu, lo, w_hi, w_lo), engine.time_lerp(vv, lo, w_hi, w_lo)
-    staged = engine.stage(uu, vv)
+    # resample= (LCS.py:88-90) is applied on the device inside the staging: coarse levels are prefiltered once, winds and
+    # coefficients are refined linearly (engine.stage)
+    staged = engine.stage(uu, vv, resample=None if resample is None else tuple(resample[1:]))
     out = engine.advect(staged, return_traj=return_traj)
     return engine, out, U, lat, lon, times
 

@@ -147,8 +147,14 @@ class FtleEngine:
         self._ws = None
 
     # ------------------------------------------------------------------ staging
-    def stage(self, u, v, raw='planar'):
+    def stage(self, u, v, raw='planar', resample=None):
         """Upload (if needed), prefilter (orders >= 2) and pack a wind series ``[nlev, nlat, nlon]``.
+
+        ``resample=(lo, w_hi, w_lo)`` (timeaxis.resample_plan): the series is refined linearly in time on the way
+        (``resample=`` of LCS.__call__, LCS.py:88-91).  The spline prefilter is linear, so the COARSE levels are
+        prefiltered and the refinement is applied to winds and coefficients alike -- the refined series is never
+        prefiltered itself (half of the filter passes for a 2x refinement; differs from filtering the refined winds,
+        what upstream does inside every map_coordinates call, by rounding only).
 
         ``raw``: how the 2*order pole rows of the spline orders get the raw winds they sample -- ``'planar'`` (default)
         lets them read ``u, v`` themselves, ``'packed'`` stages a second E/S copy of the series for them (a third more
@@ -159,6 +165,24 @@ class FtleEngine:
         v = self._to_device(v)
         if u.shape != v.shape or u.dim() != 3 or tuple(u.shape[1:]) != (self.nlat, self.nlon):
             raise ValueError(f'winds must be [nlev, {self.nlat}, {self.nlon}], got {tuple(u.shape)} / {tuple(v.shape)}')
+        if resample is not None and u.shape[0] >= 2:
+            if self.order >= 2:
+                with torch.cuda.device(self.device):
+                    cu0 = torch.empty(tuple(u.shape), dtype=torch.float64, device=self.device)
+                    cv0 = torch.empty_like(cu0)
+                    scratch = torch.empty((2,) + tuple(cu0.shape), dtype=torch.float64, device=self.device)
+                    _lib.check(self.lib.lcs_prefilter(_ptr(u), _ptr(v), _dtype_code(u), _ptr(cu0), _ptr(cv0), _ptr(scratch),
+                                                      scratch.numel() * 8, u.shape[0], self.nlat, self.nlon, self.order,
+                                                      _stream(self.device)), 'lcs_prefilter')
+                coef = (self.time_lerp(cu0, *resample), self.time_lerp(cv0, *resample))
+            else:
+                coef = None
+            u, v = self.time_lerp(u, *resample), self.time_lerp(v, *resample)      # f64, like interp1d's output upstream
+            return self._stage_levels(u, v, raw, coef)
+        return self._stage_levels(u, v, raw, None)
+
+    def _stage_levels(self, u, v, raw, coef):
+        """Prefilter (unless ``coef`` = the coefficient planes is given) and pack the device series ``u, v``."""
         nlev = u.shape[0]
         if nlev < 2:
             return StagedWinds(self.layout, self.pair_dtype, nlev)
@@ -171,7 +195,9 @@ class FtleEngine:
         with torch.cuda.device(self.device):
             st = _stream(self.device)
             cu = cv = None
-            if self.order >= 2:
+            if self.order >= 2 and coef is not None:
+                cu, cv = coef
+            elif self.order >= 2:
                 cu = torch.empty((nlev,) + shape2, dtype=torch.float64, device=self.device)
                 cv = torch.empty_like(cu)
                 scratch = torch.empty((2,) + tuple(cu.shape), dtype=torch.float64, device=self.device)

@@ -195,6 +195,21 @@ def gather_bands(local_band, nrows, group=None):
 XRANK_MAX_GROUPS = 16        # windows in flight per rank in the cross-rank outer-clamp mode (same on every rank)
 
 
+def band_xrank(engine, world_size, nwindows, group=None):
+    """The cross-rank mailboxes a row-band integration under the outer-product clamp needs (``engine.advect(xrank=)``),
+    cached on the engine; ``None`` for one rank and for the cyclic / pointwise x-boundary (no exchange).  Collective on
+    first use: every rank of ``group`` must call it with the same arguments."""
+    from . import _lib
+    if engine.xmode != _lib.LCS_X_CLAMP_OUTER or world_size <= 1:
+        return None
+    ngroups = min(nwindows, XRANK_MAX_GROUPS)
+    cache = getattr(engine, '_xrank', None)
+    if cache is None or cache.ngroups != ngroups or cache.world != world_size:
+        from .peer import ColumnFlagMail
+        cache = engine._xrank = ColumnFlagMail(engine.part_lon.size, ngroups, group=group, device=engine.device)
+    return cache
+
+
 def band_ftle(engine, staged, world_size, rank, nsteps=None, nwindows=1, level0=0, log_scale=False, group=None):
     """Row-band shard of one (or several) fields: integrate own rows + 2-row halo, run the epilogue
     on own rows.  Returns ``(sigma_band [nwindows, rows, nlon], (out0, out1))``.
@@ -202,16 +217,8 @@ def band_ftle(engine, staged, world_size, rank, nsteps=None, nwindows=1, level0=
     Cyclic / pointwise x-boundary: particles are independent, no exchange.  As-executed outer-product clamp (quirk Q6):
     the row flags of a band are local, the column flags are OR-ed over all bands after every sub-step through NVLink
     mailboxes inside the persistent kernel (``peer.ColumnFlagMail``; needs a process group on CUDA devices)."""
-    from . import _lib
     out0, out1, in0, in1 = shard_rows(engine.nlat, world_size, rank)
-    xrank = None
-    if engine.xmode == _lib.LCS_X_CLAMP_OUTER and world_size > 1:
-        ngroups = min(nwindows, XRANK_MAX_GROUPS)
-        cache = getattr(engine, '_xrank', None)
-        if cache is None or cache.ngroups != ngroups or cache.world != world_size:
-            from .peer import ColumnFlagMail
-            cache = engine._xrank = ColumnFlagMail(engine.part_lon.size, ngroups, group=group, device=engine.device)
-        xrank = cache
+    xrank = band_xrank(engine, world_size, nwindows, group)
     x, y = engine.advect(staged, nsteps=nsteps, nwindows=nwindows, level0=level0, rows=(in0, in1), xrank=xrank)
     sigma = engine.epilogue(x, y, log_scale=log_scale, in_row0=in0, out_rows=(out0, out1))
     return sigma, (out0, out1)
