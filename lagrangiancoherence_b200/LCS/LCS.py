@@ -53,12 +53,8 @@ class LCS:
         if is_dataset(ds):                                           # LCS.py:81-83
             u, v = ds.u.copy(), ds.v.copy()
         elif isinstance(ds, str):                                    # LCS.py:84-87
-            try:
-                import xarray as xr
-            except ImportError:
-                raise NotImplementedError('opening a NetCDF path needs xarray (+ netCDF4), which is not installed; '
-                                          'pass u= and v= arrays') from None
-            ds = xr.open_dataset(ds)
+            from ..ncio import open_dataset                            # xarray when installed, else classic NetCDF-3 via scipy
+            ds = open_dataset(ds)
             u, v = ds.u.copy(), ds.v.copy()
         resample_plan_ = None
         if isinstance(resample, str):                                # LCS.py:88-91: linear refinement in time
@@ -194,3 +190,42 @@ def flowmap_gradient(x_departure, y_departure, sigma=None, *, device='cuda:0'):
     full = torch.cat([jac, torch.zeros((3,) + tuple(jac.shape[1:]), dtype=jac.dtype, device=dev)])   # LCS.py:206-208
     coords = {'derivatives': np.array(DERIVATIVE_NAMES), 'latitude': lat, 'longitude': lon}
     return make_like(x_departure, full.cpu().numpy(), ('derivatives', 'latitude', 'longitude'), coords)
+
+
+def main(argv):
+    """The reference's command line (LCS.py:236-265): ``timestep timedim SETTLS_order subdomain ds_path outpath return_traj``.
+
+    As upstream: the subdomain argument (``lon0/lon1/lat0/lat1``) is parsed and then NOT used (``subdomain=None``,
+    LCS.py:246-247); the call is the global one (regrid to 360 x 721, T20 truncation, cubic); with ``return_traj`` the
+    trajectories are saved next to the field under the names upstream derives (``SL_attracting`` -> ``x_departure`` /
+    ``y_departure``); and the INPUT FILE IS REMOVED afterwards (LCS.py:265) -- the caller upstream is a job script that
+    writes one partial input per task.  An eighth argument ``keep`` (extension) leaves the input in place."""
+    import os
+    print('*----- ARGS ------*')
+    print(argv)
+    coords = str(argv[4]).split('/')
+    subdomain = {'longitude': slice(float(coords[0]), float(coords[1])),            # parsed, unused: as upstream
+                 'latitude': slice(float(coords[2]), float(coords[3]))}
+    del subdomain
+    lcs = LCS(timestep=float(argv[1]), timedim=str(argv[2]), SETTLS_order=int(argv[3]), subdomain=None)
+    input_path, outpath = str(argv[5]), str(argv[6])
+    return_traj = argv[7] == 'True'
+    if return_traj:
+        out, x_departure, y_departure = lcs(ds=input_path, isglobal=True, interp_to_common_grid=True, truncation=20,
+                                            traj_interp_order=3, return_traj=return_traj)
+        print('Saving to ' + outpath)
+        out.to_netcdf(outpath)
+        x_departure.to_netcdf(outpath.replace('SL_attracting', 'x_departure'))
+        y_departure.to_netcdf(outpath.replace('SL_attracting', 'y_departure'))
+    else:
+        out = lcs(ds=input_path, isglobal=True, interp_to_common_grid=True, truncation=20,
+                  traj_interp_order=3, return_traj=return_traj)
+        print('Saving to ' + outpath)
+        out.to_netcdf(outpath)
+    if not (len(argv) > 8 and argv[8] == 'keep'):
+        os.remove(input_path)                                                        # LCS.py:265: subprocess.call(['rm', input_path])
+
+
+if __name__ == '__main__':
+    import sys
+    main(sys.argv)

@@ -74,7 +74,7 @@ constexpr int kES32 = 2;     // internal: ES layout of f32 elements with the cub
 template <typename T, int LAYOUT> struct EsPolicy { using type = Vec2<T>; };
 template <> struct EsPolicy<float, kES32> { using type = Vec2F32Arith; };
 
-// Thread -> particle: a block is a (band x 256/band) tile of the particle grid, a warp a
+// Thread -> particle: a block is a (band x blockDim/band) tile of the particle grid, a warp a
 // (band x 32/band) patch (smaller unique tap footprint than a 1x32 strip: better L1 hit rate);
 // grid = (column tiles, row bands, windows), so no integer division is needed.
 // STRIP: block = 8 rows x 32 columns, warp = one row of 32 particles with the block's warps stacked (they share tap
@@ -91,7 +91,7 @@ __device__ __forceinline__ bool particle_rc(const AdvectParams& P, int& row, int
     const int r = threadIdx.x & (P.band - 1);
     const int c = threadIdx.x >> P.band_log2;
     row = blockIdx.y * P.band + r;
-    col = blockIdx.x * (256 >> P.band_log2) + c;
+    col = blockIdx.x * (blockDim.x >> P.band_log2) + c;          // blocks of 256, 128 or 64 threads (launch_advect)
     return row < P.nrow && col < P.ncol;
 }
 
@@ -878,8 +878,21 @@ static cudaError_t launch_outer_group(const AdvectParams& P, int nwindows, void*
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool STRICT, int ORDER, int LAYOUT, bool R32 = false>
 static cudaError_t launch_advect(const AdvectParams& P, int nwindows, void* workspace, cudaStream_t st) {
-    const dim3 block(256);
-    const int tw = 256 >> P.band_log2;
+    // Block size: 256 threads, except for launches of fewer than two blocks per SM (the 89 x 180 grid of the example: 63
+    // blocks of 256 threads per window), which are cut into blocks of 128 so that every SM gets a share.  Measured (B200,
+    // r2b_stage.log): C1 x 4 windows 0.105 -> 0.088 ms; a C2 window (423 blocks) is better left at 256 (0.097 vs 0.102 ms).
+    // The warp -> particle patch is the same for every block size (LCS_ADVECT_BLOCK = 64 / 128 / 256 forces one).
+    int bt = 256;
+    {
+        const int forced = lcs_env_int("LCS_ADVECT_BLOCK", 0);
+        const long long rows_b = (P.nrow + P.band - 1) / P.band;
+        const int tw256 = 256 >> P.band_log2;
+        if (forced == 64 || forced == 128 || forced == 256) bt = forced;
+        else if ((long long)((P.ncol + tw256 - 1) / tw256) * rows_b * nwindows < 2LL * lcs_sm_count()) bt = 128;
+        if ((bt >> P.band_log2) < 1) bt = 256;
+    }
+    const dim3 block((unsigned)bt);
+    const int tw = bt >> P.band_log2;
     const dim3 grid((unsigned)((P.ncol + tw - 1) / tw), (unsigned)((P.nrow + P.band - 1) / P.band), (unsigned)nwindows);
     // wide grids: 8 x 32 blocks of one-row warps (see particle_rc); LCS_ADVECT_STRIP=0/1 forces the choice
     constexpr bool kHasStrip = sizeof(T) == 8 && !STRICT && ORDER == 3 && LAYOUT == kES && !R32;
@@ -892,7 +905,7 @@ static cudaError_t launch_advect(const AdvectParams& P, int nwindows, void* work
     if (P.xmode != LCS_X_CLAMP_OUTER) {
         if constexpr (kHasStrip) {
             if (strip) {
-                advect_fused_kernel<T, STRICT, ORDER, LAYOUT, true, R32><<<sgrid, block, 0, st>>>(P);
+                advect_fused_kernel<T, STRICT, ORDER, LAYOUT, true, R32><<<sgrid, dim3(256), 0, st>>>(P);
                 lcs_count_launches(1);
                 return cudaGetLastError();
             }
@@ -910,12 +923,13 @@ static cudaError_t launch_advect(const AdvectParams& P, int nwindows, void* work
         return (e == cudaSuccess && !launched) ? cudaErrorLaunchOutOfResources : e;
     }
     const dim3 ggrid(4, (unsigned)nwindows);
+    const dim3 gblock(256);
     for (int q = 0; q < P.nsub; ++q) {
         if constexpr (kHasStrip) {
-            if (strip) advect_phase_move<T, STRICT, ORDER, LAYOUT, true, R32><<<sgrid, block, 0, st>>>(P, q, q / (1 + P.S), q % (1 + P.S));
+            if (strip) advect_phase_move<T, STRICT, ORDER, LAYOUT, true, R32><<<sgrid, dim3(256), 0, st>>>(P, q, q / (1 + P.S), q % (1 + P.S));
         }
         if (!strip) advect_phase_move<T, STRICT, ORDER, LAYOUT, false, R32><<<grid, block, 0, st>>>(P, q, q / (1 + P.S), q % (1 + P.S));
-        advect_phase_gtpass<<<ggrid, block, 0, st>>>(P, q);
+        advect_phase_gtpass<<<ggrid, gblock, 0, st>>>(P, q);
     }
     advect_phase_final<<<grid, block, 0, st>>>(P);
     lcs_count_launches(2 * P.nsub + 1);

@@ -335,10 +335,20 @@ __device__ __forceinline__ void gather_spline_wrap(const typename E::type* __res
 }
 
 // Fast-path cubic gather (LCS_ARITH_F32): index map, fold and the fractional offsets stay in f64 (an f32 index
-// of magnitude ~10^3 would carry 1e-4 cells of error into the weights); the four weights per axis, the 16
-// products and the accumulation are f32, two values (u, v) per packed FFMA2.  Row sums first, then the
-// latitude weights: 20 FFMA2 per sample and no per-tap weight products.  Results differ from the f64
-// evaluation of the same f32 coefficients by a few f32 ulp of the wind magnitude (tolerance-tested).
+// of magnitude ~10^3 would carry 1e-4 cells of error into the weights); the 16 products and the accumulation are f32,
+// two values (u, v) per packed FFMA2, row sums first, then the latitude weights.
+// ANOMALY FORM (round 2): the taps are differenced against the stencil's central tap c11 before they are weighted,
+//   sample = c11 + sum_ij w_ij (c_ij - c11)        (the weights sum to one),
+// so every f32 rounding -- of a weight, a product, a partial sum -- is relative to the local VARIATION of the field
+// over four cells instead of its magnitude, and the large term c11 enters once, exactly, in f64.  Numpy emulation of
+// this arithmetic (scripts/proto_f32fast.py) on the tolerance test's case: FTLE within 1e-5 at 97.9 % of the points
+// against 90.7 % for plain f32 sums and 98.2 % for f64 arithmetic on the same f32 coefficients (the storage rounding
+// is what remains).  The weights are evaluated in f64 (Horner, as the f64 path) and rounded once: with the anomaly
+// form their error no longer multiplies the field's magnitude, and f64 weights are worth another 0.8 % of the points.
+// Cost over the plain form: 16 packed subtractions, 8 + 4 conversions per sample.
+#ifndef LCS_F32_WEIGHTS64
+#define LCS_F32_WEIGHTS64 1
+#endif
 __device__ __forceinline__ void cubic_weights_f32(float y, float2 (&w)[4]) {
     const float z = 1.0f - y;
     const float s = 1.0f / 6.0f;
@@ -348,6 +358,12 @@ __device__ __forceinline__ void cubic_weights_f32(float y, float2 (&w)[4]) {
     const float w3 = 1.0f - w0 - w1 - w2;
     w[0] = make_float2(w0, w0); w[1] = make_float2(w1, w1); w[2] = make_float2(w2, w2); w[3] = make_float2(w3, w3);
 }
+__device__ __forceinline__ void cubic_weights_f32_from_f64(double y, float2 (&w)[4]) {
+    double wd[4];
+    cubic_weights<false>(y, wd);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float t = __double2float_rn(wd[i]); w[i] = make_float2(t, t); }
+}
 
 __device__ __forceinline__ void gather_cubic_wrap_f32(const float2* __restrict__ f, int nlat, int nlon,
                                                       double iy, double ix, double (&out)[2]) {
@@ -355,25 +371,37 @@ __device__ __forceinline__ void gather_cubic_wrap_f32(const float2* __restrict__
     const double cx = fold_wrap(ix, nlon);
     const double fy = floor(cy), fx = floor(cx);
     float2 wy[4], wx[4];
+#if LCS_F32_WEIGHTS64
+    cubic_weights_f32_from_f64(cy - fy, wy);
+    cubic_weights_f32_from_f64(cx - fx, wx);
+#else
     cubic_weights_f32((float)(cy - fy), wy);
     cubic_weights_f32((float)(cx - fx), wx);
+#endif
     const int sy = (int)fy - 1, sx = (int)fx - 1;
-    float2 acc = make_float2(0.0f, 0.0f);
     const int pitch = nlon + LCS_HALO_LO + LCS_HALO_HI;                      // halo layout: no tap index is ever reflected
     const float2* base = f + (sy * pitch + sx);
     (void)nlat;
+    float2 c[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        float2 c[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) c[j] = __ldg(base + j);
-        float2 r = __fmul2_rn(c[0], wx[0]);
-#pragma unroll
-        for (int j = 1; j < 4; ++j) r = __ffma2_rn(c[j], wx[j], r);
-        acc = __ffma2_rn(r, wy[i], acc);
-        base += pitch;
+        for (int j = 0; j < 4; ++j) c[i][j] = __ldg(base + i * pitch + j);
     }
-    out[0] = (double)acc.x; out[1] = (double)acc.y;
+    const float2 ref = c[1][1];
+    const float2 nref = make_float2(-ref.x, -ref.y);
+    float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 r = __fmul2_rn(__fadd2_rn(c[i][0], nref), wx[0]);
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+            if (i == 1 && j == 1) continue;                                   // c11 - c11 = 0
+            r = __ffma2_rn(__fadd2_rn(c[i][j], nref), wx[j], r);
+        }
+        acc = i == 0 ? __fmul2_rn(r, wy[0]) : __ffma2_rn(r, wy[i], acc);
+    }
+    out[0] = (double)ref.x + (double)acc.x; out[1] = (double)ref.y + (double)acc.y;
 }
 
 // Shared 2x2 tap sum of the order-1 branches (weights (1-y, 1-(1-y)), mirror taps).

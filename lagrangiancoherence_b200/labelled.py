@@ -134,6 +134,10 @@ class DataArray:
     def where(self, cond, other=np.nan):
         return self.copy(data=np.where(np.asarray(cond), self.values, other))
 
+    def to_netcdf(self, path):                      # LCS.py:250-262 (the command line saves its results this way)
+        from .ncio import to_netcdf
+        return to_netcdf(self, path)
+
     # ---- elementwise arithmetic (enough for callers' ``np.log(out) / 2``)
     def _wrap(self, vals):
         return DataArray(vals, self.dims, self.coords, self.name) if np.shape(vals) == self.shape else vals

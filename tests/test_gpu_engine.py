@@ -193,11 +193,13 @@ def test_f32_storage_fast_path_tolerance(cuda_device):
 
 
 def test_f32_arithmetic_fast_path_tolerance(cuda_device):
-    """precision='f32fast' (LCS_ARITH_F32): f32 winds AND f32 cubic weights / packed-FMA tap sums; index map,
-    positions, SETTLS update and epilogue stay f64.  Not a parity path -- stated tolerance, measured on this case
-    (B200): departure points within 3e-7 relative; >= 85 % of the FTLE values within 1e-5 and >= 98 % within 1e-4
-    (f32 storage alone: 98 % / 99.9 %; f64: 100 %).  The cyclic/pointwise and the outer-clamp kernels use the same
-    gather, so both are held to it."""
+    """precision='f32fast' (LCS_ARITH_F32): f32 winds AND f32 packed-FMA tap sums in the ANOMALY form (taps differenced
+    against the stencil's central tap, which enters once in f64: lcs_device.cuh gather_cubic_wrap_f32); index map,
+    positions, SETTLS update and epilogue stay f64.  Not a parity path -- stated tolerance (north star: FTLE within 1e-5
+    relative away from ridge-singular points), measured on this case on B200: departure points within 1e-7 relative;
+    98.0 % of the FTLE values within 1e-5 and 99.9 % within 1e-4, i.e. what f32 STORAGE of the coefficients alone costs
+    (98.2 %; the plain f32 sums of round 1 reached 85-91 %).  The cyclic/pointwise and the outer-clamp kernels use the
+    same gather, so both are held to >= 97 % / 99.5 %."""
     from lagrangiancoherence_b200.engine import FtleEngine
     lat = np.linspace(-40.0, 0.0, 161)
     lon = np.linspace(-80.0, -30.0, 201)
@@ -210,10 +212,11 @@ def test_f32_arithmetic_fast_path_tolerance(cuda_device):
         eng = FtleEngine(lat, lon, -21600, SETTLS_order=4, xmode=xmode, pair_dtype='f32', arith='f32', device=cuda_device)
         x, y = eng.advect(eng.stage(u, v))
         sig = eng.epilogue(x, y)[0].cpu().numpy()
-        assert np.abs(x[0].cpu().numpy() - rx).max() <= 3e-7 * np.abs(lon).max()
-        assert np.abs(y[0].cpu().numpy() - ry).max() <= 3e-7 * np.abs(lat).max()
+        assert np.abs(x[0].cpu().numpy() - rx).max() <= 1e-7 * np.abs(lon).max()
+        assert np.abs(y[0].cpu().numpy() - ry).max() <= 1e-7 * np.abs(lat).max()
         frel = np.abs(0.5 * np.log(sig[good]) - fref) / np.maximum(np.abs(fref), 1e-3)
-        assert (frel <= 1e-5).mean() >= 0.85 and (frel <= 1e-4).mean() >= 0.98, (xmode, (frel <= 1e-5).mean(), (frel <= 1e-4).mean())
+        print(f'f32fast {xmode}: FTLE within 1e-5 at {(frel <= 1e-5).mean():.4f}, within 1e-4 at {(frel <= 1e-4).mean():.4f} of the points')
+        assert (frel <= 1e-5).mean() >= 0.97 and (frel <= 1e-4).mean() >= 0.995, (xmode, (frel <= 1e-5).mean(), (frel <= 1e-4).mean())
 
 
 def test_f32_arithmetic_argument_validation(cuda_device):
@@ -267,6 +270,29 @@ def test_planar_and_packed_raw_winds_agree(cuda_device, xmode, dtype):
         assert np.array_equal(res['packed'][0][interior], res['planar'][0][interior])
     with pytest.raises(ValueError):
         eng.stage(u, v, raw='texture')
+
+
+def test_block_size_of_the_fused_kernel_is_bit_identical(cuda_device, monkeypatch):
+    """Small launches run the fused / phased kernels in blocks of 128 or 64 threads so that every SM gets the same share
+    (launch_advect); the warp -> particle patch does not change, so not a bit may: forced sizes on ragged grids, both
+    independent x-boundaries and the phased outer clamp, with trajectories and a row band."""
+    from lagrangiancoherence_b200.engine import FtleEngine
+    for shape, xmode in (((41, 57), 'pointwise'), ((19, 150), 'cyclic'), ((33, 70), 'outer')):
+        lat = np.linspace(-30.0, 10.0, shape[0])
+        lon = np.linspace(-80.0, -24.0, shape[1]) if xmode != 'cyclic' else np.linspace(-180.0, 178.0, shape[1])
+        u, v = S.era5_like_winds(lat, lon, 6, seed=shape[1])
+        eng = FtleEngine(lat, lon, -21600, SETTLS_order=4, xmode=xmode, device=cuda_device)
+        st = eng.stage(u, v)
+        if xmode == 'outer':
+            monkeypatch.setenv('LCS_OUTER_MODE', '1')
+        res = {}
+        for bt in ('256', '128', '64', '0'):
+            monkeypatch.setenv('LCS_ADVECT_BLOCK', bt)
+            eng._ws = None
+            res[bt] = eng.advect(st, nsteps=4, nwindows=2, return_traj=True) + eng.advect(st, nsteps=4, rows=(5, 17))
+        for bt in ('128', '64', '0'):
+            assert all(torch.equal(a, b) for a, b in zip(res['256'], res[bt])), (shape, bt)
+        monkeypatch.delenv('LCS_OUTER_MODE', raising=False)
 
 
 def test_strip_warp_mapping_is_bit_identical(cuda_device, monkeypatch):
