@@ -431,6 +431,7 @@ struct GroupParams {
     // flags are the OR over all bands.  xr_world > 1: after the local barrier of a sub-step the group's first CTA posts
     // its band's column flags (and candidate count) into every rank's mailbox over NVLink, waits for everybody's, and
     // writes the OR back into the local flag page (include/lcs_b200.h: lcs_xrank).
+    long long* timing;                    // LCS_OUTER_TIMING variant builds: [ncta][3] cycles in phase A / barrier / phase B
     int xr_world, xr_rank;
     unsigned char* const* xr_mail;        // [world] mailbox base of every rank as mapped into this process
     size_t xr_group_stride, xr_msg_stride, xr_hdr_bytes;
@@ -456,13 +457,27 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
 }
 
 // Barrier over the CTAs of one group (all resident: cooperative launch).  `target` = arrivals expected since launch.
-// One thread per CTA: acq_rel fence (this CTA's writes, ordered before it by bar.sync, become visible at gpu scope),
-// arrive on the group's counter, then poll a SEPARATE release word that the last arriver bumps to `target` -- the
-// pollers then read a line nobody is hammering with atomics -- and a second acq_rel fence before the CTA goes on.
-// Data written by other CTAs is read with ld.cg afterwards (L2), the read-only wind levels may stay in L1.
+// A group of ONE CTA (the batched case: a window per CTA) needs bar.sync only.  Otherwise one thread per CTA:
+//   fence.release.gpu  -- MEMBAR.ALL.GPU: this CTA's writes (ordered before it by bar.sync) are at L2 before ...
+//   red.add            -- ... its arrival is counted (no return value to wait for),
+//   poll the counter   -- ld.relaxed.gpu (L2) until every CTA of the group has arrived.
+// No acquire fence follows: on sm_100 `fence.acquire.gpu` IS `CCTL.IVALL` -- it throws away the SM's whole L1, i.e. the
+// wind taps the next sub-step is about to gather again -- and nothing here needs it: every datum another CTA wrote is read
+// with ld.cg (served by L2, the point of coherence), the wind levels and the coordinate tables are read-only for the
+// whole launch.  Round 2a's barrier (fence.acq_rel before AND after, a separate release word bumped by the last arriver
+// behind a third fence) cost 7 400 cycles of a 16 400-cycle sub-step with the whole machine on one C2 window (clock64
+// instrumentation, -DLCS_OUTER_TIMING): three MEMBAR + ERRBAR drains and two L2 round trips on the critical path; this one
+// has one drain and one round trip.  -DLCS_GROUP_BARRIER_V1 restores the old sequence for A/B runs.
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
-__device__ __forceinline__ void group_barrier(GroupCtl* ctl, unsigned target, unsigned* err) {
+__device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void group_barrier(GroupCtl* ctl, unsigned target, unsigned* err, int gsize) {
     __syncthreads();
+    if (gsize == 1) return;                       // uniform over the CTA
+#ifdef LCS_GROUP_BARRIER_V1
     if (threadIdx.x == 0) {
         fence_acq_rel_gpu();
         if (atomicAdd(&ctl->bar, 1u) + 1u == target) {
@@ -476,6 +491,16 @@ __device__ __forceinline__ void group_barrier(GroupCtl* ctl, unsigned target, un
         }
         fence_acq_rel_gpu();
     }
+#else
+    if (threadIdx.x == 0) {
+        asm volatile("fence.release.gpu;" ::: "memory");
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" :: "l"(&ctl->bar) : "memory");
+        unsigned spins = 0;
+        while ((int)(ld_relaxed_gpu_u32(&ctl->bar) - target) < 0) {
+            if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_volatile_u32(err))) { atomicExch(err, 1u); break; }
+        }
+    }
+#endif
     __syncthreads();
 }
 
@@ -647,6 +672,12 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
         __syncthreads();
     }
     int wstatic = g;                                      // cross-rank mode: window -> group assignment must agree on all ranks
+#ifdef LCS_OUTER_TIMING
+    long long tA = 0, tB = 0, tC = 0, t0_ = 0, t1_ = 0;    // variant builds only: where a sub-step's cycles go (scripts/probe_r2b.py timing)
+#define LCS_TICK(acc) do { t1_ = clock64(); acc += t1_ - t0_; t0_ = t1_; } while (0)
+#else
+#define LCS_TICK(acc) do { } while (0)
+#endif
     for (;;) {
         unsigned char* const wb = G.wbase + ((size_t)g * 2 + parity) * G.wstride;
         {   // this window's candidate counters and exit flags start cleared (the other parity may still be read)
@@ -656,16 +687,21 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
         }
         if (tid_w == 0) { ctl->window = xr ? wstatic : (int)atomicAdd(&G.hdr->next_window, 1u); }
         wstatic += G.ngroups;
-        group_barrier(ctl, arrivals += gsize, err);
+        group_barrier(ctl, arrivals += gsize, err, gsize);
         const int w = __ldcg(&ctl->window);
         if (w >= G.nwindows) break;
         int q = 0;
+#ifdef LCS_OUTER_TIMING
+        t0_ = clock64();
+#endif
         for (int t = 0; t < P.nsteps; ++t) {
             for (int k = 0; k <= P.S; ++k, ++q) {
                 // ---- phase A: pending clamps of q-1 (mirrored in smem), stage, y clamp, raise "< x_min" flags
                 if (k == 0) group_phase_a<T, STRICT, ORDER, LAYOUT, true, STATE, R32>(P, G, g, w, q, t, e_begin, e_end, s_f, s_pos, 2 * g + parity);
                 else group_phase_a<T, STRICT, ORDER, LAYOUT, false, STATE, R32>(P, G, g, w, q, t, e_begin, e_end, s_f, s_pos, 2 * g + parity);
-                group_barrier(ctl, arrivals += gsize, err);
+                LCS_TICK(tA);
+                group_barrier(ctl, arrivals += gsize, err, gsize);
+                LCS_TICK(tB);
                 unsigned char* const lt_page = wb + G.flags_off + (size_t)(2 * q) * G.nflag_pad;
                 int* const counts = reinterpret_cast<int*>(wb);
                 if (xr) {
@@ -674,7 +710,7 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
                         const unsigned total = xr_exchange(G, g, ++xr_seq, lt_page + P.nrow, P.ncol, (unsigned)__ldcg(counts + q), err, &s_xr_total);
                         if (threadIdx.x == 0) __stcg(counts + P.nsub + q, (int)total);
                     }
-                    group_barrier(ctl, arrivals += gsize, err);
+                    group_barrier(ctl, arrivals += gsize, err, gsize);
                 }
                 // ---- phase B: mirror the "< x_min" flags; candidates that survive that pass raise the "> x_max" flags
                 const unsigned* g_lt = reinterpret_cast<const unsigned*>(lt_page);
@@ -682,14 +718,17 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
                 const int ncand = __ldcg(counts + q);                                                              // in flight with the mirror loads
                 const int ncand_all = xr ? __ldcg(counts + P.nsub + q) : ncand;                                    // over all ranks
                 for (int i = threadIdx.x; i < (G.nflag_pad >> 2); i += kGroupThreads) s_f32[i] = __ldcg(g_lt + i);   // bytes 0 / 1
+                const int* cand = G.cand + (size_t)(2 * g + (q & 1)) * P.nslots;
+                // the first candidate of every thread is fetched before its count is known (one L2 round trip less on the
+                // sub-step's critical path; entries past the count are stale and ignored)
+                const int cand_first = (int)threadIdx.x < P.nslots ? __ldcg(cand + threadIdx.x) : 0;
                 __syncthreads();
                 if (ncand_all > 0) {                                 // uniform over the group (and over the ranks)
-                    const int* cand = G.cand + (size_t)(2 * g + (q & 1)) * P.nslots;
                     if (!xr && ncand <= G.redundant_max) {
                         // few candidates: every CTA scans them all and sets the "> x_max" bits itself -- no second barrier
                         for (int i = threadIdx.x; i < ncand; i += kGroupThreads) {
                             int row, col;
-                            slot_rc(P, __ldcg(cand + i), row, col);
+                            slot_rc(P, i == (int)threadIdx.x ? cand_first : __ldcg(cand + i), row, col);
                             // bit 0 is stable in this phase and bit 1 only ever goes 0 -> 1: plain byte read-modify-writes are safe
                             if (!(s_f[row] & s_f[P.nrow + col] & 1)) { s_f[row] |= 2; s_f[P.nrow + col] |= 2; }
                         }
@@ -701,16 +740,17 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
                             slot_rc(P, __ldcg(cand + i), row, col);
                             if (!(s_f[row] & s_f[P.nrow + col] & 1)) { g_gt[row] = 1; g_gt[P.nrow + col] = 1; }
                         }
-                        group_barrier(ctl, arrivals += gsize, err);
+                        group_barrier(ctl, arrivals += gsize, err, gsize);
                         if (xr) {
                             if (leader) xr_exchange(G, g, ++xr_seq, g_gt + P.nrow, P.ncol, 0u, err, &s_xr_total);
-                            group_barrier(ctl, arrivals += gsize, err);
+                            group_barrier(ctl, arrivals += gsize, err, gsize);
                         }
                         const unsigned* g_gt32 = reinterpret_cast<const unsigned*>(g_gt);
                         for (int i = threadIdx.x; i < (G.nflag_pad >> 2); i += kGroupThreads) s_f32[i] |= __ldcg(g_gt32 + i) << 1;
                         __syncthreads();
                     }
                 }
+                LCS_TICK(tC);
             }
         }
         // ---- final: pending clamps of the last sub-step, outputs
@@ -734,6 +774,9 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
         parity ^= 1;
     }
     if (xr && leader && threadIdx.x == 0) __stcg(reinterpret_cast<unsigned*>(G.xr_mail[G.xr_rank]) + g, xr_seq);
+#ifdef LCS_OUTER_TIMING
+    if (threadIdx.x == 0 && G.timing) { G.timing[3 * blockIdx.x] = tA; G.timing[3 * blockIdx.x + 1] = tB; G.timing[3 * blockIdx.x + 2] = tC; }
+#endif
 }
 
 // Occupancy of a kernel on the current device, cached per (device, kernel, block, shared memory); thread-safe.
@@ -870,8 +913,25 @@ static cudaError_t launch_outer_group(const AdvectParams& P, int nwindows, void*
                 nwindows, ncta, ngroups, state, smem);
     AdvectParams Pc = P;
     void* args[2] = {&Pc, &G};
+#ifdef LCS_OUTER_TIMING
+    static long long* d_timing = nullptr;
+    if (!d_timing) cudaMalloc(&d_timing, 4096 * 3 * sizeof(long long));
+    G.timing = d_timing;
+#endif
     e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)ncta), dim3(kGroupThreads), args, smem, st);
     if (e == cudaSuccess) { *launched = true; lcs_count_launches(1); }
+#ifdef LCS_OUTER_TIMING
+    if (e == cudaSuccess && lcs_env_int("LCS_OUTER_TIMING_PRINT", 0)) {
+        static long long h[4096 * 3];
+        cudaStreamSynchronize(st);
+        cudaMemcpy(h, d_timing, (size_t)ncta * 3 * sizeof(long long), cudaMemcpyDeviceToHost);
+        double a = 0, b = 0, c = 0, amax = 0, amin = 1e30;
+        for (int i = 0; i < ncta; ++i) { a += h[3 * i]; b += h[3 * i + 1]; c += h[3 * i + 2]; if (h[3 * i] > amax) amax = h[3 * i]; if (h[3 * i] < amin) amin = h[3 * i]; }
+        const double nq = (double)P.nsub * ((nwindows + ngroups - 1) / ngroups);
+        fprintf(stderr, "[lcs timing] %d windows, %d CTAs, %d groups: cycles per sub-step (mean over CTAs): phase A %.0f (min %.0f max %.0f), barrier %.0f, phase B %.0f\n",
+                nwindows, ncta, ngroups, a / ncta / nq, amin / nq, amax / nq, b / ncta / nq, c / ncta / nq);
+    }
+#endif
     return e;
 }
 

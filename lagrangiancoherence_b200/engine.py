@@ -145,9 +145,25 @@ class FtleEngine:
             self.d_kx, self.d_hx, self.d_dx = dev(kx), dev(hx), dev(dx)
             self.d_status = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._ws = None
+        self._tmp = {}
+
+    def _buf(self, name, shape, dtype):
+        """A temporary of the staging path that never leaves the engine (coefficient planes, filter scratch), or -- with
+        ``stage(reuse=True)`` -- the E / S levels: one cached allocation per name, grown when a larger one is asked for.
+        All engine work is stream-ordered on the caller's current stream, so a later call may overwrite it."""
+        n = 1
+        for d in shape:
+            n *= int(d)
+        t = self._tmp.get(name)
+        if t is None or t.dtype != dtype or t.numel() < n:
+            t = None
+            self._tmp.pop(name, None)
+            t = torch.empty(max(n, 1), dtype=dtype, device=self.device)
+            self._tmp[name] = t
+        return t[:n].view(tuple(shape))
 
     # ------------------------------------------------------------------ staging
-    def stage(self, u, v, raw='planar', resample=None):
+    def stage(self, u, v, raw='planar', resample=None, reuse=False):
         """Upload (if needed), prefilter (orders >= 2) and pack a wind series ``[nlev, nlat, nlon]``.
 
         ``resample=(lo, w_hi, w_lo)`` (timeaxis.resample_plan): the series is refined linearly in time on the way
@@ -160,7 +176,12 @@ class FtleEngine:
         lets them read ``u, v`` themselves, ``'packed'`` stages a second E/S copy of the series for them (a third more
         staging traffic and memory; same integrator time: measured 14.26 vs 14.29 ms per 296 C2 windows).  With
         ``'planar'`` the returned object keeps ``u, v`` (their device copies) alive and the integrator reads them: do
-        not overwrite them in place between ``stage`` and ``advect``."""
+        not overwrite them in place between ``stage`` and ``advect``.
+
+        ``reuse=True``: the E / S levels live in buffers owned by the engine and are overwritten by the next
+        ``stage(reuse=True)`` call (stream-ordered).  For loops that stage, integrate, stage again -- the rolling series,
+        the bench -- this removes ~11 GB of allocator traffic per 1192-level step; callers that keep two staged series
+        alive at once leave it off."""
         u = self._to_device(u)
         v = self._to_device(v)
         if u.shape != v.shape or u.dim() != 3 or tuple(u.shape[1:]) != (self.nlat, self.nlon):
@@ -178,10 +199,10 @@ class FtleEngine:
             else:
                 coef = None
             u, v = self.time_lerp(u, *resample), self.time_lerp(v, *resample)      # f64, like interp1d's output upstream
-            return self._stage_levels(u, v, raw, coef)
-        return self._stage_levels(u, v, raw, None)
+            return self._stage_levels(u, v, raw, coef, reuse)
+        return self._stage_levels(u, v, raw, None, reuse)
 
-    def _stage_levels(self, u, v, raw, coef):
+    def _stage_levels(self, u, v, raw, coef, reuse=False):
         """Prefilter (unless ``coef`` = the coefficient planes is given) and pack the device series ``u, v``."""
         nlev = u.shape[0]
         if nlev < 2:
@@ -198,9 +219,9 @@ class FtleEngine:
             if self.order >= 2 and coef is not None:
                 cu, cv = coef
             elif self.order >= 2:
-                cu = torch.empty((nlev,) + shape2, dtype=torch.float64, device=self.device)
-                cv = torch.empty_like(cu)
-                scratch = torch.empty((2,) + tuple(cu.shape), dtype=torch.float64, device=self.device)
+                cu = self._buf('coef_u', (nlev,) + shape2, torch.float64)
+                cv = self._buf('coef_v', (nlev,) + shape2, torch.float64)
+                scratch = self._buf('filter_scratch', (2, nlev) + shape2, torch.float64)
                 _lib.check(self.lib.lcs_prefilter(_ptr(u), _ptr(v), _dtype_code(u), _ptr(cu), _ptr(cv),
                                                   _ptr(scratch), scratch.numel() * 8,
                                                   nlev, self.nlat, self.nlon, self.order, st), 'lcs_prefilter')
@@ -214,11 +235,15 @@ class FtleEngine:
                 coef = pack(cu, cv, _lib.LCS_F64) if cu is not None else None
                 return StagedWinds(self.layout, self.pair_dtype, nlev, raw_a=raw, coef_a=coef)
 
-            def pack_es(a, b, code):
+            def pack_es(a, b, code, tag):
                 # halo layout (include/lcs_b200.h): every level carries a mirror-filled rim so no gather reflects an index
                 padded = (self.nlat + _lib.LCS_HALO_LO + _lib.LCS_HALO_HI, self.nlon + _lib.LCS_HALO_LO + _lib.LCS_HALO_HI)
-                e = torch.empty((nlev,) + padded + (2,), dtype=tdt, device=self.device)
-                s_ = torch.empty((nlev - 1,) + padded + (2,), dtype=tdt, device=self.device)
+                if reuse:
+                    e = self._buf(tag + '_e', (nlev,) + padded + (2,), tdt)
+                    s_ = self._buf(tag + '_s', (nlev - 1,) + padded + (2,), tdt)
+                else:
+                    e = torch.empty((nlev,) + padded + (2,), dtype=tdt, device=self.device)
+                    s_ = torch.empty((nlev - 1,) + padded + (2,), dtype=tdt, device=self.device)
                 _lib.check(self.lib.lcs_pack_es(_ptr(a), _ptr(b), code, _ptr(e), _ptr(s_), self.pair_dtype,
                                                 nlev, self.nlat, self.nlon, st), 'lcs_pack_es')
                 return e, s_
@@ -226,11 +251,11 @@ class FtleEngine:
                 raise ValueError("raw must be 'packed' or 'planar'")
             ce_ = cs_ = None
             if cu is not None:
-                ce_, cs_ = pack_es(cu, cv, _lib.LCS_F64)
+                ce_, cs_ = pack_es(cu, cv, _lib.LCS_F64, 'coef')
                 if raw == 'planar':
                     return StagedWinds(self.layout, self.pair_dtype, nlev, raw_a=u, raw_b=v, coef_a=ce_, coef_b=cs_,
                                        raw_planar=True, round32=round32)
-            re_, rs_ = pack_es(u, v, _dtype_code(u))
+            re_, rs_ = pack_es(u, v, _dtype_code(u), 'raw')
             return StagedWinds(self.layout, self.pair_dtype, nlev, raw_a=re_, raw_b=rs_, coef_a=ce_, coef_b=cs_, round32=round32)
 
     def _to_device(self, a):

@@ -16,6 +16,8 @@ NCCL is used only to gather the finished fields (``gather_fields`` / ``gather_ba
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -43,21 +45,25 @@ def chunk_starts(first, count, chunk):
     return [(s, min(chunk, first + count - s)) for s in range(first, first + count, chunk)]
 
 
-def chunk_schedule(count, chunk):
+def chunk_schedule(count, chunk, ramp=False):
     """Launch sizes of the pipelined host path: ``chunk`` windows first and last -- the first upload and the last
     download cannot overlap anything, so they should be short -- and ``2*chunk`` in between, where the copies hide
-    behind the kernels and bigger launches are cheaper per window (with ``chunk`` = 148 = one two-CTA cluster per SM
-    pair, the middle launches are whole waves of single-CTA windows: 61 instead of 64 us per C2 window).
+    behind the kernels and bigger launches are cheaper per window (with ``chunk`` = 148 the middle launches are whole
+    waves of one-CTA windows).  ``ramp``: long series start and end with ``chunk/2, chunk`` (half the exposed copy time
+    again; the half-size launches run at four CTAs per window, a few per cent slower on a sixteenth of the work).
     Returns ``[(first, n), ...]`` covering ``0 .. count``."""
     if count <= 3 * chunk:
         return chunk_starts(0, count, chunk)
-    sizes, rem = [chunk], count - chunk
-    while rem > 3 * chunk:
-        sizes.append(2 * chunk)
+    head = [chunk // 2, chunk] if ramp and chunk >= 2 and count > 6 * chunk else [chunk]
+    rem = count - 2 * sum(head)
+    mid = []
+    while rem > 2 * chunk:
+        mid.append(2 * chunk)
         rem -= 2 * chunk
-    sizes += [rem - chunk, chunk] if rem > chunk else [rem]
+    if rem > 0:
+        mid.append(rem)
     out, s = [], 0
-    for n in sizes:
+    for n in head + mid + head[::-1]:
         out.append((s, n))
         s += n
     return out
@@ -124,7 +130,7 @@ def rolling_ftle(u, v, lat, lon, window_levels, timestep, SETTLS_order=4, interp
     sigma = None if to_host else torch.empty((count, lat.size, lon.size), dtype=torch.float64, device=dev)
     if count == 0:                                       # an empty shard (more ranks than start times): nothing to integrate
         return sigma if return_device else (out.numpy() if own_out else out)
-    chunks = chunk_starts(0, count, chunk) if on_device else chunk_schedule(count, chunk)
+    chunks = chunk_starts(0, count, chunk) if on_device else chunk_schedule(count, chunk, ramp=os.environ.get('LCS_ROLLING_RAMP', '1') != '0')
     engine.reset_status()                                # chunks OR into one flag, checked once after the loop
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream(dev)
@@ -142,7 +148,7 @@ def rolling_ftle(u, v, lat, lon, window_levels, timestep, SETTLS_order=4, interp
                     du.copy_(u[lo:hi], non_blocking=True)
                     dv.copy_(v[lo:hi], non_blocking=True)
                 main.wait_event(up.record_event())
-            staged = engine.stage(du, dv)
+            staged = engine.stage(du, dv, reuse=True)            # one chunk's levels alive at a time (stream-ordered)
             x, y = engine.advect(staged, nsteps=nsteps, nwindows=n, level0=0, level_stride=1)
             if not on_device:
                 pipe['in_free'][i % 2] = main.record_event()     # the integrator's pole rows read the raw levels too

@@ -120,6 +120,25 @@ def blocks():
             print(json.dumps(dict(case='block size ' + name, windows=B, advect_ms=res)), flush=True)
 
 
+def timing():
+    # with LCS_B200_LIB = a -DLCS_OUTER_TIMING build and LCS_OUTER_TIMING_PRINT=1: cycles per sub-step by phase
+    lat, lon = S.grid_c2()
+    for B in (1, 4, 296):
+        u, v = S.era5_like_winds(lat, lon, 8 + B, noise=0.0)
+        eng = FtleEngine(lat, lon, -21600, SETTLS_order=4, xmode='outer', device=dev)
+        st = eng.stage(torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev))
+        x = torch.empty((B, lat.size, lon.size), dtype=torch.float64, device=dev); y = torch.empty_like(x)
+        os.environ['LCS_OUTER_TIMING_PRINT'] = '0'
+        for _ in range(3):
+            eng.advect(st, nsteps=8, nwindows=B, out=(x, y))
+        torch.cuda.synchronize()
+        os.environ['LCS_OUTER_TIMING_PRINT'] = '1'
+        eng.advect(st, nsteps=8, nwindows=B, out=(x, y))
+        torch.cuda.synchronize()
+        os.environ['LCS_OUTER_TIMING_PRINT'] = '0'
+        print(json.dumps(dict(case='outer timing', windows=B, advect_ms=timeit(lambda: eng.advect(st, nsteps=8, nwindows=B, out=(x, y))))), flush=True)
+
+
 def profile():
     from lagrangiancoherence_b200.labelled import DataArray
     from lagrangiancoherence_b200.LCS.LCS import LCS

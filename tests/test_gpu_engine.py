@@ -22,14 +22,17 @@ def rel_err(a, b, scale):
     return np.abs(a - b) / scale
 
 
-@pytest.mark.parametrize('shape', [(41, 57), (5, 7), (281, 321), (64, 33)])
+@pytest.mark.parametrize('form', ['1', '2'])
+@pytest.mark.parametrize('shape', [(41, 57), (5, 7), (281, 321), (64, 33), (2, 130)])
 @pytest.mark.parametrize('dtype', [np.float64, np.float32])
-def test_prefilter_matches_scipy(cuda_device, shape, dtype):
-    """Run-recursive form of the truncated two-sided exponential filter == scipy's recursive spline_filter to
+def test_prefilter_matches_scipy(cuda_device, shape, dtype, form, monkeypatch):
+    """Both forms of the truncated two-sided exponential filter -- independent runs per thread (LCS_PREFILTER_FORM=1: what
+    small launches take) and the column-streaming kernel (=2: what series take) == scipy's recursive spline_filter to
     ~1e-15 of the field magnitude (f64 tolerance stated: 2e-14 * max|c|), including lines shorter than the
-    truncation half-width and than a thread's run of outputs."""
+    truncation half-width, than a thread's run of outputs and than a tile of the column walk."""
     from scipy import ndimage as ndi
     from lagrangiancoherence_b200 import engine as E
+    monkeypatch.setenv('LCS_PREFILTER_FORM', form)
     rng = np.random.default_rng(1)
     u = (rng.normal(size=(3,) + shape) * 10).astype(dtype)
     v = (rng.normal(size=(3,) + shape) * 10).astype(dtype)
@@ -41,14 +44,16 @@ def test_prefilter_matches_scipy(cuda_device, shape, dtype):
             assert np.abs(got - ref).max() <= 2e-14 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize('form', ['1', '2'])
 @pytest.mark.parametrize('order', [2, 4, 5])
 @pytest.mark.parametrize('shape', [(5, 7), (41, 57), (64, 33)])
-def test_prefilter_other_orders_match_scipy(cuda_device, shape, order):
+def test_prefilter_other_orders_match_scipy(cuda_device, shape, order, form, monkeypatch):
     """Orders 2 (one pole), 4 and 5 (two poles, applied as two lat/lon pass pairs).  Stated tolerance 5e-13 * max|c|:
     the second pole's gain (1-z)(1-1/z) ~ 75 (order 4) amplifies rounding; scipy's own recursion differs from the
     exact coefficients by as much (tests/test_oracle_scipy_spec.py)."""
     from scipy import ndimage as ndi
     from lagrangiancoherence_b200 import engine as E
+    monkeypatch.setenv('LCS_PREFILTER_FORM', form)       # orders 4, 5 (two poles, kh > 32) take the run form either way
     rng = np.random.default_rng(order)
     u = rng.normal(size=(2,) + shape) * 10
     v = rng.normal(size=(2,) + shape) * 10
@@ -270,6 +275,26 @@ def test_planar_and_packed_raw_winds_agree(cuda_device, xmode, dtype):
         assert np.array_equal(res['packed'][0][interior], res['planar'][0][interior])
     with pytest.raises(ValueError):
         eng.stage(u, v, raw='texture')
+
+
+def test_stage_reuse_keeps_results_and_leaves_private_stagings_alone(cuda_device):
+    """stage(reuse=True) packs the E / S levels into engine-owned buffers that the next reuse-staging overwrites (the
+    rolling series and the bench stage this way); a staging made without it must survive any number of them."""
+    from lagrangiancoherence_b200.engine import FtleEngine
+    u, v, lat, lon = small_case()
+    eng = FtleEngine(lat, lon, -21600, SETTLS_order=4, xmode='pointwise', device=cuda_device)
+    private = eng.stage(u, v)
+    ref = eng.advect(private)
+    a = eng.advect(eng.stage(u, v, reuse=True))
+    assert torch.equal(a[0], ref[0]) and torch.equal(a[1], ref[1])
+    other = eng.stage(u[::-1].copy(), v[::-1].copy(), reuse=True)        # overwrites the engine-owned levels, grows nothing
+    b = eng.advect(other)
+    assert not torch.equal(b[0], ref[0])
+    again = eng.advect(private)
+    assert torch.equal(again[0], ref[0]) and torch.equal(again[1], ref[1])
+    longer = eng.stage(np.concatenate([u, u]), np.concatenate([v, v]), reuse=True)     # a longer series grows the buffers
+    c = eng.advect(longer, nsteps=u.shape[0] - 1)
+    assert torch.equal(c[0], ref[0])
 
 
 def test_block_size_of_the_fused_kernel_is_bit_identical(cuda_device, monkeypatch):

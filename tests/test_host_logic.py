@@ -153,6 +153,10 @@ def test_chunk_schedule_covers_the_series_with_short_ends():
             assert all(a + n == b for (a, n), (b, _) in zip(sched, sched[1:]))
             assert all(0 < n <= 2 * chunk for _, n in sched)
             assert sched[0][1] <= chunk and sched[-1][1] <= chunk
+            ramp = chunk_schedule(count, chunk, ramp=True)
+            assert ramp[0][0] == 0 and sum(n for _, n in ramp) == count and all(0 < n <= 2 * chunk for _, n in ramp)
+            assert all(a + n == b for (a, n), (b, _) in zip(ramp, ramp[1:]))
+    assert chunk_schedule(1184, 148, ramp=True) == [(0, 74), (74, 148), (222, 296), (518, 296), (814, 148), (962, 148), (1110, 74)]
 
 
 def test_latlonsel_strict_open_intervals():
