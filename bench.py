@@ -288,6 +288,7 @@ def run_b200(args):
             gathered = torch.empty((world, B, lat.size, lon.size), dtype=torch.float64, device=dev)
     x = torch.empty((B, lat.size, lon.size), dtype=torch.float64, device=dev)
     y = torch.empty_like(x)
+    sigma_out = torch.empty_like(x)
 
     def step_starts(timed):
         st = eng.stage(d_u, d_v, reuse=True)
@@ -296,7 +297,7 @@ def run_b200(args):
             a.record()
             eng.advect(st, nsteps=nt - 1, nwindows=B, out=(x, y))
             b.record()
-            sigma = eng.epilogue(x, y)
+            sigma = eng.epilogue(x, y, out=sigma_out)
             if timed:
                 adv_ms.append([(a, b)])
             return sigma
@@ -311,7 +312,7 @@ def run_b200(args):
             eng.advect(st, nsteps=nt - 1, nwindows=n, level0=lo, out=(x[lo:lo + n], y[lo:lo + n]))
             b.record()
             evs.append((a, b))
-            sig.append(eng.epilogue(x[lo:lo + n], y[lo:lo + n]))
+            sig.append(eng.epilogue(x[lo:lo + n], y[lo:lo + n], out=sigma_out[lo:lo + n]))
             if peer is not None:
                 peer.push(lo, sig[-1])
             else:
@@ -344,15 +345,15 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    last = None
     for _ in range(args.warmup):
-        step(False)
-    barrier()
+        last = step(False)                          # held like the timed steps hold it: the caching allocator reaches its
+    barrier()                                       # steady state here, not with a cudaMalloc inside the second timed step
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = lib.lcs_kernel_launches()
     mallocs0 = torch.cuda.memory_stats(dev).get('num_device_alloc', 0)
     t_wall0 = time.time()
     step_ms = []
-    last = None
     for _ in range(args.steps):
         flush.fill_(1)                              # evict L2 between timed iterations
         barrier()

@@ -154,6 +154,10 @@ iir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__
 // shared tile (coalesced stores).
 constexpr int kColThreads = 64;
 constexpr int CQ = 16;
+#ifndef LCS_PREFILTER_AHEAD
+#define LCS_PREFILTER_AHEAD 1
+#endif
+constexpr int kColAhead = LCS_PREFILTER_AHEAD;     // tiles in flight beyond the three being read
 __device__ __forceinline__ int mirror_row(int r, int n) {       // d c b | a b c d | c b a, any r
     const int period = 2 * n - 2;
     r %= period;
@@ -188,7 +192,7 @@ iir_column_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b, in
             for (int j = 0; j < CQ; ++j) S[j] = (double)__ldg(src + (size_t)mirror_row(r + j, n0) * n1);
         }
     };
-    double S0[CQ], S1[CQ], S2[CQ], P[CQ], A[CQ];
+    double S0[CQ], S1[CQ], S2[CQ], P[kColAhead][CQ], A[CQ];
     // causal start: two tiles of the mirror extension above row 0, then tile 0
     double a = 0.0;
     load_tile(-2, S0); load_tile(-1, S1); load_tile(0, S2);
@@ -199,9 +203,11 @@ iir_column_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b, in
 #pragma unroll
     for (int j = 0; j < CQ; ++j) { a = fma(z, a, S2[j]); A[j] = a; S0[j] = S2[j]; }
     load_tile(1, S1); load_tile(2, S2);
+#pragma unroll
+    for (int k = 0; k + 1 < kColAhead; ++k) load_tile(3 + k, P[k]);
     const int half = (tid >> 4) & 1, l16 = tid & 15, warp = tid >> 5;
     for (int i = 0; i < ntile; ++i) {
-        load_tile(i + 3, P);                                // in flight during this tile's arithmetic
+        load_tile(i + 2 + kColAhead, P[kColAhead - 1]);     // in flight during the arithmetic of kColAhead tiles
         // anticausal restart below tile i: m = sum_{k < 2 CQ} z^k s[(i + 1) CQ + k]
         double m = 0.0;
 #pragma unroll
@@ -224,7 +230,11 @@ iir_column_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b, in
             if (r0 + l16 < n0) dst[(size_t)(c0 + cl) * n0 + r0 + l16] = ot[cl][l16];
         }
 #pragma unroll
-        for (int j = 0; j < CQ; ++j) { S0[j] = S1[j]; S1[j] = S2[j]; S2[j] = P[j]; }
+        for (int j = 0; j < CQ; ++j) {
+            S0[j] = S1[j]; S1[j] = S2[j]; S2[j] = P[0][j];
+#pragma unroll
+            for (int k = 0; k + 1 < kColAhead; ++k) P[k][j] = P[k + 1][j];
+        }
     }
 }
 

@@ -314,8 +314,9 @@ class FtleEngine:
         return (x, y, xt, yt) if return_traj else (x, y)
 
     # ------------------------------------------------------------------ epilogue
-    def epilogue(self, x_dep, y_dep, log_scale=False, mask=None, return_jac=False, in_row0=0, out_rows=None):
-        """lcs_ftle_epilogue on ``[nfields, nrow_in, nlon]`` departure points (wind-grid shaped)."""
+    def epilogue(self, x_dep, y_dep, log_scale=False, mask=None, return_jac=False, in_row0=0, out_rows=None, out=None):
+        """lcs_ftle_epilogue on ``[nfields, nrow_in, nlon]`` departure points (wind-grid shaped); ``out`` = a device
+        tensor ``[nfields, rows, nlon]`` f64 to fill instead of a fresh one."""
         if x_dep.dim() == 2:
             x_dep, y_dep = x_dep[None], y_dep[None]
         nfields, nrow_in, nlon = x_dep.shape
@@ -323,7 +324,12 @@ class FtleEngine:
             raise ValueError('the epilogue needs departure points on the wind grid columns')
         o0, o1 = (0, self.nlat) if out_rows is None else out_rows
         with torch.cuda.device(self.device):
-            sigma = torch.empty((nfields, o1 - o0, nlon), dtype=torch.float64, device=self.device)
+            if out is not None:
+                if tuple(out.shape) != (nfields, o1 - o0, nlon) or out.dtype != torch.float64 or not out.is_contiguous():
+                    raise ValueError('epilogue(out=): need a contiguous f64 tensor of shape %r' % ((nfields, o1 - o0, nlon),))
+                sigma = out
+            else:
+                sigma = torch.empty((nfields, o1 - o0, nlon), dtype=torch.float64, device=self.device)
             jac = torch.empty((nfields, 6, o1 - o0, nlon), dtype=torch.float64, device=self.device) if return_jac else None
             d_mask = None
             if mask is not None:
