@@ -490,6 +490,30 @@ def run_b200(args):
         return Bp * npts * iters * taps * vec * elt / (best * 1e-3) / 1e9
     gather_peak_es = measure_peak(2)         # 2-value elements: what the ES kernel issues
     gather_peak = measure_peak(4)            # 4-value elements: the reference formulation's taps
+    # ---- ONE field (north star: "a 48 h backward FTLE field on one B200 at >= 60 % of its gather roofline"): the
+    # integrator of a single window of this workload, 30 launches back to back between two events so that the host's
+    # launch path (25 us per call from Python) is not in the figure; both x-boundaries.  Outside the timed region.
+    single_field = None
+    if world == 1 and not rowbands:
+        single_field = {'what': 'lcs_advect of ONE window of the workload, mean of 30 back-to-back launches (CUDA events)',
+                        'bytes_per_particle_step': issued_bytes_pstep, 'peak': gather_peak_es, 'unit': 'GB/s'}
+        st1 = eng.stage(d_u[:nt], d_v[:nt])
+        for xm in ('pointwise', 'outer'):
+            e1 = eng if xm == args.xclamp else FtleEngine(lat, lon, dt, SETTLS_order=S_ORDER, interp_order=args.order, xmode=xm,
+                                                          device=dev, **precision_args(args.precision))
+            for _ in range(5):
+                e1.advect(st1, nsteps=nt - 1, nwindows=1, out=(x[:1], y[:1]))
+            torch.cuda.synchronize(dev)
+            a, b = ev(), ev()
+            a.record()
+            for _ in range(30):
+                e1.advect(st1, nsteps=nt - 1, nwindows=1, out=(x[:1], y[:1]))
+            b.record()
+            torch.cuda.synchronize(dev)
+            us = a.elapsed_time(b) / 30 * 1e3
+            gbs = npts * (nt - 1) * issued_bytes_pstep / (us * 1e-6) / 1e9
+            single_field[xm] = {'advect_us': us, 'achieved': gbs, 'frac': gbs / gather_peak_es}
+        del st1
     hbm_peak, hbm_src = measured_peaks()
     # compulsory HBM traffic of the integrator: every staged level read once, final positions written once
     hbm_bytes = (nlev * 2 - 1) * npts * 2 * elt + B * 2 * rows_rank * lon.size * 8
@@ -529,6 +553,7 @@ def run_b200(args):
         'clocks': clocks,
         'host_binding': numa,
         'gather_check': gather_check,
+        'single_field': single_field,
         'roofline': {
             'bound': 'l1-gather',
             'bound_note': note,

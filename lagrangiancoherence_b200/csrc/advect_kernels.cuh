@@ -405,8 +405,9 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) 
 // and every sub-step streams it through DRAM (ncu, round 1: 241 GB per 1184 windows, 42 % of the DRAM bandwidth,
 // L2 hit rate 37 %).  Here the launch is ONE cooperative grid of `ncta` resident CTAs split into `ngroups` groups; a
 // group integrates one window at a time and draws the next one from a global counter, so only `ngroups` windows
-// are in flight and their state (ngroups x 3 MB at C2) stays in L2 -- or, STATE = 1, the positions live in the
-// owning CTA's shared memory for the whole window (a thread owns the same slots in every sub-step).  The two
+// are in flight and their state (ngroups x 3 MB at C2) stays in L2 -- or, STATE = 1, when a group is large enough that
+// every thread owns at most ONE slot (few windows on the whole machine), position and Euler sample never leave the
+// thread's registers: no state loads, and no stores for the barrier's release fence to drain.  The two
 // window-wide dependencies of a sub-step are resolved with a group barrier in global memory (arrive counter +
 // spin by one thread per CTA, the cooperative launch guarantees co-residency) and -- when few particles left
 // through x_max, the common case -- the second barrier is replaced by every CTA scanning the whole candidate
@@ -468,12 +469,21 @@ __device__ __forceinline__ unsigned ld_volatile_u32(const unsigned* p) {
 // behind a third fence) cost 7 400 cycles of a 16 400-cycle sub-step with the whole machine on one C2 window (clock64
 // instrumentation, -DLCS_OUTER_TIMING): three MEMBAR + ERRBAR drains and two L2 round trips on the critical path; this one
 // has one drain and one round trip.  -DLCS_GROUP_BARRIER_V1 restores the old sequence for A/B runs.
+#ifndef LCS_GROUP_BARRIER_MODE
+#define LCS_GROUP_BARRIER_MODE 0
+#endif
+#ifndef LCS_GROUP_BARRIER_SLEEP
+#define LCS_GROUP_BARRIER_SLEEP 64
+#endif
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ unsigned ld_relaxed_gpu_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// Measured and dropped (one C2 window, 257-266 us either way): skipping the fence in CTAs that wrote nothing other CTAs read,
+// arrivals and polls on separate words, back-off between polls (LCS_GROUP_BARRIER_MODE 2 / 3) -- what is left of the barrier
+// is L2 latency on a large die (one-way arrival + 1-2 polling round trips) and the skew between CTAs.
 __device__ __forceinline__ void group_barrier(GroupCtl* ctl, unsigned target, unsigned* err, int gsize) {
     __syncthreads();
     if (gsize == 1) return;                       // uniform over the CTA
@@ -491,12 +501,30 @@ __device__ __forceinline__ void group_barrier(GroupCtl* ctl, unsigned target, un
         }
         fence_acq_rel_gpu();
     }
+#elif LCS_GROUP_BARRIER_MODE == 2
+    // arrivals and polls on different words: the last arriver (atom with return) bumps `released`
+    if (threadIdx.x == 0) {
+        asm volatile("fence.release.gpu;" ::: "memory");
+        unsigned old;
+        asm volatile("atom.relaxed.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(&ctl->bar) : "memory");
+        if (old + 1u == target) {
+            asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" :: "l"(&ctl->released), "r"(target) : "memory");
+        } else {
+            unsigned spins = 0;
+            while ((int)(ld_relaxed_gpu_u32(&ctl->released) - target) < 0) {
+                if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_volatile_u32(err))) { atomicExch(err, 1u); break; }
+            }
+        }
+    }
 #else
     if (threadIdx.x == 0) {
         asm volatile("fence.release.gpu;" ::: "memory");
         asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" :: "l"(&ctl->bar) : "memory");
         unsigned spins = 0;
         while ((int)(ld_relaxed_gpu_u32(&ctl->bar) - target) < 0) {
+#if LCS_GROUP_BARRIER_MODE == 3
+            __nanosleep(LCS_GROUP_BARRIER_SLEEP);
+#endif
             if ((++spins & 1023u) == 0 && (spins > kSpinLimit || ld_volatile_u32(err))) { atomicExch(err, 1u); break; }
         }
     }
@@ -526,26 +554,27 @@ __device__ __forceinline__ void gst_state(double2* p, double2 v) {
 template <typename T, bool STRICT, int ORDER, int LAYOUT, bool EULER, int STATE, bool R32>
 __device__ __forceinline__ void group_phase_a(const AdvectParams& P, const GroupParams& G, const int g, const int w,
                                               const int q, const int t, const int e_begin, const int e_end,
-                                              const unsigned char* s_f, double2* s_pos, const int wsel) {
+                                              const unsigned char* s_f, double2& rpos, double2& rwind, const int wsel) {
     const unsigned sbase = (unsigned)g * (unsigned)P.nslots;        // host guarantees ngroups*nslots < 2^32
     constexpr int nthr_w = kGroupThreads;                           // a CTA owns a contiguous block of slots (see the kernel)
     int it = 0;
     for (int e = e_begin; e < e_end; e += nthr_w, ++it) {
-        double2* const ps = (STATE == 1) ? s_pos + (it * kGroupThreads + threadIdx.x) : G.pos + (sbase + (unsigned)e);
+        double2* const ps = G.pos + (sbase + (unsigned)e);             // STATE = 1: unused (one slot per thread, in registers)
         double2* const pw = G.wind + (sbase + (unsigned)e);
-        if (G.prefetch == 3) {
+        if (STATE == 1) {
+        } else if (G.prefetch == 3) {
             // one bulk L2 prefetch per CTA and iteration (TMA unit: no LSU wavefronts, unlike 2 x 16 prefetch instructions)
             if (threadIdx.x == 0 && e + nthr_w < e_end) {
                 const unsigned bytes = (unsigned)min(nthr_w, e_end - (e + nthr_w)) * (unsigned)sizeof(double2);
-                if (STATE == 0 && q != 0) bulk_prefetch_l2(ps + nthr_w, bytes);
+                if (q != 0) bulk_prefetch_l2(ps + nthr_w, bytes);
                 if (!EULER) bulk_prefetch_l2(pw + nthr_w, bytes);
             }
         } else if (G.prefetch && e + nthr_w < e_end) {               // next slot's state: on its way by the time it is needed
             if (G.prefetch == 1) {
-                if (STATE == 0 && q != 0) prefetch_l1(ps + nthr_w);
+                if (q != 0) prefetch_l1(ps + nthr_w);
                 if (!EULER) prefetch_l1(pw + nthr_w);
             } else {
-                if (STATE == 0 && q != 0) prefetch_l2(ps + nthr_w);
+                if (q != 0) prefetch_l2(ps + nthr_w);
                 if (!EULER) prefetch_l2(pw + nthr_w);
             }
         }
@@ -556,7 +585,7 @@ __device__ __forceinline__ void group_phase_a(const AdvectParams& P, const Group
         double x, y;
         if (q == 0) { x = __ldg(P.lon + col); y = __ldg(P.lat + row); }
         else {
-            const double2 s = (STATE == 1) ? *ps : gld_state(ps);
+            const double2 s = (STATE == 1) ? rpos : gld_state(ps);
             x = s.x; y = s.y;
             const unsigned m = (unsigned)s_f[row] & (unsigned)s_f[P.nrow + col];   // bit 0: "< x_min" pass, bit 1: "> x_max" pass
             if (m & 1u) x = P.lon_min;                               // trajectory.py:96
@@ -570,13 +599,14 @@ __device__ __forceinline__ void group_phase_a(const AdvectParams& P, const Group
             }
             double ua, va;
             stage_euler<T, STRICT, ORDER, LAYOUT, R32>(P, pair, pole, __ldg(P.kx + row), x, y, ua, va);
-            gst_state(pw, make_double2(ua, va));
+            if (STATE == 1) rwind = make_double2(ua, va);
+            else gst_state(pw, make_double2(ua, va));
         } else {
-            const double2 wv = gld_state(pw);
+            const double2 wv = (STATE == 1) ? rwind : gld_state(pw);
             stage_settls<T, STRICT, ORDER, LAYOUT, R32>(P, pair, pole, __ldg(P.hx + row), wv.x, wv.y, x, y);
         }
         y = clamp_y(y, P.lat_min, P.lat_max);
-        if (STATE == 1) *ps = make_double2(x, y);
+        if (STATE == 1) rpos = make_double2(x, y);
         else gst_state(ps, make_double2(x, y));
         if (x < P.lon_min) {
             // rare: the window's flag page and the slot's row / column are re-derived rather than kept live
@@ -642,7 +672,7 @@ __global__ void __launch_bounds__(kGroupThreads, LCS_GROUP_MINBLOCKS)
 advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
     extern __shared__ __align__(16) unsigned char s_raw[];
     unsigned char* const s_f = s_raw;                    // [rows | cols] bit 0 = "< x_min" flag, bit 1 = "> x_max" flag
-    double2* const s_pos = reinterpret_cast<double2*>(s_raw + G.sflag_bytes);      // STATE = 1: [iterations][threads]
+    double2 rpos = make_double2(0.0, 0.0), rwind = make_double2(0.0, 0.0);          // STATE = 1: this thread's one slot
     // G.per_sm > 1: CTAs b, b + nsm, ... (the ones that share an SM on an idle device) are neighbours in `bid`, so they
     // land in the same group and an SM works on one window at a time; 1: consecutive CTAs, an SM hosts several groups
     const int nsm_ = G.ncta / G.per_sm;
@@ -697,8 +727,8 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
         for (int t = 0; t < P.nsteps; ++t) {
             for (int k = 0; k <= P.S; ++k, ++q) {
                 // ---- phase A: pending clamps of q-1 (mirrored in smem), stage, y clamp, raise "< x_min" flags
-                if (k == 0) group_phase_a<T, STRICT, ORDER, LAYOUT, true, STATE, R32>(P, G, g, w, q, t, e_begin, e_end, s_f, s_pos, 2 * g + parity);
-                else group_phase_a<T, STRICT, ORDER, LAYOUT, false, STATE, R32>(P, G, g, w, q, t, e_begin, e_end, s_f, s_pos, 2 * g + parity);
+                if (k == 0) group_phase_a<T, STRICT, ORDER, LAYOUT, true, STATE, R32>(P, G, g, w, q, t, e_begin, e_end, s_f, rpos, rwind, 2 * g + parity);
+                else group_phase_a<T, STRICT, ORDER, LAYOUT, false, STATE, R32>(P, G, g, w, q, t, e_begin, e_end, s_f, rpos, rwind, 2 * g + parity);
                 LCS_TICK(tA);
                 group_barrier(ctl, arrivals += gsize, err, gsize);
                 LCS_TICK(tB);
@@ -759,7 +789,7 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
         for (int e = e_begin; e < e_end; e += kGroupThreads, ++it) {
             int row, col;
             if (!slot_rc(P, e, row, col)) continue;
-            const double2 s = (STATE == 1) ? s_pos[it * kGroupThreads + threadIdx.x] : gld_state(G.pos + (sbase + (unsigned)e));
+            const double2 s = (STATE == 1) ? rpos : gld_state(G.pos + (sbase + (unsigned)e));
             double x = s.x;
             const unsigned m = (unsigned)s_f[row] & (unsigned)s_f[P.nrow + col];
             if (m & 1u) x = P.lon_min;
@@ -846,41 +876,27 @@ static cudaError_t launch_outer_group(const AdvectParams& P, int nwindows, void*
     *launched = false;
     const lcs_xrank* xr = (P.xr_host && P.xr_host->world > 1) ? P.xr_host : nullptr;
     const GroupLayout L = group_layout(P.nrow, P.ncol, P.nslots, P.nsub, nwindows, xr ? xr->ngroups : 0);
-    int state = lcs_env_int("LCS_OUTER_STATE", 0);               // 0: positions in global memory (L2), 1: in shared memory
+    // state placement: registers when every thread of the smallest group owns at most one slot (LCS_OUTER_STATE: -1 = that
+    // rule, 0 = always global memory, 1 = registers whenever possible -- the same thing, kept for the tests' sake)
+    const int state_req = lcs_env_int("LCS_OUTER_STATE", -1);
     const int nsm = lcs_sm_count();
     const int sflag = (int)lcs_align_up((size_t)L.nflag_pad, 16);
-    int ncta = 0, ngroups = 0, per_sm_used = 1;
-    size_t smem = 0;
+    int ncta = 0, ngroups = 0, per_sm_used = 1, state = 0;
+    const size_t smem = (size_t)sflag;
     const void* fn = nullptr;
     const int cap = lcs_env_int("LCS_OUTER_CTAS", 0);
-    for (;; state = 0) {
+    for (int pass = 0; pass < 2; ++pass) {
         fn = state == 1 ? (const void*)advect_outer_group_kernel<T, STRICT, ORDER, LAYOUT, 1, R32>
                         : (const void*)advect_outer_group_kernel<T, STRICT, ORDER, LAYOUT, 0, R32>;
-        if (state == 0) {
-            smem = (size_t)sflag;
-            per_sm_used = lcs_blocks_per_sm(fn, kGroupThreads, smem);
-            ncta = per_sm_used * nsm;
-            if (cap > 0 && cap < ncta) { ncta = cap; per_sm_used = 1; }
-        } else {
-            // a CTA keeps ceil(nslots / (gsize * threads)) positions per thread: that depends on the group size, which
-            // depends on how many CTAs fit with that much shared memory -- try the fullest shape first
-            ncta = 0;
-            for (int per_sm = LCS_GROUP_MINBLOCKS; per_sm >= 1 && !ncta; --per_sm) {
-                int c = per_sm * nsm;
-                if (cap > 0 && cap < c) c = cap;
-                const int n = L.ngroups_max < c ? L.ngroups_max : c;
-                const int gmin = c / n;                               // smallest group
-                const int chunk = ((P.nslots >> 5) + gmin - 1) / gmin * 32;
-                const int iters = (chunk + kGroupThreads - 1) / kGroupThreads;
-                smem = (size_t)sflag + (size_t)iters * kGroupThreads * sizeof(double2);
-                if (smem > 200 * 1024) continue;
-                if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) continue;
-                if (lcs_blocks_per_sm(fn, kGroupThreads, smem) >= per_sm) { ncta = c; per_sm_used = (cap > 0 && cap < per_sm * nsm) ? 1 : per_sm; }
-            }
-            (void)cudaGetLastError();
-            if (!ncta) continue;                                      // does not fit: positions in global memory
-        }
-        break;
+        per_sm_used = lcs_blocks_per_sm(fn, kGroupThreads, smem);
+        ncta = per_sm_used * nsm;
+        if (cap > 0 && cap < ncta) { ncta = cap; per_sm_used = 1; }
+        if (pass == 1 || state_req == 0 || ncta < 1) break;
+        const int n = L.ngroups_max < ncta ? L.ngroups_max : ncta;
+        const int gmin = ncta / n;                                    // smallest group
+        const int chunk = ((P.nslots >> 5) + gmin - 1) / gmin * 32;
+        if (chunk > kGroupThreads) break;                             // several slots per thread: state in global memory
+        state = 1;                                                    // occupancy of that instantiation: second pass
     }
     if (ncta < 1) return cudaSuccess;                                 // caller reports the failure
     ngroups = L.ngroups_max < ncta ? L.ngroups_max : ncta;

@@ -85,6 +85,35 @@ def single():
         print(json.dumps(out), flush=True)
 
 
+def kernels():
+    # true kernel times of ONE C2 field: 30 launches back to back between two events (the CPU runs ahead of the GPU),
+    # against the one-launch-per-event-pair figure that includes the host's launch path
+    lat, lon = S.grid_c2()
+    u, v = S.era5_like_winds(lat, lon, 9)
+    du, dv = torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev)
+    for xmode in ('pointwise', 'outer'):
+        eng = FtleEngine(lat, lon, -21600, SETTLS_order=4, xmode=xmode, device=dev)
+        st = eng.stage(du, dv)
+        x, y = eng.advect(st)
+        out = dict(case='one C2 field, back-to-back launches', xmode=xmode)
+        for name, fn in (('stage', lambda: eng.stage(du, dv, reuse=True)), ('advect', lambda: eng.advect(st, out=(x, y))),
+                         ('epilogue', lambda: eng.epilogue(x, y)), ('ftle', lambda: eng.ftle(du, dv))):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
+            a.record()
+            for _ in range(30):
+                fn()
+            b.record()
+            t1 = time.perf_counter()
+            torch.cuda.synchronize()
+            out[name + '_ms'] = a.elapsed_time(b) / 30
+            out[name + '_host_issue_ms'] = (t1 - t0) * 1e3 / 30
+        print(json.dumps(out), flush=True)
+
+
 def stage():
     for name, (lat, lon), nlev in (('C2', S.grid_c2(), 1192), ('C3', S.grid_c3(), 73), ('C2 single', S.grid_c2(), 9)):
         u, v = S.era5_like_winds(lat, lon, min(nlev, 40), noise=0.0)
@@ -113,10 +142,14 @@ def blocks():
             st = eng.stage(torch.from_numpy(u).to(dev), torch.from_numpy(v).to(dev))
             x = torch.empty((B, lat.size, lon.size), dtype=torch.float64, device=dev); y = torch.empty_like(x)
             res = {}
+            os.environ['LCS_ADVECT_SMALL'] = '0'
             for bt in ('256', '128', '64', '0'):
                 os.environ['LCS_ADVECT_BLOCK'] = bt
                 res[bt] = timeit(lambda: eng.advect(st, nsteps=nt - 1, nwindows=B, out=(x, y)), n=15)
             os.environ['LCS_ADVECT_BLOCK'] = '0'
+            for sm in ('1', '-1'):
+                os.environ['LCS_ADVECT_SMALL'] = sm
+                res['small=' + sm] = timeit(lambda: eng.advect(st, nsteps=nt - 1, nwindows=B, out=(x, y)), n=15)
             print(json.dumps(dict(case='block size ' + name, windows=B, advect_ms=res)), flush=True)
 
 
