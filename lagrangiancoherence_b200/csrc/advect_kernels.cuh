@@ -158,6 +158,7 @@ __device__ __forceinline__ void pole_sample_planar(const AdvectParams& P, int k,
     const double wy[2] = {wy0, __dsub_rn(1.0, wy0)}, wx[2] = {wx0, __dsub_rn(1.0, wx0)};   // scipy: last weight = 1 - sum(others)
     const int r0 = (int)fy, c0 = (int)fx;
     const int r1 = mirror_near(r0 + 1, P.nlat), c1 = mirror_near(c0 + 1, P.nlon);
+    LCS_ASSERT(r0 >= 0 && r0 < P.nlat && r1 >= 0 && r1 < P.nlat && c0 >= 0 && c0 < P.nlon && c1 >= 0 && c1 < P.nlon);
     const int off[4] = {r0 * P.nlon + c0, r0 * P.nlon + c1, r1 * P.nlon + c0, r1 * P.nlon + c1};
     const size_t o = (size_t)k * P.plane;
     if (P.raw_f32) pole_taps_planar<float, SETTLS, STRICT>(static_cast<const float*>(P.raw_a) + o, static_cast<const float*>(P.raw_b) + o, P.plane, off, wy, wx, out);
@@ -342,6 +343,7 @@ advect_phase_move(const AdvectParams P, int q /* global sub-step index */, int t
         f[row] = 1; f[P.nrow + col] = 1;
     } else if (x > P.lon_max) {
         const int slot = atomicAdd(P.cand_count + (size_t)w * P.nsub + q, 1);
+        LCS_ASSERT(slot >= 0 && slot < P.np);
         P.cand[(size_t)w * P.np + slot] = p;
     }
 }
@@ -579,6 +581,7 @@ __device__ __forceinline__ void group_phase_a(const AdvectParams& P, const Group
             }
         }
         int row, col;
+        LCS_ASSERT(e >= 0 && e < P.nslots && g >= 0 && g < G.ngroups);
         if (!slot_rc(P, e, row, col)) continue;
         const int grow = P.row0 + row;
         const bool pole = (grow < ORDER) || (grow >= P.nrow_global - ORDER);
@@ -616,6 +619,7 @@ __device__ __forceinline__ void group_phase_a(const AdvectParams& P, const Group
             g_lt[r2] = 1; g_lt[P.nrow + c2] = 1;
         } else if (x > P.lon_max) {
             const int slot = atomicAdd(reinterpret_cast<int*>(G.wbase + (size_t)wsel * G.wstride) + q, 1);
+            LCS_ASSERT(slot >= 0 && slot < P.nslots && q >= 0 && q < P.nsub);
             G.cand[((size_t)(2 * g + (q & 1))) * P.nslots + slot] = e;
         }
     }
@@ -758,7 +762,10 @@ advect_outer_group_kernel(const AdvectParams P, const GroupParams G) {
                         // few candidates: every CTA scans them all and sets the "> x_max" bits itself -- no second barrier
                         for (int i = threadIdx.x; i < ncand; i += kGroupThreads) {
                             int row, col;
-                            slot_rc(P, i == (int)threadIdx.x ? cand_first : __ldcg(cand + i), row, col);
+                            const int ce = i == (int)threadIdx.x ? cand_first : __ldcg(cand + i);
+                            LCS_ASSERT(ce >= 0 && ce < P.nslots);
+                            const bool cin = slot_rc(P, ce, row, col);
+                            LCS_ASSERT(cin); (void)cin;
                             // bit 0 is stable in this phase and bit 1 only ever goes 0 -> 1: plain byte read-modify-writes are safe
                             if (!(s_f[row] & s_f[P.nrow + col] & 1)) { s_f[row] |= 2; s_f[P.nrow + col] |= 2; }
                         }

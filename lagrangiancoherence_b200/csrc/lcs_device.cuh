@@ -14,6 +14,16 @@
 #include <stdint.h>
 #include "../../include/lcs_b200.h"
 
+// -DLCS_BOUNDS_CHECK builds (tests/test_gpu_bounds.py, scripts/sanitize_case.py): device-side asserts on every index the
+// gathers, the persistent kernel's state / candidate / flag tables and the prefilter form -- compute-sanitizer is closed on
+// the measurement pool, so memory safety is checked with bounds checks of our own on ragged cases.  No code otherwise.
+#ifdef LCS_BOUNDS_CHECK
+#include <assert.h>
+#define LCS_ASSERT(c) assert(c)
+#else
+#define LCS_ASSERT(c) ((void)0)
+#endif
+
 namespace lcs {
 
 // ------------------------------------------------------------------ gather element policies
@@ -188,6 +198,7 @@ __device__ __forceinline__ void gather_cubic_wrap(const typename E::type* __rest
 #pragma unroll
     for (int v = 0; v < NV; ++v) out[v] = 0.0;
     if (E::HALO || (sy >= 0 && sy + 3 < nlat && sx >= 0 && sx + 3 < nlon)) {
+        LCS_ASSERT(!E::HALO || (sy >= -LCS_HALO_LO && sy + 3 <= nlat - 1 + LCS_HALO_HI && sx >= -LCS_HALO_LO && sx + 3 <= nlon - 1 + LCS_HALO_HI));
         const typename E::type* base = f + (sy * pitch + sx);               // a level has < 2^31 elements
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -300,6 +311,7 @@ __device__ __forceinline__ void gather_spline_wrap(const typename E::type* __res
     for (int v = 0; v < NV; ++v) out[v] = 0.0;
     const int pitch = level_pitch<E>(nlon);
     if (E::HALO || (sy >= 0 && sy + ORDER < nlat && sx >= 0 && sx + ORDER < nlon)) {
+        LCS_ASSERT(!E::HALO || (sy >= -LCS_HALO_LO && sy + ORDER <= nlat - 1 + LCS_HALO_HI && sx >= -LCS_HALO_LO && sx + ORDER <= nlon - 1 + LCS_HALO_HI));
         const typename E::type* base = f + (sy * pitch + sx);
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
@@ -382,6 +394,7 @@ __device__ __forceinline__ void gather_cubic_wrap_f32(const float2* __restrict__
     const int pitch = nlon + LCS_HALO_LO + LCS_HALO_HI;                      // halo layout: no tap index is ever reflected
     const float2* base = f + (sy * pitch + sx);
     (void)nlat;
+    LCS_ASSERT(sy >= -LCS_HALO_LO && sy + 3 <= nlat - 1 + LCS_HALO_HI && sx >= -LCS_HALO_LO && sx + 3 <= nlon - 1 + LCS_HALO_HI);
     float2 c[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -417,6 +430,7 @@ __device__ __forceinline__ void bilinear_taps(const typename E::type* __restrict
     const double wy[2] = {wy0, __dsub_rn(1.0, wy0)};
     const double wx[2] = {wx0, __dsub_rn(1.0, wx0)};
     const int iy0 = (int)fy, ix0 = (int)fx;
+    LCS_ASSERT(iy0 >= (E::HALO ? -LCS_HALO_LO : 0) && iy0 + 1 <= nlat - 1 + (E::HALO ? LCS_HALO_HI : 1) && ix0 >= (E::HALO ? -LCS_HALO_LO : 0) && ix0 + 1 <= nlon - 1 + (E::HALO ? LCS_HALO_HI : 1));
     const int pitch = level_pitch<E>(nlon);
     const int col[2] = {E::HALO ? ix0 : mirror_near(ix0, nlon), E::HALO ? ix0 + 1 : mirror_near(ix0 + 1, nlon)};
 #pragma unroll

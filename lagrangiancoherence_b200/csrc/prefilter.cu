@@ -76,7 +76,7 @@ iir_axis0_transpose_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__
                                         : in_a + (size_t)p * plane + c;
     double* dst = split_out ? ((p & 1) ? out_b : out_a) + (size_t)(p >> 1) * plane
                             : out_a + (size_t)p * plane;
-    auto ld = [&](int i) { return (double)__ldg(src + (size_t)i * n1); };
+    auto ld = [&](int i) { LCS_ASSERT(i >= 0 && i < n0); return (double)__ldg(src + (size_t)i * n1); };
     double* const mine = tile[threadIdx.x];
     // Loads are taken kIirBatch at a time ahead of the recursion steps that consume them: a rolled loop has ONE load in
     // flight per thread (load, dependent FMA, next load), i.e. 2 x (kh + KQ) serialised L2 round trips per run.
@@ -189,7 +189,11 @@ iir_column_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b, in
             for (int j = 0; j < CQ; ++j) S[j] = (double)__ldg(g + (size_t)j * n1);
         } else {
 #pragma unroll
-            for (int j = 0; j < CQ; ++j) S[j] = (double)__ldg(src + (size_t)mirror_row(r + j, n0) * n1);
+            for (int j = 0; j < CQ; ++j) {
+                const int rr = mirror_row(r + j, n0);
+                LCS_ASSERT(rr >= 0 && rr < n0);
+                S[j] = (double)__ldg(src + (size_t)rr * n1);
+            }
         }
     };
     double S0[CQ], S1[CQ], S2[CQ], P[kColAhead][CQ], A[CQ];
@@ -227,6 +231,7 @@ iir_column_kernel(const Tin* __restrict__ in_a, const Tin* __restrict__ in_b, in
         // transposed copy-out: half a warp per destination row (CQ consecutive doubles)
         const int r0 = i * CQ;
         for (int cl = 2 * warp + half; cl < kColThreads && c0 + cl < n1; cl += kColThreads / 16) {
+            LCS_ASSERT(c0 + cl < n1 && cl < kColThreads);
             if (r0 + l16 < n0) dst[(size_t)(c0 + cl) * n0 + r0 + l16] = ot[cl][l16];
         }
 #pragma unroll
