@@ -534,13 +534,25 @@ __device__ __forceinline__ void group_barrier(GroupCtl* ctl, unsigned target, un
     __syncthreads();
 }
 
-// thread-private state in global memory (LCS_GROUP_STATE_POLICY: 0 = ld.cg / st.cg, kept in L2; 1 = ld.cs / st.cs, evict-first)
+// thread-private state in global memory.  LCS_GROUP_STATE_POLICY: 0 = ld.cg / st.cg (L2 only); 1 = ld.cs / st.cs
+// (evict-first); 2 = plain ld (L1-allocating) / st.cg; 3 = ld with L1 evict-first / st.cg.
+// The loads of policy 0 are LDG.STRONG.GPU: they bypass L1, so the `prefetch.global.L1` of the next slot issued one iteration
+// earlier never serves them and every iteration exposes an L2 round trip -- ncu's source view (round 2b) put 16 % of the
+// kernel's stall samples on the position load and its first use.  A slot's state is written and read by ONE thread, and a
+// thread always observes its own stores (the SM's L1 is kept coherent with the SM's own global stores), so an
+// L1-allocating load is safe here; the prefetch then lands the line in L1 before it is needed.
 #ifndef LCS_GROUP_STATE_POLICY
 #define LCS_GROUP_STATE_POLICY 0
 #endif
 __device__ __forceinline__ double2 gld_state(const double2* p) {
 #if LCS_GROUP_STATE_POLICY == 1
     return __ldcs(p);
+#elif LCS_GROUP_STATE_POLICY == 2
+    return *p;
+#elif LCS_GROUP_STATE_POLICY == 3
+    double2 v;
+    asm volatile("ld.global.L1::evict_first.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
 #else
     return __ldcg(p);
 #endif
