@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from ..engine import FtleEngine
-from ..labelled import coord_values, is_dataset, make_like
+from ..labelled import coord_values, is_dataset, is_xarray, make_like
 from .trajectory import propagate, XCLAMP_DEFAULT
 
 DERIVATIVE_NAMES = ['dxdx', 'dxdy', 'dydx', 'dydy', 'dzdx', 'dzdy', 'dxdr', 'dydr', 'dzdr']   # LCS.py:210-218
@@ -136,14 +136,18 @@ class LCS:
 
 def _to_common_grid(da, timedim, device):
     """LCS.py:101-114 for one component: sort, then ``interp(linear)`` to the 360 x 721 grid with the NaNs filled from
-    ``reindex(nearest)`` -- one device kernel (engine.regrid_device)."""
+    ``reindex(nearest)`` -- one device kernel (engine.regrid_device).  The result stays on the device (DeviceArray)."""
     from ..engine import regrid_device
+    from ..labelled import DeviceArray
     from ..regrid import common_grid
     d = da.sortby('latitude').sortby('longitude').transpose(timedim, 'latitude', 'longitude')
     lats, lons = common_grid()
-    out = regrid_device(d.values, coord_values(d, 'latitude'), coord_values(d, 'longitude'), lats, lons, device=device)
+    src = getattr(d, '_device_values', None)
+    out = regrid_device(d.values if src is None else src, coord_values(d, 'latitude'), coord_values(d, 'longitude'), lats, lons, device=device)
     coords = {timedim: coord_values(d, timedim), 'latitude': lats, 'longitude': lons}
-    return make_like(da, out.cpu().numpy(), (timedim, 'latitude', 'longitude'), coords)
+    if is_xarray(da):                    # pragma: no cover - needs xarray: xarray in, xarray out
+        return make_like(da, out.cpu().numpy(), (timedim, 'latitude', 'longitude'), coords)
+    return DeviceArray(out, (timedim, 'latitude', 'longitude'), coords)
 
 
 def _truncate(da, timedim, truncation, device):
@@ -151,13 +155,17 @@ def _truncate(da, timedim, truncation, device):
     one device operator (engine.spectral_truncate_device; spectral.py describes it and why its parity is unpinned).
     windspharm refuses grids that are not global and equally spaced with a ValueError; so does this."""
     from ..engine import spectral_truncate_device
+    from ..labelled import DeviceArray
     from ..spectral import check_regular_global_grid
     d = da.sortby('latitude').sortby('longitude').transpose(timedim, 'latitude', 'longitude')
     lat, lon = coord_values(d, 'latitude'), coord_values(d, 'longitude')
     check_regular_global_grid(lat, lon)
-    out = spectral_truncate_device(d.values, int(truncation), device=device)
+    src = getattr(d, '_device_values', None)
+    out = spectral_truncate_device(d.values if src is None else src, int(truncation), device=device)
     coords = {timedim: coord_values(d, timedim), 'latitude': lat, 'longitude': lon}
-    return make_like(da, out.cpu().numpy(), (timedim, 'latitude', 'longitude'), coords)
+    if is_xarray(da):                    # pragma: no cover
+        return make_like(da, out.cpu().numpy(), (timedim, 'latitude', 'longitude'), coords)
+    return DeviceArray(out, (timedim, 'latitude', 'longitude'), coords)
 
 
 def drop_unused_levels(sigma, lat, lon):

@@ -50,7 +50,11 @@ def propagate(U, V, timestep, propdim, return_traj, SETTLS_order, interp_order, 
     xmode = 'cyclic' if cyclic_xboundary else xclamp
     if engine is None:
         engine = _cached_engine(lat, lon, timestep, SETTLS_order, interp_order, xmode, device, precision)
-    uu, vv = np.asarray(U.values), np.asarray(V.values)
+    # winds the global path already regridded / truncated on the device stay there (labelled.DeviceArray)
+    uu = getattr(U, '_device_values', None)
+    vv = getattr(V, '_device_values', None)
+    if uu is None or vv is None:
+        uu, vv = np.asarray(U.values), np.asarray(V.values)
     # resample= (LCS.py:88-90) is applied on the device inside the staging: coarse levels are prefiltered once, winds and
     # coefficients are refined linearly (engine.stage)
     staged = engine.stage(uu, vv, resample=None if resample is None else tuple(resample[1:]))

@@ -443,20 +443,37 @@ def map_coordinates_device(field, pos_x, pos_y, lat, lon, order=1, device='cuda:
     return out
 
 
+def _series_on_device(series, device):
+    """``[nlev, n0, n1]`` series (numpy array or tensor on any device) -> contiguous f32 / f64 tensor on ``device``."""
+    if isinstance(series, torch.Tensor):
+        t = series if series.dtype in (torch.float32, torch.float64) else series.to(torch.float64)
+        return t.to(device).contiguous()
+    a = np.asarray(series)
+    if a.dtype not in (np.float32, np.float64):
+        a = a.astype(np.float64)
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+_REGRID_PLANS = {}
+
+
 def regrid_device(series, lat, lon, new_lat, new_lon, device='cuda:0'):
     """LCS.py:108-113 on the device: linear interpolation (latitude, then longitude) of ``[nlev, nlat, nlon]`` to the
     new coordinates, NaNs (outside the source range) filled with the nearest-label value.  Returns an f64 tensor."""
     from .regrid import axis_plan
     lib = _lib.load()
     device = torch.device(device)
-    a = np.asarray(series)
-    if a.dtype not in (np.float32, np.float64):
-        a = a.astype(np.float64)
     with torch.cuda.device(device):
-        t = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        t = _series_on_device(series, device)
         plans = []
         for src, dst in ((lat, new_lat), (lon, new_lon)):
-            plans += [torch.from_numpy(np.ascontiguousarray(p)).to(device) for p in axis_plan(src, dst)]
+            src, dst = np.ascontiguousarray(src, dtype=np.float64), np.ascontiguousarray(dst, dtype=np.float64)
+            key = (src.tobytes(), dst.tobytes(), str(device))
+            if key not in _REGRID_PLANS:                       # u and v of a call, and every call of a series, share them
+                while len(_REGRID_PLANS) >= 8:
+                    _REGRID_PLANS.pop(next(iter(_REGRID_PLANS)))
+                _REGRID_PLANS[key] = [torch.from_numpy(np.ascontiguousarray(p)).to(device) for p in axis_plan(src, dst)]
+            plans += _REGRID_PLANS[key]
         out = torch.empty((t.shape[0], len(new_lat), len(new_lon)), dtype=torch.float64, device=device)
         _lib.check(lib.lcs_regrid_linear_nearest(_ptr(t), _dtype_code(t), t.shape[0], t.shape[1], t.shape[2],
                                                  *[_ptr(p) for p in plans], len(new_lat), len(new_lon), _ptr(out),
@@ -473,10 +490,7 @@ def spectral_truncate_device(series, ntrunc, device='cuda:0'):
     from .spectral import truncation_tables
     lib = _lib.load()
     device = torch.device(device)
-    a = np.asarray(series)
-    if a.dtype not in (np.float32, np.float64):
-        a = a.astype(np.float64)
-    nlev, nlat, nlon = a.shape
+    nlev, nlat, nlon = tuple(series.shape)
     key = (nlat, nlon, int(ntrunc), str(device))
     with torch.cuda.device(device):
         if key not in _SPECTRAL_TABLES:
@@ -484,7 +498,7 @@ def spectral_truncate_device(series, ntrunc, device='cuda:0'):
             dev = lambda m: torch.from_numpy(np.ascontiguousarray(m)).to(device)
             _SPECTRAL_TABLES[key] = (dev(A.transpose(0, 2, 1)), dev(Fc), dev(Fi))
         At, Fc, Fi = _SPECTRAL_TABLES[key]
-        t = torch.from_numpy(np.ascontiguousarray(a)).to(device)
+        t = _series_on_device(series, device)
         out = torch.empty((nlev, nlat, nlon), dtype=torch.float64, device=device)
         nbytes = int(lib.lcs_spectral_truncate_scratch_bytes(nlev, nlat, int(ntrunc)))
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=device)

@@ -167,6 +167,68 @@ class DataArray:
     __ge__ = lambda s, o: s._bin(o, np.greater_equal)
 
 
+class DeviceArray(DataArray):
+    """A DataArray whose values live on the GPU until somebody asks for them.  The global path of ``LCS.__call__`` regrids
+    and truncates the winds on the device (LCS.py:105-118) and hands them straight to the integrator; the host copy that
+    ``.values`` promises is made on first access only (a 360 x 721 series is 19 MB per component: copying every
+    intermediate down and up again was 25 of the 34 ms of a default global call)."""
+
+    def __init__(self, tensor, dims, coords=None, name=None):
+        self._device_values = tensor
+        self._host_values = None
+        self.dims = tuple(dims)
+        if len(self.dims) != tensor.dim():
+            raise ValueError(f'{len(self.dims)} dims for a {tensor.dim()}-d array')
+        self.coords = {}
+        for k, v in (coords or {}).items():
+            v = v.values if isinstance(v, DataArray) else np.asarray(v)
+            if k in self.dims and v.shape != (tensor.shape[self.dims.index(k)],):
+                raise ValueError(f'coordinate {k!r} has shape {v.shape}')
+            self.coords[k] = v
+        self.name = name
+
+    @property
+    def values(self):
+        if self._host_values is None:
+            self._host_values = self._device_values.cpu().numpy()
+        return self._host_values
+
+    @property
+    def shape(self):
+        return tuple(self._device_values.shape)
+
+    @property
+    def dtype(self):
+        return np.dtype(str(self._device_values.dtype).replace('torch.', ''))
+
+    @property
+    def size(self):
+        return self._device_values.numel()
+
+    @property
+    def ndim(self):
+        return self._device_values.dim()
+
+    def transpose(self, *dims):
+        if tuple(dims) == self.dims:                    # already in that order: stay on the device
+            return self
+        return DataArray(self.values, self.dims, self.coords, self.name).transpose(*dims)
+
+    def isel(self, indexers=None, **kw):
+        indexers = dict(indexers or {}, **kw)
+        if len(indexers) == 1 and self._host_values is None:
+            (d, idx), = indexers.items()
+            if d == self.dims[0] and np.ndim(idx) == 0 and not isinstance(idx, slice):     # one level: download that level only
+                coords = dict(self.coords)
+                if d in coords:
+                    coords[d] = coords[d][idx]
+                return DataArray(self._device_values[int(idx)].cpu().numpy(), self.dims[1:], coords, self.name)
+        return DataArray(self.values, self.dims, self.coords, self.name).isel(indexers)
+
+    def copy(self, deep=True, data=None):
+        return DataArray(self.values, self.dims, self.coords, self.name).copy(deep, data)
+
+
 class Dataset:
     """Bag of named DataArrays: ``ds.u`` / ``ds.v`` as LCS.__call__ expects (LCS.py:81-83)."""
 

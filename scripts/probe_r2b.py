@@ -172,6 +172,41 @@ def timing():
         print(json.dumps(dict(case='outer timing', windows=B, advect_ms=timeit(lambda: eng.advect(st, nsteps=8, nwindows=B, out=(x, y))))), flush=True)
 
 
+def global_call():
+    # the reference's default global call: 2-degree winds -> 360x721 regrid -> T20 truncation -> cyclic integration -> FTLE
+    from lagrangiancoherence_b200.labelled import DataArray, Dataset
+    from lagrangiancoherence_b200.LCS.LCS import LCS
+    u, v, lat, lon = S.ideal_vortex(**S.vortex_config_subtropical)
+    t = (np.datetime64('2000-01-01T00') + np.arange(u.shape[0]) * np.timedelta64(6, 'h')).astype('datetime64[ns]')
+    c = {'time': t, 'latitude': lat, 'longitude': lon}
+    ds = Dataset({'u': DataArray(u, ('time', 'latitude', 'longitude'), c), 'v': DataArray(v, ('time', 'latitude', 'longitude'), c)})
+    lcs = LCS(timestep=-21600, timedim='time', SETTLS_order=4)
+    devnull = open(os.devnull, 'w')
+
+    def call():
+        so = sys.stdout
+        sys.stdout = devnull
+        try:
+            return lcs(ds, isglobal=True, verbose=False)
+        finally:
+            sys.stdout = so
+    for _ in range(3):
+        out = call()
+    ts = []
+    for _ in range(7):
+        torch.cuda.synchronize(); t0 = time.perf_counter(); call(); torch.cuda.synchronize(); ts.append((time.perf_counter() - t0) * 1e3)
+    print(json.dumps(dict(case='global default call (regrid + T20), 89x180 -> 360x721, nt=%d' % u.shape[0], ms_median=float(np.median(ts)),
+                          ms_min=float(np.min(ts)), checksum=float(np.nansum(out.values)))), flush=True)
+    pr = cProfile.Profile()
+    pr.enable()
+    for _ in range(5):
+        call()
+    pr.disable()
+    s_ = io.StringIO()
+    pstats.Stats(pr, stream=s_).sort_stats('cumulative').print_stats(22)
+    print(s_.getvalue()[:5000])
+
+
 def profile():
     from lagrangiancoherence_b200.labelled import DataArray
     from lagrangiancoherence_b200.LCS.LCS import LCS
