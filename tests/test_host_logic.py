@@ -219,3 +219,22 @@ def test_regrid_axis_plan_reproduces_interp1d_and_nearest():
     assert lats.size == 360 and lons.size == 721 and lats[0] == -89.75 and lons[-1] == 179.5     # LCS.py:106-107
     with pytest.raises(ValueError):
         axis_plan([0.0, 0.0, 1.0], [0.5])
+
+
+def test_device_array_stays_lazy_until_values_are_asked_for():
+    """labelled.DeviceArray (the winds of the global path after the device regrid / truncation): the operations LCS.__call__
+    and propagate() apply -- sortby on sorted coordinates, transpose to the order it already has, coordinate lookup, isel of
+    one level -- must not download the series; everything else falls back to a host DataArray."""
+    import torch
+    from lagrangiancoherence_b200.labelled import DeviceArray, DataArray, coord_values
+    t = torch.arange(24, dtype=torch.float64).reshape(2, 3, 4)
+    d = DeviceArray(t, ('time', 'latitude', 'longitude'), {'time': np.arange(2), 'latitude': np.arange(3.0), 'longitude': np.arange(4.0)})
+    assert d.shape == (2, 3, 4) and d.dtype == np.float64 and d.size == 24 and d.ndim == 3
+    assert d.sortby('longitude').sortby('latitude') is d and d.transpose('time', 'latitude', 'longitude') is d
+    assert np.array_equal(coord_values(d, 'latitude'), np.arange(3.0))
+    lvl = d.isel({'time': 0})
+    assert isinstance(lvl, DataArray) and lvl.dims == ('latitude', 'longitude') and np.array_equal(lvl.values, t[0].numpy())
+    assert d._host_values is None                                   # nothing above touched the whole series
+    assert d.transpose('latitude', 'time', 'longitude').shape == (3, 2, 4)
+    assert np.array_equal(d.values, t.numpy()) and np.array_equal((d * 2).values, 2 * t.numpy())
+    assert np.array_equal(d.copy().values, t.numpy()) and np.array_equal(d.isel(latitude=slice(1, 3)).values, t.numpy()[:, 1:3])
