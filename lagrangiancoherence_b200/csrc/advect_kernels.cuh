@@ -402,9 +402,9 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Outer-product clamp, group-persistent form (the default).  The cluster kernel above keeps one window per CTA
-// (or per hardware cluster) resident, so 296 windows x 3 MB of position / Euler-sample state are in flight at once
-// and every sub-step streams it through DRAM (ncu, round 1: 241 GB per 1184 windows, 42 % of the DRAM bandwidth,
+// Outer-product clamp, group-persistent form (the default).  Round 1's cluster kernel kept one window per CTA
+// (or per hardware cluster) resident, so 296 windows x 3 MB of position / Euler-sample state were in flight at once
+// and every sub-step streamed it through DRAM (ncu, round 1: 241 GB per 1184 windows, 42 % of the DRAM bandwidth,
 // L2 hit rate 37 %).  Here the launch is ONE cooperative grid of `ncta` resident CTAs split into `ngroups` groups; a
 // group integrates one window at a time and draws the next one from a global counter, so only `ngroups` windows
 // are in flight and their state (ngroups x 3 MB at C2) stays in L2 -- or, STATE = 1, when a group is large enough that

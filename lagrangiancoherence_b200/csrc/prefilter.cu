@@ -9,9 +9,11 @@
 // sequential along a line; its closed form is a symmetric two-sided exponential
 //      c[i] = sum_k  h0 * z^|k| * s[mirror(i + k)],
 // and |z| <= 0.43, so truncating at |k| <= log(1e-18)/log|z| leaves a remainder far below one f64 ulp: every run of
-// outputs can start from truncated end sums.  iir_axis0_transpose_kernel gives each thread a run of KQ consecutive
-// outputs: the two one-sided sums at the run's ends by Horner over the mirror extension, the same one-pole
-// recursions scipy uses inside the run.  Both passes filter along axis 0 of their input with threads along axis 1
+// outputs can start from truncated end sums.  Two kernels, chosen by lcs_prefilter: iir_column_kernel (series: a thread
+// walks a whole column with the tiles it needs in registers, every input read once -- 66-70 % of the copy bandwidth) and
+// iir_axis0_transpose_kernel (single fields and the two-pole orders: each thread a run of KQ consecutive outputs, the two
+// one-sided sums at the run's ends by Horner over the mirror extension, the same one-pole recursions scipy uses inside
+// the run).  Both passes filter along axis 0 of their input with threads along axis 1
 // (coalesced) and write their result transposed, so two applications filter axis 0 (lat) then axis 1 (lon) --
 // scipy's order -- and restore the layout.  Agreement with scipy.ndimage.spline_filter is ~1e-15 of the field
 // magnitude (tests/test_gpu_engine.py), not bitwise: the summation order differs from the whole-line recursion.
