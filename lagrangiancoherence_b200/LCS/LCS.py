@@ -79,10 +79,23 @@ class LCS:
             s = int(10 * u0.size * u0.std())
             print('using s = ' + str(s / 1e6) + '1e6')
         verboseprint("*---- Parcel propagation ----*")
-        engine, out, Us, lat, lon, times = propagate(u, v, timestep, timedim, return_traj, self.SETTLS_order,
-                                                     traj_interp_order, cyclic_xboundary, xclamp, device, precision,
-                                                     resample=resample_plan_)
+        # Subdomain work skipping: the crop keeps rows [o0, o1) of the sorted grid and the y-stencil reaches
+        # two rows beyond them, so where particles are independent (pointwise clamp; the as-executed outer clamp couples all
+        # rows) and neither the departure points nor their Gaussian smoothing are asked for, only rows [o0-2, o1+2) are
+        # integrated.  The band is decided inside propagate(), on the sorted latitudes.
+        sub = self.subdomain if isinstance(self.subdomain, dict) else None
+        skip_ok = sub is not None and not (self.return_dpts or return_traj) and not isinstance(self.gauss_sigma, (float, int))
+
+        def band_of(lat_sorted):
+            keep = np.flatnonzero(_crop_index(lat_sorted, sub.get('latitude')))
+            if not keep.size:
+                return None
+            return max(0, int(keep[0]) - 2), min(lat_sorted.size, int(keep[-1]) + 3)
+        engine, out, Us, lat, lon, times, band = propagate(u, v, timestep, timedim, return_traj, self.SETTLS_order,
+                                                           traj_interp_order, cyclic_xboundary, xclamp, device, precision,
+                                                           resample=resample_plan_, rows=band_of if skip_ok else None)
         x_dep, y_dep = out[0], out[1]
+        in_row0 = band[0] if band is not None else 0
         verboseprint("*---- Computing deformation tensor ----*")
         xs, ys = x_dep, y_dep
         if isinstance(self.gauss_sigma, (float, int)):               # LCS.py:187-190 (inside flowmap_gradient upstream)
@@ -99,7 +112,7 @@ class LCS:
                 mask = np.outer(latkeep[out_rows[0]:out_rows[1]], lonkeep)
         verboseprint("*---- Computing eigenvalues ----*")
         engine.reset_status()
-        sigma = engine.epilogue(xs, ys, out_rows=out_rows, mask=mask)
+        sigma = engine.epilogue(xs, ys, out_rows=out_rows, mask=mask, in_row0=in_row0)
         engine.check_finite()                                        # ValueError on inf, as scipy.linalg.norm (LCS.py:154)
         sigma = sigma[0].cpu().numpy()
         verboseprint("*---- Done eigenvalues ----*")

@@ -37,9 +37,10 @@ def _cached_engine(lat, lon, timestep, SETTLS_order, interp_order, xmode, device
 
 
 def propagate(U, V, timestep, propdim, return_traj, SETTLS_order, interp_order, cyclic_xboundary,
-              xclamp=XCLAMP_DEFAULT, device='cuda:0', precision='f64', engine=None, resample=None):
+              xclamp=XCLAMP_DEFAULT, device='cuda:0', precision='f64', engine=None, resample=None, rows=None):
     """Shared by parcel_propagation and LCS.__call__: returns device tensors plus the metadata the
-    callers need to label them."""
+    callers need to label them.  ``rows(lat) -> (r0, r1) or None``: restrict the integration to a band of particle rows of
+    the SORTED grid (subdomain work skipping; only where particles are independent, i.e. not under the outer clamp)."""
     U, V = _sorted_winds(U, V, propdim)
     lat = coord_values(U, 'latitude')
     lon = coord_values(U, 'longitude')
@@ -58,8 +59,9 @@ def propagate(U, V, timestep, propdim, return_traj, SETTLS_order, interp_order, 
     # resample= (LCS.py:88-90) is applied on the device inside the staging: coarse levels are prefiltered once, winds and
     # coefficients are refined linearly (engine.stage)
     staged = engine.stage(uu, vv, resample=None if resample is None else tuple(resample[1:]))
-    out = engine.advect(staged, return_traj=return_traj)
-    return engine, out, U, lat, lon, times
+    band = rows(lat) if (rows is not None and xmode != 'outer') else None
+    out = engine.advect(staged, return_traj=return_traj, rows=band)
+    return engine, out, U, lat, lon, times, band
 
 
 def parcel_propagation(U, V, timestep=1, propdim='time', verbose=True, return_traj=False,
@@ -76,8 +78,8 @@ def parcel_propagation(U, V, timestep=1, propdim='time', verbose=True, return_tr
     or 'pointwise'), ``device``, ``precision`` ('f64' | 'f32' packed-wind storage).
     """
     verboseprint = print if verbose else (lambda *a, **k: None)
-    _, out, Us, lat, lon, times = propagate(U, V, timestep, propdim, return_traj, SETTLS_order, interp_order,
-                                            cyclic_xboundary, xclamp, device, precision)
+    _, out, Us, lat, lon, times, _ = propagate(U, V, timestep, propdim, return_traj, SETTLS_order, interp_order,
+                                               cyclic_xboundary, xclamp, device, precision)
     for t in times[:-1]:
         verboseprint(f'Propagating time {t}')                       # trajectory.py:81
     if return_traj:

@@ -73,6 +73,48 @@ def test_lcs_subdomain_crops_like_latlonsel(cuda_device):
     assert close_fraction(out.values[0], ref, FTLE_REL) >= 0.995
 
 
+@pytest.mark.parametrize('flip', [False, True])
+def test_subdomain_skips_rows_under_the_pointwise_clamp_without_changing_a_bit(cuda_device, flip, monkeypatch):
+    """with a subdomain and independent particles (xclamp='pointwise') only the kept rows +-2 are integrated
+    (the y-stencil's reach); the result must equal the crop of the full field bit for bit -- pole-row and one-sided-stencil
+    rules are keyed on global row indices.  Crops touching the first / last rows, descending input latitudes, and the
+    cases where skipping must NOT happen (departure points returned, Gaussian smoothing) included."""
+    from lagrangiancoherence_b200.LCS.LCS import LCS
+    from lagrangiancoherence_b200.engine import FtleEngine
+    du, dv, u, v, lat, lon, _ = winds(flip=flip)
+    full = LCS(timestep=-21600, SETTLS_order=4)(u=du, v=dv, verbose=False, xclamp='pointwise')
+    seen = []
+    orig = FtleEngine.advect
+
+    def spy(self, staged, *a, **k):
+        seen.append(k.get('rows'))
+        return orig(self, staged, *a, **k)
+    monkeypatch.setattr(FtleEngine, 'advect', spy)
+    for sub in ({'latitude': slice(-20, 0), 'longitude': slice(-70, -40)}, {'latitude': slice(-31, -25)}, {'latitude': slice(5, 11)},
+                {'longitude': slice(-60, -50)}):
+        out = LCS(timestep=-21600, SETTLS_order=4, subdomain=sub)(u=du, v=dv, verbose=False, xclamp='pointwise')
+        keep_lat = _keep(lat, sub.get('latitude'))
+        keep_lon = _keep(lon, sub.get('longitude'))
+        assert np.array_equal(out.coords['latitude'], lat[keep_lat]) and np.array_equal(out.coords['longitude'], lon[keep_lon])
+        assert np.array_equal(out.values[0], full.values[0][keep_lat][:, keep_lon], equal_nan=True), sub
+        r = np.flatnonzero(keep_lat)
+        assert seen[-1] == (max(0, r[0] - 2), min(lat.size, r[-1] + 3))
+    sub = {'latitude': slice(-20, 0)}
+    res = LCS(timestep=-21600, SETTLS_order=4, subdomain=sub, return_dpts=True)(u=du, v=dv, verbose=False, xclamp='pointwise')
+    assert seen[-1] is None and res[1].shape == (lat.size, lon.size)                 # departure points asked for: no skipping
+    LCS(timestep=-21600, SETTLS_order=4, subdomain=sub, gauss_sigma=1.0)(u=du, v=dv, verbose=False, xclamp='pointwise')
+    assert seen[-1] is None                                                          # smoothing reaches beyond the band
+    LCS(timestep=-21600, SETTLS_order=4, subdomain=sub)(u=du, v=dv, verbose=False)   # as-executed outer clamp couples all rows
+    assert seen[-1] is None
+
+
+def _keep(coord, sl):
+    k = np.ones(coord.shape, bool)
+    if sl is not None:
+        k &= (coord > sl.start) & (coord < sl.stop)
+    return k
+
+
 def test_lcs_asserts_on_bad_dims(cuda_device):
     from lagrangiancoherence_b200.LCS.LCS import LCS
     du, dv, *_ = winds()
