@@ -239,7 +239,7 @@ extern "C" int lcs_ftle_epilogue(const double* x_dep, const double* y_dep, int n
     // enough warps to cover the machine without excessive halo recomputation (4 extra rows per chunk)
     int rpc = lcs_env_int("LCS_EPILOGUE_ROWS", 0);
     if (rpc <= 0) {
-        rpc = 16;
+        rpc = 64;                                   // 4 halo rows per chunk: 6 % of recomputed sincos at 64 rows, 25 % at 16
         while (rpc > 4 && (long long)nfields * P.nstrips * ((nrow_out + rpc - 1) / rpc) < 148LL * 16) rpc >>= 1;
     }
     P.rows_per_chunk = rpc;
