@@ -54,7 +54,10 @@ def chunk_schedule(count, chunk, ramp=False):
     Returns ``[(first, n), ...]`` covering ``0 .. count``."""
     if count <= 3 * chunk:
         return chunk_starts(0, count, chunk)
-    head = [chunk // 2, chunk] if ramp and chunk >= 2 and count > 6 * chunk else [chunk]
+    if ramp and chunk >= 8 and count > 6 * chunk:
+        head = [chunk // 6, chunk // 2, chunk] if int(ramp) >= 2 else [chunk // 2, chunk]
+    else:
+        head = [chunk]
     rem = count - 2 * sum(head)
     mid = []
     while rem > 2 * chunk:
@@ -130,7 +133,7 @@ def rolling_ftle(u, v, lat, lon, window_levels, timestep, SETTLS_order=4, interp
     sigma = None if to_host else torch.empty((count, lat.size, lon.size), dtype=torch.float64, device=dev)
     if count == 0:                                       # an empty shard (more ranks than start times): nothing to integrate
         return sigma if return_device else (out.numpy() if own_out else out)
-    chunks = chunk_starts(0, count, chunk) if on_device else chunk_schedule(count, chunk, ramp=os.environ.get('LCS_ROLLING_RAMP', '1') != '0')
+    chunks = chunk_starts(0, count, chunk) if on_device else chunk_schedule(count, chunk, ramp=int(os.environ.get('LCS_ROLLING_RAMP', '1')))
     engine.reset_status()                                # chunks OR into one flag, checked once after the loop
     with torch.cuda.device(dev):
         main = torch.cuda.current_stream(dev)
