@@ -573,7 +573,7 @@ def run_b200(args):
             'hbm': hbm,
         },
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:          # the CPU leg is timed at N = 1 only (rank 0 is the only rank there)
         cores = os.cpu_count() or 1
         lat2, lon2, nt2, _, desc2 = workload(args.workload)
         nwin = cores if args.workload == 'C3' else 4 * cores          # ~10 s of wall on the 16 cores of the GPU box
