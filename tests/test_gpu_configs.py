@@ -54,6 +54,38 @@ def test_c3_shape_short_window_against_oracle_and_row_bands(cuda_device):
         assert torch.equal(torch.cat(bands, dim=1), full)
 
 
+@pytest.mark.parametrize('cfg', ['C3 full length', 'C2 batch'])
+def test_full_size_outer_clamp_group_kernel_equals_phased_launches(cuda_device, cfg, monkeypatch):
+    """BASELINE sizes where the oracle would take minutes: the as-executed outer clamp of configs[2] at FULL size
+    (721 x 1440 particles, hourly winds, 72 h = 360 sub-steps, the whole machine on one window) and of the bench step's
+    shape (C2, a wave of 296 windows, one CTA each) -- the persistent kernel (group barriers, state in registers or in
+    global memory, candidate lists) against the phased launches (kernel boundaries as barriers: an independent
+    implementation of the same clamp), bit for bit, and run twice for determinism (candidate lists are filled by
+    atomics in arbitrary order; the result must not depend on it)."""
+    from lagrangiancoherence_b200.engine import FtleEngine
+    if cfg == 'C3 full length':
+        (lat, lon), nt, dt, nw = S.grid_c3(), 73, -3600, 1
+    else:
+        (lat, lon), nt, dt, nw = S.grid_c2(), 9, -21600, 296
+    u, v = S.era5_like_winds(lat, lon, nt - 1 + nw, noise=0.0)
+    eng = FtleEngine(lat, lon, dt, SETTLS_order=4, xmode='outer', device=cuda_device)
+    st = eng.stage(torch.from_numpy(u).to(cuda_device), torch.from_numpy(v).to(cuda_device))
+    del u, v
+    monkeypatch.setenv('LCS_OUTER_MODE', '0')
+    a = eng.advect(st, nsteps=nt - 1, nwindows=nw)
+    b = eng.advect(st, nsteps=nt - 1, nwindows=nw)
+    eng.check_finite()
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    monkeypatch.setenv('LCS_OUTER_MODE', '1')
+    eng._ws = None
+    c = eng.advect(st, nsteps=nt - 1, nwindows=nw)
+    assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+    lo, hi = float(lon.min()), float(lon.max())
+    assert float(a[0].min()) >= lo and float(a[0].max()) <= hi and bool(torch.isfinite(a[1]).all())
+    sig = eng.epilogue(a[0], a[1])
+    assert bool(torch.isfinite(sig[sig == sig]).all())
+
+
 def test_c4_rolling_equals_independent_windows(cuda_device):
     """configs[3]: every start time of a rolling series equals a stand-alone call on its own window, bit for bit
     (each level is prefiltered once for all windows that use it)."""
